@@ -1,0 +1,123 @@
+// Shared helpers for the deeplio_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/deeplio_b200.h"
+
+namespace dlio {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define DLIO_CHECK_ARG(cond, ...)            \
+    do {                                     \
+        if (!(cond)) {                       \
+            dlio::set_error(__VA_ARGS__);    \
+            return DLIO_ERR_INVALID;         \
+        }                                    \
+    } while (0)
+
+#define DLIO_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            dlio::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return DLIO_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define DLIO_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        dlio::count_launch();                                                             \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            dlio::set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return DLIO_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+// geometry of a padded NHWC tensor
+struct Geo {
+    int n, h, w, c, ph, pw;
+    int hp, wp;  // h + 2ph, w + 2pw
+    __host__ __device__ Geo() {}
+    __host__ __device__ Geo(const dlio_tensor4 &t)
+        : n(t.n), h(t.h), w(t.w), c(t.c), ph(t.ph), pw(t.pw), hp(t.h + 2 * t.ph), wp(t.w + 2 * t.pw) {}
+    // element offset of logical (n, y, x), channel 0
+    __host__ __device__ __forceinline__ size_t off(int in, int y, int x) const {
+        return (((size_t)in * hp + (y + ph)) * wp + (x + pw)) * (size_t)c;
+    }
+    __host__ __device__ size_t numel() const { return (size_t)n * hp * wp * c; }
+    __host__ __device__ size_t pixels() const { return (size_t)n * h * w; }
+    __host__ __device__ size_t padded_pixels() const { return (size_t)n * hp * wp; }
+};
+
+inline bool valid_t4(const dlio_tensor4 &t) {
+    return t.n > 0 && t.h > 0 && t.w > 0 && t.c > 0 && t.ph >= 0 && t.pw >= 0;
+}
+
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+// split v = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits zero)
+__device__ __forceinline__ void tf32_split(float v, float &hi, float &lo) {
+    hi = tf32_rna(v);
+    lo = v - hi;  // exact in fp32; the tensor core reads its top 19 bits
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 ld4_sum(const float *hi, const float *lo, size_t off) {
+    float4 v = ld4(hi + off);
+    if (lo) v = add4(v, ld4(lo + off));
+    return v;
+}
+__device__ __forceinline__ void st4_split(float *hi, float *lo, size_t off, const float4 &v) {
+    if (lo) {
+        float4 h, l;
+        tf32_split(v.x, h.x, l.x);
+        tf32_split(v.y, h.y, l.y);
+        tf32_split(v.z, h.z, l.z);
+        tf32_split(v.w, h.w, l.w);
+        st4(hi + off, h);
+        st4(lo + off, l);
+    } else {
+        st4(hi + off, v);
+    }
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+        case DLIO_ACT_RELU: return v > 0.f ? v : 0.f;
+        case DLIO_ACT_LEAKY: return v > 0.f ? v : 0.01f * v;
+        case DLIO_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case DLIO_ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+// derivative expressed through the activation OUTPUT y
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    switch (act) {
+        case DLIO_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case DLIO_ACT_LEAKY: return y > 0.f ? 1.f : 0.01f;
+        case DLIO_ACT_SIGMOID: return y * (1.f - y);
+        case DLIO_ACT_TANH: return 1.f - y * y;
+        default: return 1.f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dlio

@@ -1,0 +1,682 @@
+// HBM-bound passes around the convolutions: input packing, batch-norm statistics -> scale/shift,
+// fused BN-apply (+residual)(+ReLU)(+3x3 max-pool) consumer pass and its two-pass backward, spatial
+// reductions (global average pool, SE squeeze), SE channel scaling, small element-wise helpers.
+//
+// All activations are padded NHWC fp32 (see deeplio_b200.h).  Threads are mapped channel-fastest with one
+// float4 (4 channels) per thread, so a warp reads / writes 512 contiguous bytes per pixel group.
+// Kernels that reduce over pixels keep a FIXED channel group per thread (block size is a multiple of
+// the number of channel groups), accumulate in registers, combine through shared-memory atomics and
+// finish with one fp64 global atomic per channel per block.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace dlio {
+
+constexpr int MAX_C = 1024;  // channel limit of the reducing kernels (largest on the path: FlowNet conv6)
+
+static inline int block_for_cg(int cg) { return cg * (256 / cg > 0 ? 256 / cg : 1); }
+static inline int grid_for(long long total, int block, int per_sm = 8) {
+    long long g = (total + block - 1) / block;
+    long long cap = 148LL * per_sm;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ float4 fma4(const float4 &a, const float4 &b, const float4 &c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 mul4(const float4 &a, const float4 &b) {
+    return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ float4 relu4(const float4 &a) {
+    return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+
+// ------------------------------------------------------------------ input packing
+__global__ void pack_input_kernel(const float *__restrict__ src, long long sn, long long st, long long sc, int T,
+                                  int C, Geo d, float *__restrict__ dst) {
+    long long total = (long long)d.n * d.hp * d.wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int xx = (int)(i % d.wp);
+        long long t = i / d.wp;
+        int yy = (int)(t % d.hp);
+        int n = (int)(t / d.hp);
+        int h = yy - d.ph, w = xx - d.pw;
+        float *o = dst + (size_t)i * d.c;
+        bool in = h >= 0 && h < d.h && w >= 0 && w < d.w;
+        for (int c0 = 0; c0 < d.c; c0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int c = c0 + j;
+                float x = 0.f;
+                if (in && c < T * C) {
+                    int tt = c / C, cc = c - tt * C;
+                    x = src[(size_t)n * sn + (size_t)tt * st + (size_t)cc * sc + (size_t)h * d.w + w];
+                }
+                v[j] = x;
+            }
+            st4(o + c0, make_float4(v[0], v[1], v[2], v[3]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ BN statistics -> scale / shift
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, double count, int c,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float *running_mean, float *running_var, float momentum, float eps,
+                                   int use_running, float *mean, float *invstd, float *scale, float *shift) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float m, is;
+    if (use_running) {
+        m = running_mean[i];
+        is = 1.f / sqrtf(running_var[i] + eps);
+    } else {
+        double mu = stats[i] / count;
+        double var = stats[c + i] / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        m = (float)mu;
+        is = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * m;
+            running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unb;
+        }
+    }
+    float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+    mean[i] = m;
+    invstd[i] = is;
+    scale[i] = g * is;
+    shift[i] = b - m * g * is;
+}
+
+// ------------------------------------------------------------------ fused BN-apply / residual / ReLU / max-pool
+struct BnPool {
+    Geo y, out, res;
+    const float *yp, *scale, *shift, *resp;
+    int res_mode;  // 0 none, 1 added before the activation, 2 added after it
+    int relu, pk, sh, sw, c_off, cg;
+    float *out_hi, *out_lo;
+    uint8_t *idx;
+};
+
+__device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, int w, int c, const float4 &sc,
+                                               const float4 &sf) {
+    float4 v = ld4(a.yp + a.y.off(n, h, w) + c);
+    if (a.scale) v = fma4(sc, v, sf);
+    if (a.res_mode == 1) v = add4(v, ld4(a.resp + a.res.off(n, h, w) + a.c_off + c));
+    if (a.relu) v = relu4(v);
+    if (a.res_mode == 2) v = add4(v, ld4(a.resp + a.res.off(n, h, w) + a.c_off + c));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
+    const long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % a.cg) * 4;
+        long long pix = i / a.cg;
+        int xx = (int)(pix % a.out.wp);
+        long long t = pix / a.out.wp;
+        int yy = (int)(t % a.out.hp);
+        int n = (int)(t / a.out.hp);
+        size_t o = (size_t)pix * a.out.c + a.c_off + c;
+        int ho = yy - a.out.ph, wo = xx - a.out.pw;
+        if (ho < 0 || ho >= a.out.h || wo < 0 || wo >= a.out.w) {
+            st4(a.out_hi + o, f4(0.f));
+            if (a.out_lo) st4(a.out_lo + o, f4(0.f));
+            continue;
+        }
+        float4 sc = f4(1.f), sf = f4(0.f);
+        if (a.scale) {
+            sc = ld4(a.scale + c);
+            sf = ld4(a.shift + c);
+        }
+        float4 best;
+        if (a.pk == 1) {
+            best = bnpool_value(a, n, ho, wo, c, sc, sf);
+        } else {
+            best = f4(-FLT_MAX);
+            uchar4 bi = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                int h = ho * a.sh - 1 + dy;
+                if (h < 0 || h >= a.y.h) continue;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    int w = wo * a.sw - 1 + dx;
+                    if (w < 0 || w >= a.y.w) continue;
+                    float4 v = bnpool_value(a, n, h, w, c, sc, sf);
+                    unsigned char r = (unsigned char)(dy * 3 + dx);
+                    if (v.x > best.x) { best.x = v.x; bi.x = r; }
+                    if (v.y > best.y) { best.y = v.y; bi.y = r; }
+                    if (v.z > best.z) { best.z = v.z; bi.z = r; }
+                    if (v.w > best.w) { best.w = v.w; bi.w = r; }
+                }
+            }
+            if (a.idx)
+                *reinterpret_cast<uchar4 *>(a.idx + (((size_t)n * a.out.h + ho) * a.out.w + wo) * a.y.c + c) = bi;
+        }
+        st4_split(a.out_hi, a.out_lo, o, best);
+    }
+}
+
+// backward pass 1: dz (gradient at the BN output position, after un-pooling and the ReLU mask) + sums
+struct BnBwd {
+    Geo y, res, dout;
+    const float *yp, *scale, *shift, *mean, *invstd, *resp, *doutp;
+    int res_mode, relu, pk, sh, sw, c_off, cg;
+    int grad_src, ld_dout;
+    int pooled_h, pooled_w;
+    const uint8_t *idx;
+    float *dz;
+    float *dres;
+    int dres_c, dres_acc;
+    double *sums;
+};
+
+__global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
+    __shared__ float red[2 * MAX_C];
+    const int C = a.cg * 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const long long total = (long long)a.y.n * a.y.h * a.y.w * a.cg;
+    const int c = (int)(threadIdx.x % a.cg) * 4;  // fixed per thread: blockDim.x % cg == 0
+    float4 sc = f4(1.f), sf = f4(0.f), mu = f4(0.f), is = f4(1.f);
+    if (a.scale) {
+        sc = ld4(a.scale + c);
+        sf = ld4(a.shift + c);
+    }
+    if (a.mean) {
+        mu = ld4(a.mean + c);
+        is = ld4(a.invstd + c);
+    }
+    const float inv_hw = 1.f / (float)(a.y.h * a.y.w);
+    float4 s1 = f4(0.f), s2 = f4(0.f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long pix = i / a.cg;
+        int w = (int)(pix % a.y.w);
+        long long t = pix / a.y.w;
+        int h = (int)(t % a.y.h);
+        int n = (int)(t / a.y.h);
+        float4 g = f4(0.f);
+        if (a.grad_src == DLIO_GRAD_AVG) {
+            g = ld4(a.doutp + (size_t)n * a.ld_dout + a.c_off + c);
+            g = make_float4(g.x * inv_hw, g.y * inv_hw, g.z * inv_hw, g.w * inv_hw);
+        } else if (a.pk == 1) {
+            g = ld4(a.doutp + a.dout.off(n, h, w) + a.c_off + c);
+        } else {
+            // windows (ho, wo) that contain (h, w): ho*sh - 1 <= h <= ho*sh + 1
+            int ho_lo = (h - 1 + a.sh - 1) / a.sh, ho_hi = (h + 1) / a.sh;
+            int wo_lo = (w - 1 + a.sw - 1) / a.sw, wo_hi = (w + 1) / a.sw;
+            if (h - 1 < 0) ho_lo = 0;
+            if (w - 1 < 0) wo_lo = 0;
+            if (ho_hi >= a.pooled_h) ho_hi = a.pooled_h - 1;
+            if (wo_hi >= a.pooled_w) wo_hi = a.pooled_w - 1;
+            for (int ho = ho_lo; ho <= ho_hi; ++ho)
+                for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                    unsigned char r = (unsigned char)((h - (ho * a.sh - 1)) * 3 + (w - (wo * a.sw - 1)));
+                    uchar4 bi = *reinterpret_cast<const uchar4 *>(
+                        a.idx + (((size_t)n * a.pooled_h + ho) * a.pooled_w + wo) * C + c);
+                    float4 d = ld4(a.doutp + a.dout.off(n, ho, wo) + a.c_off + c);
+                    if (bi.x == r) g.x += d.x;
+                    if (bi.y == r) g.y += d.y;
+                    if (bi.z == r) g.z += d.z;
+                    if (bi.w == r) g.w += d.w;
+                }
+        }
+        const size_t yo = a.y.off(n, h, w) + c;
+        float4 y = ld4(a.yp + yo);
+        size_t ro = (size_t)pix * a.dres_c + a.c_off + c;
+        if (a.res_mode == 2 && a.dres) st4(a.dres + ro, a.dres_acc ? add4(ld4(a.dres + ro), g) : g);
+        if (a.relu) {
+            float4 v = a.scale ? fma4(sc, y, sf) : y;
+            if (a.res_mode == 1) v = add4(v, ld4(a.resp + a.res.off(n, h, w) + a.c_off + c));
+            if (!(v.x > 0.f)) g.x = 0.f;
+            if (!(v.y > 0.f)) g.y = 0.f;
+            if (!(v.z > 0.f)) g.z = 0.f;
+            if (!(v.w > 0.f)) g.w = 0.f;
+        }
+        if (a.res_mode == 1 && a.dres) st4(a.dres + ro, a.dres_acc ? add4(ld4(a.dres + ro), g) : g);
+        st4(a.dz + (size_t)pix * C + c, g);
+        if (a.sums) {
+            float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
+            s1 = add4(s1, g);
+            s2 = fma4(g, yh, s2);
+        }
+    }
+    if (a.sums) {
+        atomicAdd(&red[c + 0], s1.x); atomicAdd(&red[c + 1], s1.y);
+        atomicAdd(&red[c + 2], s1.z); atomicAdd(&red[c + 3], s1.w);
+        atomicAdd(&red[C + c + 0], s2.x); atomicAdd(&red[C + c + 1], s2.y);
+        atomicAdd(&red[C + c + 2], s2.z); atomicAdd(&red[C + c + 3], s2.w);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + i, (double)red[i]);
+    }
+}
+
+// backward pass 2: dy = scale * (dz - mean(dz) - yhat * mean(dz * yhat)) [* (y > 0)]
+struct BnApply {
+    Geo y, dy;
+    const float *yp, *dz, *scale, *mean, *invstd;
+    const double *sums;
+    double count;
+    int pre_relu, batch_stats, cg;
+    float *dy_hi, *dy_lo, *dgamma, *dbeta;
+    double *dbias;
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
+    __shared__ float red[MAX_C];
+    const int C = a.cg * 4;
+    if (a.dbias) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+        __syncthreads();
+    }
+    const int c = (int)(threadIdx.x % a.cg) * 4;
+    float4 sc = f4(1.f), mu = f4(0.f), is = f4(1.f), m1 = f4(0.f), m2 = f4(0.f);
+    if (a.scale) sc = ld4(a.scale + c);
+    if (a.mean) {
+        mu = ld4(a.mean + c);
+        is = ld4(a.invstd + c);
+    }
+    if (a.sums && a.batch_stats) {
+        m1 = make_float4((float)(a.sums[c] / a.count), (float)(a.sums[c + 1] / a.count),
+                         (float)(a.sums[c + 2] / a.count), (float)(a.sums[c + 3] / a.count));
+        m2 = make_float4((float)(a.sums[C + c] / a.count), (float)(a.sums[C + c + 1] / a.count),
+                         (float)(a.sums[C + c + 2] / a.count), (float)(a.sums[C + c + 3] / a.count));
+    }
+    if (blockIdx.x == 0 && a.sums && threadIdx.x < a.cg) {
+        // parameter gradients: dgamma = sum dz * yhat, dbeta = sum dz
+        int cc = threadIdx.x * 4;
+        for (int j = 0; j < 4; ++j) {
+            if (a.dbeta) a.dbeta[cc + j] = (float)a.sums[cc + j];
+            if (a.dgamma) a.dgamma[cc + j] = (float)a.sums[C + cc + j];
+        }
+    }
+    float4 sb = f4(0.f);
+    const long long total = (long long)a.dy.n * a.dy.hp * a.dy.wp * a.cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long pix = i / a.cg;
+        int xx = (int)(pix % a.dy.wp);
+        long long t = pix / a.dy.wp;
+        int yy = (int)(t % a.dy.hp);
+        int n = (int)(t / a.dy.hp);
+        int h = yy - a.dy.ph, w = xx - a.dy.pw;
+        size_t o = (size_t)pix * C + c;
+        if (h < 0 || h >= a.dy.h || w < 0 || w >= a.dy.w) {
+            st4(a.dy_hi + o, f4(0.f));
+            if (a.dy_lo) st4(a.dy_lo + o, f4(0.f));
+            continue;
+        }
+        float4 y = ld4(a.yp + a.y.off(n, h, w) + c);
+        float4 dz = ld4(a.dz + (((size_t)n * a.y.h + h) * a.y.w + w) * C + c);
+        float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
+        float4 d = make_float4(sc.x * (dz.x - m1.x - yh.x * m2.x), sc.y * (dz.y - m1.y - yh.y * m2.y),
+                               sc.z * (dz.z - m1.z - yh.z * m2.z), sc.w * (dz.w - m1.w - yh.w * m2.w));
+        if (a.pre_relu) {
+            if (!(y.x > 0.f)) d.x = 0.f;
+            if (!(y.y > 0.f)) d.y = 0.f;
+            if (!(y.z > 0.f)) d.z = 0.f;
+            if (!(y.w > 0.f)) d.w = 0.f;
+        }
+        st4_split(a.dy_hi, a.dy_lo, o, d);
+        sb = add4(sb, d);
+    }
+    if (a.dbias) {
+        atomicAdd(&red[c + 0], sb.x); atomicAdd(&red[c + 1], sb.y);
+        atomicAdd(&red[c + 2], sb.z); atomicAdd(&red[c + 3], sb.w);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(a.dbias + i, (double)red[i]);
+    }
+}
+
+__global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
+// ------------------------------------------------------------------ spatial reductions
+// mode 0: out[n, c_off + c] (+)= inv * sum_hw act(scale * x + shift)
+// mode 1: out[n, c_off + c] (+)= sum_hw x * other          (SE gate gradient)
+struct SpatialRed {
+    Geo x, other;
+    const float *xp, *otherp, *scale, *shift;
+    int relu, mode, cg, ld_out, c_off, use_atomic;
+    float inv;
+    float *out;
+};
+
+__global__ void __launch_bounds__(256) spatial_reduce_kernel(SpatialRed a) {
+    __shared__ float red[MAX_C];
+    const int C = a.cg * 4;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int c = (int)(threadIdx.x % a.cg) * 4;
+    const int row = threadIdx.x / a.cg, rows = blockDim.x / a.cg;
+    float4 sc = f4(1.f), sf = f4(0.f);
+    if (a.scale) {
+        sc = ld4(a.scale + c);
+        sf = ld4(a.shift + c);
+    }
+    float4 s = f4(0.f);
+    const int hw = a.x.h * a.x.w;
+    for (int p = blockIdx.x * rows + row; p < hw; p += gridDim.x * rows) {
+        int h = p / a.x.w, w = p - h * a.x.w;
+        float4 v = ld4(a.xp + a.x.off(n, h, w) + c);
+        if (a.mode == 0) {
+            if (a.scale) v = fma4(sc, v, sf);
+            if (a.relu) v = relu4(v);
+            s = add4(s, v);
+        } else {
+            s = fma4(v, ld4(a.otherp + a.other.off(n, h, w) + c), s);
+        }
+    }
+    atomicAdd(&red[c + 0], s.x); atomicAdd(&red[c + 1], s.y);
+    atomicAdd(&red[c + 2], s.z); atomicAdd(&red[c + 3], s.w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float *o = a.out + (size_t)n * a.ld_out + a.c_off + i;
+        if (a.use_atomic) atomicAdd(o, red[i] * a.inv);
+        else *o = red[i] * a.inv;
+    }
+}
+
+__global__ void zero_strided_kernel(float *p, int rows, int cols, int ld) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) p[(size_t)(i / cols) * ld + (i % cols)] = 0.f;
+}
+
+// ------------------------------------------------------------------ SE channel scaling
+__global__ void __launch_bounds__(256) channel_scale_fwd_kernel(Geo x, const float *__restrict__ xp,
+                                                                const float *__restrict__ gate, Geo o,
+                                                                float *out_hi, float *out_lo, int cg) {
+    const long long total = (long long)o.n * o.hp * o.wp * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cg) * 4;
+        long long pix = i / cg;
+        int xx = (int)(pix % o.wp);
+        long long t = pix / o.wp;
+        int yy = (int)(t % o.hp);
+        int n = (int)(t / o.hp);
+        int h = yy - o.ph, w = xx - o.pw;
+        size_t oo = (size_t)pix * o.c + c;
+        if (h < 0 || h >= o.h || w < 0 || w >= o.w) {
+            st4(out_hi + oo, f4(0.f));
+            if (out_lo) st4(out_lo + oo, f4(0.f));
+            continue;
+        }
+        float4 v = mul4(ld4(xp + x.off(n, h, w) + c), ld4(gate + (size_t)n * x.c + c));
+        st4_split(out_hi, out_lo, oo, v);
+    }
+}
+
+// dx[n,h,w,c] = dout * gate[n,c] + dmean[n,c] * inv   (dx, dout unpadded)
+__global__ void __launch_bounds__(256) channel_scale_bwd_kernel(const float *__restrict__ dout,
+                                                                const float *__restrict__ gate,
+                                                                const float *__restrict__ dmean, float inv,
+                                                                float *__restrict__ dx, int n, int hw, int cg) {
+    const long long total = (long long)n * hw * cg;
+    const int C = cg * 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cg) * 4;
+        long long pix = i / cg;
+        int in = (int)(pix / hw);
+        float4 g = ld4(gate + (size_t)in * C + c);
+        float4 v = mul4(ld4(dout + (size_t)pix * C + c), g);
+        if (dmean) {
+            float4 m = ld4(dmean + (size_t)in * C + c);
+            v = make_float4(fmaf(m.x, inv, v.x), fmaf(m.y, inv, v.y), fmaf(m.z, inv, v.z), fmaf(m.w, inv, v.w));
+        }
+        st4(dx + (size_t)pix * C + c, v);
+    }
+}
+
+// ------------------------------------------------------------------ element-wise helpers
+__global__ void axpby_kernel(const float *__restrict__ a, float alpha, const float *__restrict__ b, float beta,
+                             float *out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = n >> 2;
+    for (long long q = i; q < n4; q += stride) {
+        float4 x = ld4(a + q * 4), y = ld4(b + q * 4);
+        st4(out + q * 4, make_float4(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y, alpha * x.z + beta * y.z,
+                                     alpha * x.w + beta * y.w));
+    }
+    for (long long q = n4 * 4 + i; q < n; q += stride) out[q] = alpha * a[q] + beta * b[q];
+}
+// out[a, c] = sum_t x[a, t, c]
+__global__ void sum_mid_kernel(const float *__restrict__ x, float *__restrict__ out, long long A, int T, int C) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= A * C) return;
+    long long a = i / C;
+    int c = (int)(i - a * C);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += x[((size_t)a * T + t) * C + c];
+    out[i] = s;
+}
+__global__ void mul_kernel(const float *__restrict__ a, const float *__restrict__ b, float *out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = a[i] * b[i];
+}
+// counter-based keep mask: splitmix64(seed + i) -> uniform [0,1); mask = keep ? 1/(1-p) : 0
+__global__ void dropout_mask_kernel(float *mask, long long n, float p, unsigned long long seed) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float keep_scale = 1.f / (1.f - p);
+    for (; i < n; i += stride) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        float u = (float)(z >> 40) * (1.f / 16777216.f);
+        mask[i] = u >= p ? keep_scale : 0.f;
+    }
+}
+
+}  // namespace dlio
+
+using namespace dlio;
+
+extern "C" int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
+                               dlio_tensor4 dst, float *dst_ptr, void *stream) {
+    DLIO_CHECK_ARG(src && dst_ptr && valid_t4(dst) && dst.c % 4 == 0 && dst.c >= T * C, "pack_input: bad argument");
+    Geo d(dst);
+    long long total = (long long)d.n * d.hp * d.wp;
+    pack_input_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, sn, st, sc, T, C, d, dst_ptr);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma,
+                                const float *beta, float *running_mean, float *running_var, float momentum,
+                                float eps, int use_running, float *mean, float *invstd, float *scale,
+                                float *shift, void *stream) {
+    DLIO_CHECK_ARG(c > 0 && mean && invstd && scale && shift, "bn_finalize: bad argument");
+    DLIO_CHECK_ARG(use_running ? (running_mean && running_var) : (stats && count > 0), "bn_finalize: missing statistics");
+    bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(
+        stats, (double)count, c, gamma, beta, running_mean, running_var, momentum, eps, use_running, mean, invstd,
+        scale, shift);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+static int check_cg(int c, const char *who) {
+    DLIO_CHECK_ARG(c % 4 == 0 && c > 0 && c <= MAX_C, "%s: channel count %d must be a multiple of 4 and <= %d", who, c, MAX_C);
+    return DLIO_OK;
+}
+
+extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
+                                    dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
+                                    float *out_hi, float *out_lo, uint8_t *pool_idx, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(out) && y_ptr && out_hi, "bn_act_pool_fwd: bad argument");
+    int rc = check_cg(y.c, "bn_act_pool_fwd");
+    if (rc) return rc;
+    DLIO_CHECK_ARG(p.c_off % 4 == 0 && p.c_off + y.c <= out.c && out.c % 4 == 0, "bn_act_pool_fwd: bad channel offset");
+    DLIO_CHECK_ARG(p.pool_k == 1 || p.pool_k == 3, "bn_act_pool_fwd: pool_k must be 1 or 3");
+    DLIO_CHECK_ARG(p.pool_k == 3 || (y.h == out.h && y.w == out.w), "bn_act_pool_fwd: extent mismatch");
+    DLIO_CHECK_ARG(p.res_mode == 0 || (res_ptr && res.h == y.h && res.w == y.w && res.c >= p.c_off + y.c),
+                   "bn_act_pool_fwd: bad residual");
+    DLIO_CHECK_ARG((scale == nullptr) == (shift == nullptr), "bn_act_pool_fwd: scale/shift");
+    BnPool a;
+    a.y = Geo(y); a.out = Geo(out); a.res = p.res_mode ? Geo(res) : Geo(y);
+    a.yp = y_ptr; a.scale = scale; a.shift = shift; a.resp = res_ptr;
+    a.res_mode = p.res_mode; a.relu = p.relu; a.pk = p.pool_k; a.sh = p.pool_sh; a.sw = p.pool_sw;
+    a.c_off = p.c_off; a.cg = y.c / 4;
+    a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx;
+    long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
+    bn_act_pool_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(a);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float *scale,
+                                           const float *shift, const float *mean, const float *invstd,
+                                           dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, int grad_src,
+                                           dlio_tensor4 dout, const float *dout_ptr, int ld_dout,
+                                           const uint8_t *pool_idx, float *dz, float *dres, int dres_c,
+                                           int dres_accumulate, double *sums, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(y) && y_ptr && dout_ptr && dz, "bn_act_pool_bwd_reduce: bad argument");
+    int rc = check_cg(y.c, "bn_act_pool_bwd_reduce");
+    if (rc) return rc;
+    DLIO_CHECK_ARG(grad_src == DLIO_GRAD_AVG || valid_t4(dout), "bn_act_pool_bwd_reduce: bad dout");
+    DLIO_CHECK_ARG(p.pool_k == 1 || (p.pool_k == 3 && pool_idx), "bn_act_pool_bwd_reduce: pooling needs pool_idx");
+    DLIO_CHECK_ARG(p.res_mode != 1 || res_ptr, "bn_act_pool_bwd_reduce: residual pointer missing");
+    BnBwd a;
+    a.y = Geo(y); a.res = p.res_mode == 1 ? Geo(res) : Geo(y); a.dout = grad_src == DLIO_GRAD_AVG ? Geo(y) : Geo(dout);
+    a.yp = y_ptr; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.resp = res_ptr;
+    a.doutp = dout_ptr;
+    a.res_mode = p.res_mode; a.relu = p.relu; a.pk = grad_src == DLIO_GRAD_AVG ? 1 : p.pool_k;
+    a.sh = p.pool_sh; a.sw = p.pool_sw; a.c_off = p.c_off; a.cg = y.c / 4;
+    a.grad_src = grad_src; a.ld_dout = ld_dout;
+    a.pooled_h = dout.h; a.pooled_w = dout.w;
+    a.idx = pool_idx; a.dz = dz; a.dres = dres; a.dres_c = dres_c; a.dres_acc = dres_accumulate; a.sums = sums;
+    int block = block_for_cg(a.cg);
+    long long total = (long long)y.n * y.h * y.w * a.cg;
+    bn_act_pool_bwd_reduce_kernel<<<grid_for(total, block, 8), block, 0, (cudaStream_t)stream>>>(a);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
+                                 long long count, const float *scale, const float *mean, const float *invstd,
+                                 int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
+                                 float *dgamma, float *dbeta, double *dbias_sums, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && dz && dy_hi, "bn_bwd_apply: bad argument");
+    DLIO_CHECK_ARG(dy_t.n == y.n && dy_t.h == y.h && dy_t.w == y.w && dy_t.c == y.c, "bn_bwd_apply: dy geometry");
+    int rc = check_cg(y.c, "bn_bwd_apply");
+    if (rc) return rc;
+    BnApply a;
+    a.y = Geo(y); a.dy = Geo(dy_t);
+    a.yp = y_ptr; a.dz = dz; a.scale = scale; a.mean = mean; a.invstd = invstd; a.sums = sums;
+    a.count = (double)count; a.pre_relu = pre_relu; a.batch_stats = batch_stats; a.cg = y.c / 4;
+    a.dy_hi = dy_hi; a.dy_lo = dy_lo; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias_sums;
+    int block = block_for_cg(a.cg);
+    long long total = (long long)a.dy.n * a.dy.hp * a.dy.wp * a.cg;
+    bn_bwd_apply_kernel<<<grid_for(total, block, 8), block, 0, (cudaStream_t)stream>>>(a);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_f64_to_f32(const double *src, float *dst, int n, void *stream) {
+    DLIO_CHECK_ARG(src && dst && n > 0, "f64_to_f32: bad argument");
+    f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+static int launch_spatial(SpatialRed &a, cudaStream_t st) {
+    int rc = check_cg(a.x.c, "spatial_reduce");
+    if (rc) return rc;
+    a.cg = a.x.c / 4;
+    int block = block_for_cg(a.cg);
+    int rows = block / a.cg;
+    int hw = a.x.h * a.x.w;
+    int split = ceil_div(hw, rows * 64);  // ~64 pixels per thread
+    int cap = ceil_div(148 * 8, a.x.n);
+    if (split > cap) split = cap;
+    if (split < 1) split = 1;
+    a.use_atomic = split > 1;
+    if (a.use_atomic) {
+        zero_strided_kernel<<<ceil_div((long long)a.x.n * a.x.c, 256), 256, 0, st>>>(a.out + a.c_off, a.x.n, a.x.c, a.ld_out);
+        DLIO_LAUNCH_CHECK();
+    }
+    spatial_reduce_kernel<<<dim3(split, a.x.n), block, 0, st>>>(a);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_spatial_mean_fwd(dlio_tensor4 x, const float *x_ptr, const float *scale, const float *shift,
+                                     int relu, float *out, int ld_out, int c_off, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(x) && x_ptr && out && ld_out >= c_off + x.c, "spatial_mean_fwd: bad argument");
+    SpatialRed a;
+    a.x = Geo(x); a.other = a.x; a.xp = x_ptr; a.otherp = nullptr; a.scale = scale; a.shift = shift;
+    a.relu = relu; a.mode = 0; a.ld_out = ld_out; a.c_off = c_off; a.inv = 1.f / (float)(x.h * x.w); a.out = out;
+    return launch_spatial(a, (cudaStream_t)stream);
+}
+
+extern "C" int dlio_spatial_dot(dlio_tensor4 a_t, const float *a_ptr, dlio_tensor4 b_t, const float *b_ptr,
+                                float *out, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(a_t) && valid_t4(b_t) && a_ptr && b_ptr && out, "spatial_dot: bad argument");
+    DLIO_CHECK_ARG(a_t.n == b_t.n && a_t.h == b_t.h && a_t.w == b_t.w && a_t.c == b_t.c, "spatial_dot: geometry mismatch");
+    SpatialRed a;
+    a.x = Geo(a_t); a.other = Geo(b_t); a.xp = a_ptr; a.otherp = b_ptr; a.scale = nullptr; a.shift = nullptr;
+    a.relu = 0; a.mode = 1; a.ld_out = a_t.c; a.c_off = 0; a.inv = 1.f; a.out = out;
+    return launch_spatial(a, (cudaStream_t)stream);
+}
+
+extern "C" int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const float *gate, dlio_tensor4 out,
+                                      float *out_hi, float *out_lo, void *stream) {
+    DLIO_CHECK_ARG(valid_t4(x) && valid_t4(out) && x_ptr && gate && out_hi, "channel_scale_fwd: bad argument");
+    DLIO_CHECK_ARG(x.n == out.n && x.h == out.h && x.w == out.w && x.c == out.c && x.c % 4 == 0, "channel_scale_fwd: geometry");
+    Geo xg(x), og(out);
+    long long total = (long long)og.n * og.hp * og.wp * (x.c / 4);
+    channel_scale_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(xg, x_ptr, gate, og, out_hi, out_lo, x.c / 4);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_channel_scale_bwd(const float *dout, const float *gate, const float *dmean, int n, int hw,
+                                      int c, float *dx, void *stream) {
+    DLIO_CHECK_ARG(dout && gate && dx && c % 4 == 0 && n > 0 && hw > 0, "channel_scale_bwd: bad argument");
+    long long total = (long long)n * hw * (c / 4);
+    channel_scale_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dout, gate, dmean, 1.f / (float)hw, dx, n, hw, c / 4);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_axpby(const float *a, float alpha, const float *b, float beta, float *out, long long n,
+                          void *stream) {
+    DLIO_CHECK_ARG(a && b && out && n > 0, "axpby: bad argument");
+    DLIO_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "axpby: pointers must be 16-byte aligned");
+    axpby_kernel<<<grid_for((n + 3) / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+extern "C" int dlio_sum_mid(const float *x, float *out, long long a, int t, int c, void *stream) {
+    DLIO_CHECK_ARG(x && out && a > 0 && t > 0 && c > 0, "sum_mid: bad argument");
+    sum_mid_kernel<<<ceil_div(a * c, 256), 256, 0, (cudaStream_t)stream>>>(x, out, a, t, c);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+extern "C" int dlio_mul(const float *a, const float *b, float *out, long long n, void *stream) {
+    DLIO_CHECK_ARG(a && b && out && n > 0, "mul: bad argument");
+    mul_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+extern "C" int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed, void *stream) {
+    DLIO_CHECK_ARG(mask && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad argument");
+    dropout_mask_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}

@@ -1,0 +1,291 @@
+"""Host-side executor for the convolutional encoders: a small tape over the C ABI.
+
+The LiDAR encoders do not go through torch autograd op by op.  A forward pass runs a straight-line
+"program" of fused C-ABI calls (conv + bias + ReLU + BN statistics; BN-apply + residual + ReLU + max-pool;
+SE; global average) on padded-NHWC buffers and records one backward closure per call; the backward pass
+replays the closures in reverse.  torch is used for device memory (the caching allocator) and the
+current stream only.
+
+Reference semantics implemented here: base_net.py:55-71 (conv helper), lidar_feat_nets.py:306-342
+(Simple-1 blocks), pointseg_modules.py:110-141,203-221 (Fire / SE), torchvision resnet.py:88-103
+(BasicBlock), BatchNorm2d train/eval statistics.
+"""
+import torch
+
+from . import _lib as L
+from ._lib import ptr
+
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pool_out(n, s, ceil_mode):
+    """Output extent of MaxPool2d(3, s, padding=1) (torch ceil_mode rule: the last window must start
+    inside the input or its left padding)."""
+    if not ceil_mode:
+        return (n + 2 - 3) // s + 1
+    o = -(-(n + 2 - 3) // s) + 1
+    if (o - 1) * s >= n + 1:
+        o -= 1
+    return o
+
+
+class Act:
+    """Padded NHWC fp32 activation: memory [n][h+2ph][w+2pw][c], zero pads."""
+    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "needs_grad")
+
+    def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True):
+        self.n, self.h, self.w, self.c, self.ph, self.pw = n, h, w, c, ph, pw
+        self.t = t if t is not None else torch.empty((n, h + 2 * ph, w + 2 * pw, c), device=device,
+                                                     dtype=torch.float32)
+        self.needs_grad = needs_grad
+
+    @property
+    def t4(self):
+        return L.Tensor4(self.n, self.h, self.w, self.c, self.ph, self.pw)
+
+    @property
+    def t4_unpadded(self):
+        return L.Tensor4(self.n, self.h, self.w, self.c, 0, 0)
+
+
+class Run:
+    """One forward pass (and, if ``record``, its backward tape)."""
+
+    def __init__(self, params, buffers, device, training, record):
+        self.params = params      # name -> tensor (OIHW conv weights, BN affine, SE linears)
+        self.buffers = buffers    # name -> tensor (BN running statistics)
+        self.device = device
+        self.training = training
+        self.record = record
+        self.tape = []
+        self.agrad = {}           # id(Act) -> unpadded NHWC gradient tensor
+        self.fgrad = {}           # id(feature buffer) -> gradient tensor [N, ld]
+        self.pgrad = {}           # parameter name -> gradient tensor
+        self.keep = []            # keeps Acts alive so that id() stays unique
+
+    # -- helpers
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(shape, device=self.device, dtype=dtype)
+
+    def grad_slot(self, act, zeroed=False):
+        """Returns (buffer, existed).  A fresh buffer is uninitialised unless ``zeroed``."""
+        g = self.agrad.get(id(act))
+        if g is not None:
+            return g, True
+        make = self.zeros if zeroed else self.empty
+        g = make(act.n, act.h, act.w, act.c)
+        self.agrad[id(act)] = g
+        return g, False
+
+    def add_grad(self, act, write):
+        """``write(buf)`` overwrites ``buf`` with a full gradient contribution for ``act``."""
+        g, existed = self.grad_slot(act)
+        if not existed:
+            write(g)
+        else:
+            tmp = torch.empty_like(g)
+            write(tmp)
+            L.axpby(ptr(g), 1.0, ptr(tmp), 1.0, ptr(g), g.numel(), stream())
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+
+def pack_input(run, view, c_pad, ph, pw):
+    """[N, T, C, H, W] strided view (H, W contiguous) -> padded NHWC Act with c_pad channels
+    (lidar_feat_nets.py:216-218 reshape; channel order t-major)."""
+    n, t, c, h, w = view.shape
+    if view.stride(4) != 1 or view.stride(3) != w:
+        view = view.contiguous()
+    x = Act(n, h, w, c_pad, ph, pw, device=run.device, needs_grad=False)
+    L.pack_input(ptr(view), view.stride(0), view.stride(1), view.stride(2), t, c, x.t4, ptr(x.t), stream())
+    run.keep.append((x, view))
+    return x
+
+
+def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
+            res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0):
+    """conv(+bias)(+ReLU if pre_relu) -> BatchNorm (batch statistics when run.training) -> (+res)(ReLU)(+res)
+    -> optional 3x3 max-pool, or -> global average into ``feat`` [N, feat_ld] at column feat_off.
+
+    Returns the output Act (None when ``feat`` is given)."""
+    p, st = run.params, stream()
+    w = p[cname + ".weight"]
+    b = p.get(cname + ".bias")
+    gamma, beta = p[bname + ".weight"], p[bname + ".bias"]
+    rm, rv = run.buffers[bname + ".running_mean"], run.buffers[bname + ".running_var"]
+    cout, cin, kh, kw = w.shape
+    assert x.c >= cin and x.c - cin < 4, (cname, x.c, cin)
+    cin_pad = x.c
+    sh, sw = stride
+    cph, cpw = (kh - 1) // 2, (kw - 1) // 2
+    ho, wo = (x.h + 2 * cph - kh) // sh + 1, (x.w + 2 * cpw - kw) // sw + 1
+    cv = L.Conv(kh, kw, sh, sw, cph, cpw)
+    n = x.n
+    w_ohwi = run.empty(cout, kh, kw, cin_pad)
+    L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), None, st)
+    y = Act(n, ho, wo, cout, device=run.device)
+    stats = run.zeros(2 * cout, dtype=torch.float64) if run.training else None
+    L.conv2d_fwd(x.t4, ptr(x.t), None, ptr(w_ohwi), None, ptr(b), cv, L.ACT_RELU if pre_relu else L.ACT_NONE,
+                 y.t4, ptr(y.t), ptr(stats), st)
+    bnv = run.empty(4, cout)  # mean, invstd, scale, shift
+    count = n * ho * wo
+    L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), BN_MOMENTUM, BN_EPS,
+                  0 if run.training else 1, ptr(bnv[0]), ptr(bnv[1]), ptr(bnv[2]), ptr(bnv[3]), st)
+    if run.training:
+        nbt = run.buffers.get(bname + ".num_batches_tracked")
+        if nbt is not None:
+            nbt.add_(1)
+    bp = L.BnPool(1 if relu else 0, res_mode if res is not None else 0, 3 if pool else 1,
+                  pool[0] if pool else 1, pool[1] if pool else 1, c_off)
+    idx = None
+    dummy = y.t4
+    if feat is not None:
+        assert res is None and not pool
+        L.spatial_mean_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), 1 if relu else 0, ptr(feat), feat_ld, feat_off, st)
+        result = None
+    else:
+        oh, ow = (pool_out(ho, pool[0], ceil), pool_out(wo, pool[1], ceil)) if pool else (ho, wo)
+        if out is None:
+            out = Act(n, oh, ow, out_c or cout, out_pad[0], out_pad[1], device=run.device)
+        assert out.h == oh and out.w == ow and out.n == n
+        if pool and run.record:
+            idx = run.empty(n, oh, ow, cout, dtype=torch.uint8)
+        L.bn_act_pool_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), res.t4 if res is not None else dummy,
+                          ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), None, ptr(idx), st)
+        result = out
+    if not run.record:
+        return result
+
+    def bwd():
+        st = stream()
+        if feat is not None:
+            dout = run.fgrad[id(feat)]
+            src, dout_t4, ld = L.GRAD_AVG, dummy, feat_ld
+            bpb = L.BnPool(bp.relu, 0, 1, 1, 1, feat_off)
+        else:
+            # the writer of channel 0 ran first in the forward pass, so it is the last reader of the gradient
+            dout = run.agrad.pop(id(out)) if c_off == 0 else run.agrad[id(out)]
+            src, dout_t4, ld = (L.GRAD_POOL if pool else L.GRAD_DIRECT), out.t4_unpadded, 0
+            bpb = bp
+        dz = run.empty(n, ho, wo, cout)
+        sums = run.zeros(2 * cout, dtype=torch.float64)
+        dres, dres_c, dres_acc = None, 0, 0
+        if res is not None and res.needs_grad:
+            partial = res.c != cout
+            dres, existed = run.grad_slot(res, zeroed=partial)
+            dres_c, dres_acc = res.c, 1 if (existed or partial) else 0
+        L.bn_act_pool_bwd_reduce(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), ptr(bnv[0]), ptr(bnv[1]),
+                                 res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
+                                 bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
+                                 ptr(sums), st)
+        dy = run.empty(n, ho, wo, cout)
+        dgb = run.empty(2, cout)
+        dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
+        L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
+                       1 if pre_relu else 0, 1 if run.training else 0, y.t4, ptr(dy), None, ptr(dgb[0]),
+                       ptr(dgb[1]), ptr(dbs), st)
+        del dz
+        run.pgrad[bname + ".weight"] = dgb[0]
+        run.pgrad[bname + ".bias"] = dgb[1]
+        if b is not None:
+            db = run.empty(cout)
+            L.f64_to_f32(ptr(dbs), ptr(db), cout, st)
+            run.pgrad[cname + ".bias"] = db
+        dw_ohwi = run.empty(cout, kh, kw, cin_pad)
+        L.conv2d_bwd_weight(x.t4, ptr(x.t), None, y.t4, ptr(dy), None, cv, ptr(dw_ohwi), st)
+        dw = torch.empty_like(w)
+        L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
+        run.pgrad[cname + ".weight"] = dw
+        if x.needs_grad:
+            run.add_grad(x, lambda buf: L.conv2d_bwd_data(y.t4, ptr(dy), None, ptr(w_ohwi), None, cv,
+                                                          x.t4_unpadded, ptr(buf), st))
+
+    run.tape.append(bwd)
+    run.keep.append((x, y, out, res))
+    return result
+
+
+def se_layer(run, x, prefix, out_pad=(0, 0)):
+    """SELayer (pointseg_modules.py:203-221): x * sigmoid(W2 relu(W1 mean_hw(x))), no biases."""
+    p, st = run.params, stream()
+    w1, w2 = p[prefix + "fc.0.weight"], p[prefix + "fc.2.weight"]
+    n, c, cr = x.n, x.c, w1.shape[0]
+    m = run.empty(n, c)
+    L.spatial_mean_fwd(x.t4, ptr(x.t), None, None, 0, ptr(m), c, 0, st)
+    hid = run.empty(n, cr)
+    L.linear_fwd(ptr(m), c, ptr(w1), None, n, cr, c, L.ACT_RELU, ptr(hid), cr, st)
+    gate = run.empty(n, c)
+    L.linear_fwd(ptr(hid), cr, ptr(w2), None, n, c, cr, L.ACT_SIGMOID, ptr(gate), c, st)
+    out = Act(n, x.h, x.w, c, out_pad[0], out_pad[1], device=run.device)
+    L.channel_scale_fwd(x.t4, ptr(x.t), ptr(gate), out.t4, ptr(out.t), None, st)
+    if not run.record:
+        return out
+
+    def bwd():
+        st = stream()
+        dout = run.agrad.pop(id(out))
+        dgate = run.empty(n, c)
+        L.spatial_dot(out.t4_unpadded, ptr(dout), x.t4, ptr(x.t), ptr(dgate), st)
+        dhid, dw2, scr = run.empty(n, cr), torch.empty_like(w2), run.empty(n, c)
+        L.linear_bwd(ptr(hid), cr, ptr(w2), ptr(gate), c, ptr(dgate), c, n, c, cr, L.ACT_SIGMOID, ptr(dhid), cr,
+                     ptr(dw2), None, ptr(scr), st)
+        dm, dw1, scr2 = run.empty(n, c), torch.empty_like(w1), run.empty(n, cr)
+        L.linear_bwd(ptr(m), c, ptr(w1), ptr(hid), cr, ptr(dhid), cr, n, cr, c, L.ACT_RELU, ptr(dm), c, ptr(dw1),
+                     None, ptr(scr2), st)
+        run.pgrad[prefix + "fc.0.weight"] = dw1
+        run.pgrad[prefix + "fc.2.weight"] = dw2
+        run.add_grad(x, lambda buf: L.channel_scale_bwd(ptr(dout), ptr(gate), ptr(dm), n, x.h * x.w, c, ptr(buf), st))
+
+    run.tape.append(bwd)
+    run.keep.append((x, out))
+    return out
+
+
+def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
+    """MaxPool2d(3, stride, padding=1) on its own (PointSeg pools, pointseg_net.py:28,35,43,50)."""
+    st = stream()
+    oh, ow = pool_out(x.h, stride[0], ceil), pool_out(x.w, stride[1], ceil)
+    out = Act(x.n, oh, ow, x.c, out_pad[0], out_pad[1], device=run.device)
+    bp = L.BnPool(0, 0, 3, stride[0], stride[1], 0)
+    idx = run.empty(x.n, oh, ow, x.c, dtype=torch.uint8) if run.record else None
+    L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), None, ptr(idx), st)
+    if not run.record:
+        return out
+
+    def bwd():
+        dout = run.agrad.pop(id(out))
+        run.add_grad(x, lambda buf: L.bn_act_pool_bwd_reduce(
+            x.t4, ptr(x.t), None, None, None, None, x.t4, None, bp, L.GRAD_POOL, out.t4_unpadded, ptr(dout), 0,
+            ptr(idx), ptr(buf), None, 0, 0, None, stream()))
+
+    run.tape.append(bwd)
+    run.keep.append((x, out))
+    return out
+
+
+def global_avg(run, x, feat, feat_ld, feat_off):
+    """adaptive_avg_pool2d((1,1)) of an activation into feat[:, feat_off : feat_off + c]."""
+    L.spatial_mean_fwd(x.t4, ptr(x.t), None, None, 0, ptr(feat), feat_ld, feat_off, stream())
+    if not run.record:
+        return
+    bp = L.BnPool(0, 0, 1, 1, 1, feat_off)
+
+    def bwd():
+        dout = run.fgrad[id(feat)]
+        run.add_grad(x, lambda buf: L.bn_act_pool_bwd_reduce(
+            x.t4, ptr(x.t), None, None, None, None, x.t4, None, bp, L.GRAD_AVG, x.t4, ptr(dout), feat_ld, None,
+            ptr(buf), None, 0, 0, None, stream()))
+
+    run.tape.append(bwd)
+    run.keep.append((x,))

@@ -1,0 +1,221 @@
+"""torch.autograd.Function shims over the small-tensor C-ABI ops (dense layers, RNNs, dropout, gating).
+
+torch supplies memory, streams and the autograd graph between these calls; every arithmetic op is a
+kernel from libdeeplio_b200.so.  Inputs must be fp32 CUDA tensors.
+"""
+import torch
+
+from . import _lib as L
+from ._lib import ptr
+
+_ACTS = {None: L.ACT_NONE, "none": L.ACT_NONE, "relu": L.ACT_RELU, "leaky_relu": L.ACT_LEAKY,
+         "sigmoid": L.ACT_SIGMOID, "tanh": L.ACT_TANH}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError("deeplio_b200: %s must be a float32 CUDA tensor (got %s on %s); there is no CPU path"
+                           % (name, t.dtype, t.device))
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        _check(x, "input")
+        _check(w, "weight")
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        m, k = x2.shape
+        n = w.shape[0]
+        if w.shape[1] != k:
+            raise RuntimeError("linear: mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (m, k, w.shape[1], n))
+        y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        L.linear_fwd(ptr(x2), x2.stride(0), ptr(w), ptr(b), m, n, k, act, ptr(y), n, _stream())
+        ctx.save_for_backward(x2, w, y)
+        ctx.act, ctx.has_b, ctx.in_shape = act, b is not None, x.shape
+        return y.view(*x.shape[:-1], n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        m, k = x2.shape
+        n = w.shape[0]
+        dy2 = dy.reshape(m, n)
+        if dy2.stride(-1) != 1 or dy2.stride(0) < n:
+            dy2 = dy2.contiguous()
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_b and ctx.needs_input_grad[2]
+        dx = torch.empty((m, k), device=dy.device, dtype=torch.float32) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty((n,), device=dy.device, dtype=torch.float32) if need_b else None
+        scr = torch.empty((m, n), device=dy.device, dtype=torch.float32) if ctx.act != L.ACT_NONE else None
+        L.linear_bwd(ptr(x2), x2.stride(0), ptr(w), ptr(y), n, ptr(dy2), dy2.stride(0), m, n, k, ctx.act, ptr(dx), k,
+                     ptr(dw), ptr(db), ptr(scr), _stream())
+        return (dx.view(ctx.in_shape) if need_x else None), dw, db, None
+
+
+def linear(x, w, b=None, act=None):
+    """act(x @ w.T + b) -- nn.Linear + activation (aten::linear at lidar_feat_nets.py:97,144,185,233 etc.)."""
+    return _Linear.apply(x, w, b, _ACTS[act])
+
+
+class _Mul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        L.mul(ptr(a), ptr(b), ptr(out), a.numel(), _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        a, b = ctx.saved_tensors
+        d = d.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            L.mul(ptr(d), ptr(b), ptr(da), a.numel(), _stream())
+        if ctx.needs_input_grad[1]:
+            db = torch.empty_like(b)
+            L.mul(ptr(d), ptr(a), ptr(db), a.numel(), _stream())
+        return da, db
+
+
+def mul(a, b):
+    """Element-wise product of two same-shape tensors (soft-fusion gating, fusion_nets.py:72-73)."""
+    assert a.shape == b.shape
+    return _Mul.apply(a, b)
+
+
+_drop_counter = [0]
+
+
+def dropout_mask(shape, p, device):
+    """Pre-scaled Bernoulli keep mask from the library's counter-based generator.  The stream is seeded by
+    torch.initial_seed() and a per-process call counter, so torch.manual_seed() makes runs repeatable."""
+    mask = torch.empty(shape, device=device, dtype=torch.float32)
+    _drop_counter[0] += 1
+    seed = (torch.initial_seed() * 0x9E3779B1 + _drop_counter[0] * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+    L.dropout_mask(ptr(mask), mask.numel(), float(p), seed, _stream())
+    return mask
+
+
+def dropout(x, p, training):
+    """nn.Dropout: identity in eval mode or for p == 0."""
+    if not training or p <= 0.0:
+        return x
+    return mul(x, dropout_mask(x.shape, p, x.device))
+
+
+class _SumMid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        a, t, c = x.shape
+        out = torch.empty((a, c), device=x.device, dtype=torch.float32)
+        L.sum_mid(ptr(x), ptr(out), a, t, c, _stream())
+        ctx.t = t
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d.unsqueeze(1).expand(-1, ctx.t, -1)
+
+
+def sum_mid(x):
+    """[A, T, C] -> [A, C], sum over T (ImuFeatFC time sum, imu_feat_nets.py:50)."""
+    return _SumMid.apply(x)
+
+
+class _Axpby(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        L.axpby(ptr(a), alpha, ptr(b), beta, ptr(out), a.numel(), _stream())
+        ctx.alpha, ctx.beta = alpha, beta
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+
+        def scaled(s):
+            if s == 1.0:
+                return d
+            o = torch.empty_like(d)
+            L.axpby(ptr(d), s, ptr(d), 0.0, ptr(o), d.numel(), _stream())
+            return o
+        return scaled(ctx.alpha), scaled(ctx.beta), None, None
+
+
+def axpby(a, b, alpha=1.0, beta=1.0):
+    return _Axpby.apply(a, b, float(alpha), float(beta))
+
+
+class _Rnn(torch.autograd.Function):
+    """Multi-layer (bi)LSTM / GRU, batch_first (aten::lstm / aten::gru at imu_feat_nets.py:79-82,
+    odom_feat_nets.py:80).  Returns (out [B,T,D*H], h_n, c_n)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, kind, L_, D, H, drop_mask, *weights):
+        _check(x, "rnn input")
+        x = x.contiguous()
+        B, T, I = x.shape
+        dev = x.device
+        for w in weights:
+            _check(w, "rnn weight")
+        ws = [w if w.is_contiguous() else w.contiguous() for w in weights]
+        out = torch.empty((B, T, D * H), device=dev, dtype=torch.float32)
+        hn = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
+        cn = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
+        reserve = torch.empty((L.rnn_reserve_floats(kind, L_, D, B, T, I, H),), device=dev, dtype=torch.float32)
+        h0c = h0.contiguous() if h0 is not None else None
+        c0c = c0.contiguous() if c0 is not None else None
+        L.rnn_fwd(kind, L_, D, B, T, I, H, L.ptr_array(ws), ptr(x), ptr(h0c), ptr(c0c), ptr(drop_mask), ptr(out),
+                  ptr(hn), ptr(cn), ptr(reserve), _stream())
+        ctx.save_for_backward(x, reserve, drop_mask, *ws)
+        ctx.dims = (kind, L_, D, B, T, I, H)
+        ctx.has_state = (h0 is not None, c0 is not None)
+        ctx.mark_non_differentiable()
+        return out, hn, cn
+
+    @staticmethod
+    def backward(ctx, dout, dhn, dcn):
+        x, reserve, drop_mask, *ws = ctx.saved_tensors
+        kind, L_, D, B, T, I, H = ctx.dims
+        dev = x.device
+        grads = [torch.empty_like(w) for w in ws]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dh0 = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
+        dc0 = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
+        nscr = L.rnn_bwd_scratch_floats(kind, L_, D, B, T, I, H)
+        scratch = torch.empty((nscr,), device=dev, dtype=torch.float32)
+        dout = dout.contiguous() if dout is not None else None
+        dhn = dhn.contiguous() if dhn is not None else None
+        dcn = dcn.contiguous() if (dcn is not None and kind == 0) else None
+        L.rnn_bwd(kind, L_, D, B, T, I, H, L.ptr_array(ws), ptr(x), ptr(drop_mask), ptr(dout), ptr(dhn), ptr(dcn),
+                  ptr(reserve), L.ptr_array(grads), ptr(dx), ptr(dh0), ptr(dc0), ptr(scratch), nscr, _stream())
+        return (dx, dh0 if ctx.has_state[0] else None, dc0 if ctx.has_state[1] else None,
+                None, None, None, None, None, *grads)
+
+
+def rnn(x, state, kind, num_layers, bidirectional, hidden_size, weights, dropout_p=0.0, training=False):
+    """kind 'lstm' | 'gru'; state None | (h0, c0) | h0; weights in torch's flat order
+    (w_ih, w_hh, b_ih, b_hh per layer and direction).  Returns (out, new_state) like nn.LSTM / nn.GRU."""
+    k = 0 if kind == "lstm" else 1
+    D = 2 if bidirectional else 1
+    h0 = c0 = None
+    if state is not None:
+        h0, c0 = state if k == 0 else (state, None)
+    mask = None
+    if training and dropout_p > 0.0 and num_layers > 1:
+        B, T, _ = x.shape
+        mask = dropout_mask((num_layers - 1, B, T, D * hidden_size), dropout_p, x.device)
+    out, hn, cn = _Rnn.apply(x, h0, c0, k, num_layers, D, hidden_size, mask, *weights)
+    return out, ((hn, cn) if k == 0 else hn)

@@ -1,0 +1,337 @@
+"""LiDAR feature nets: two independent encoders (xyz pair, normal pair) + add/sub/cat + fc1 -> 128.
+
+Drop-in classes for the reference's ``LidarSimpleFeat1``, ``LidarPointSegFeat``, ``LidarResNetFeat`` and
+``LidarFlowNetFeat`` (lidar_feat_nets.py:46-237) with their encoders ``FeatureNetSimple1`` (:270-342),
+``FlowNetEncoder`` (:240-267), ``PSEncoder`` (pointseg_net.py:9-82) and ``ResNetEncoder`` (resnet.py:14-112).
+Same constructor signatures, ``state_dict`` keys and outputs; the convolutional work runs as a tape of
+fused C-ABI calls (deeplio_b200.engine) instead of nn.Module forwards.
+
+Differences from the reference, on purpose:
+  * the output shape is computed analytically (the reference runs a dummy CPU forward, :33-40);
+  * ``fusion: cat`` builds ``fc1`` with 2*C inputs -- the reference hard-codes C (:66,116,161,204) and
+    crashes on the first forward;
+  * Simple-1 ``bypass: true`` raises at construction: the reference adds a 128- to a 256-channel tensor
+    (:322-326) and cannot run either.
+"""
+import torch
+from torch import nn
+
+from .. import engine as E
+from .. import functional as Fn
+from .. import _lib as L
+from .._lib import ptr
+from ..config import get_config_container
+from .base import BaseNet, ParamTree, conv_params, require_cuda
+
+
+# ----------------------------------------------------------------------------- encoder definitions
+class _Encoder(ParamTree):
+    """Parameter container + forward program of one encoder.  ``out_channels`` = pooled feature width."""
+    out_channels = 0
+    first_pad = (0, 0)
+
+    def _conv(self, name, cin, cout, k, bias):
+        return self.put(name, conv_params(cin, cout, k, bias))
+
+    def _bn(self, name, c, momentum=0.1):
+        return self.put(name, nn.BatchNorm2d(c, momentum=momentum))
+
+    def program(self, run, x, feat, ld, off):
+        raise NotImplementedError
+
+
+class Simple1Encoder(_Encoder):
+    """conv(+bias) -> ReLU -> BN, seven times; ceil-mode max-pools after blocks 1, 2, 4, 6; global mean."""
+    out_channels = 512
+    first_pad = (2, 3)
+    SPEC = [(1, 64, (5, 7)), (2, 128, (3, 5)), (3, 128, 3), (4, 256, 3), (5, 256, 3), (6, 512, 3), (7, 512, 3)]
+
+    def __init__(self, cin, bypass=False):
+        super().__init__()
+        if bypass:
+            raise ValueError("lidar-feat-simple-1: bypass=true adds tensors of different channel counts "
+                             "(reference lidar_feat_nets.py:322-326) and is not runnable")
+        for i, cout, k in self.SPEC:
+            self._conv("conv%d" % i, cin, cout, k, True)
+            self._bn("bn%d" % i, cout)
+            cin = cout
+
+    def program(self, run, x, feat, ld, off):
+        def blk(i, t, stride=(1, 1), pool=None, pad=(1, 1), **kw):
+            return E.conv_bn(run, t, "conv%d" % i, "bn%d" % i, stride, pre_relu=True, relu=False, pool=pool,
+                             ceil=True, out_pad=pad, **kw)
+        t = blk(1, x, (1, 2), pool=(1, 2), pad=(1, 2))
+        t = blk(2, t, pool=(1, 2))
+        t = blk(3, t)
+        t = blk(4, t, pool=(2, 2))
+        t = blk(5, t)
+        t = blk(6, t, pool=(2, 2))
+        blk(7, t, feat=feat, feat_ld=ld, feat_off=off)
+
+
+class FlowNetEncoder(_Encoder):
+    """Nine conv(no bias) -> BN -> ReLU blocks (base_net.py:55-71), global mean."""
+    out_channels = 1024
+    first_pad = (2, 3)
+    SPEC = [("conv1", 64, (5, 7), (1, 2)), ("conv2", 128, (3, 5), (1, 2)), ("conv3", 256, (3, 5), (1, 2)),
+            ("conv3_1", 256, 3, (1, 1)), ("conv4", 512, 3, (2, 2)), ("conv4_1", 512, 3, (1, 1)),
+            ("conv5", 512, 3, (2, 2)), ("conv5_1", 512, 3, (1, 1)), ("conv6", 1024, 3, (2, 2))]
+
+    def __init__(self, cin):
+        super().__init__()
+        for name, cout, k, _ in self.SPEC:
+            self._conv(name + ".0", cin, cout, k, False)
+            self._bn(name + ".1", cout)
+            cin = cout
+
+    def program(self, run, x, feat, ld, off):
+        t = x
+        for i, (name, _, k, stride) in enumerate(self.SPEC):
+            last = i == len(self.SPEC) - 1
+            if last:
+                E.conv_bn(run, t, name + ".0", name + ".1", stride, feat=feat, feat_ld=ld, feat_off=off)
+            else:
+                nk = self.SPEC[i + 1][2]
+                nkh, nkw = (nk, nk) if isinstance(nk, int) else nk
+                t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, (nkw - 1) // 2))
+
+
+class ResNetEncoder(_Encoder):
+    """conv1 5x7 (bias) -> BN -> ReLU -> max-pool s(1,2); layers [3,3,3,2] of BasicBlocks
+    (torchvision resnet.py:59-105) with first-block strides (1,2),(1,2),(2,2),(2,2); global mean."""
+    out_channels = 512
+    first_pad = (2, 3)
+    LAYERS = [("layer1", 3, 64, (1, 2)), ("layer2", 3, 128, (1, 2)), ("layer3", 3, 256, (2, 2)),
+              ("layer4", 2, 512, (2, 2))]
+
+    def __init__(self, cin):
+        super().__init__()
+        self._conv("conv1", cin, 64, (5, 7), True)
+        self._bn("bn1", 64)
+        inpl = 64
+        for lname, nblk, planes, _ in self.LAYERS:
+            for b in range(nblk):
+                q = "%s.%d." % (lname, b)
+                self._conv(q + "conv1", inpl, planes, 3, False)
+                self._bn(q + "bn1", planes)
+                self._conv(q + "conv2", planes, planes, 3, False)
+                self._bn(q + "bn2", planes)
+                if b == 0:
+                    self._conv(q + "downsample.0", inpl, planes, 1, False)
+                    self._bn(q + "downsample.1", planes)
+                inpl = planes
+        for m in self.modules():  # resnet.py:51-56
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def program(self, run, x, feat, ld, off):
+        t = E.conv_bn(run, x, "conv1", "bn1", (1, 1), pool=(1, 2), ceil=False, out_pad=(1, 1))
+        for lname, nblk, _, stride in self.LAYERS:
+            for b in range(nblk):
+                q = "%s.%d." % (lname, b)
+                s = stride if b == 0 else (1, 1)
+                o = E.conv_bn(run, t, q + "conv1", q + "bn1", s, out_pad=(1, 1))
+                idn = t
+                if b == 0:
+                    idn = E.conv_bn(run, t, q + "downsample.0", q + "downsample.1", s, relu=False)
+                t = E.conv_bn(run, o, q + "conv2", q + "bn2", (1, 1), relu=True, res=idn, res_mode=1, out_pad=(1, 1))
+        E.global_avg(run, t, feat, ld, off)
+
+
+class PointSegEncoder(_Encoder):
+    """PSEncoder: conv1a 3x5 s(1,2) -> BN -> ReLU -> pool; five Fire blocks with SE layers and pools."""
+    out_channels = 768
+    first_pad = (1, 2)
+    # block -> entries: ('F', cin, squeeze, expand) fire | ('S', c) SE | ('P', stride) pool
+    BLOCKS = [("fire_blk1", [("F", 64, 16, 64), ("F", 128, 16, 64), ("S", 128), ("P", (1, 2))]),
+              ("fire_blk2", [("F", 128, 32, 128), ("F", 256, 32, 128), ("S", 256), ("P", (1, 2))]),
+              ("fire_blk3", [("F", 256, 48, 192), ("F", 384, 48, 192), ("F", 384, 64, 256), ("F", 512, 64, 256),
+                             ("S", 512), ("P", (2, 2))]),
+              ("fire_blk4", [("F", 512, 64, 256), ("F", 512, 64, 256), ("S", 512), ("P", (2, 2))]),
+              ("fire_blk5", [("F", 512, 80, 384), ("FN", 768, 80, 384)])]
+
+    def __init__(self, cin, bypass="simple", bn_d=0.1):
+        super().__init__()
+        self.bypass = bypass
+        self._conv("conv1a.0", cin, 64, (3, 5), True)
+        self._bn("conv1a.1", 64, bn_d)
+        for bname, entries in self.BLOCKS:
+            for i, e in enumerate(entries):
+                q = "%s.%d." % (bname, i)
+                if e[0] in ("F", "FN"):
+                    _, ci, sq, ex = e
+                    self._conv(q + "squeeze", ci, sq, 1, True)
+                    self._bn(q + "squeeze_bn", sq, bn_d)
+                    self._conv(q + "expand1x1", sq, ex, 1, True)
+                    self._bn(q + "expand1x1_bn", ex, bn_d)
+                    self._conv(q + "expand3x3", sq, ex, 3, True)
+                    self._bn(q + "expand3x3_bn", ex, bn_d)
+                elif e[0] == "S":
+                    c = e[1]
+                    self.put(q + "fc.0", nn.Linear(c, c // 2, bias=False))
+                    self.put(q + "fc.2", nn.Linear(c // 2, c, bias=False))
+
+    def _fire(self, run, q, x, ex, bypass):
+        """Fire (pointseg_modules.py:110-141): squeeze1x1 -> {expand1x1 || expand3x3} -> cat (+ x)."""
+        s = E.conv_bn(run, x, q + "squeeze", q + "squeeze_bn", out_pad=(1, 1))
+        res = x if (bypass and x.c == 2 * ex) else None
+        out = E.conv_bn(run, s, q + "expand1x1", q + "expand1x1_bn", res=res, res_mode=2, c_off=0, out_c=2 * ex,
+                        out_pad=(1, 1))
+        E.conv_bn(run, s, q + "expand3x3", q + "expand3x3_bn", res=res, res_mode=2, out=out, c_off=ex)
+        return out
+
+    def program(self, run, x, feat, ld, off):
+        t = E.conv_bn(run, x, "conv1a.0", "conv1a.1", (1, 2), pool=(1, 2), ceil=False, out_pad=(1, 1))
+        for bname, entries in self.BLOCKS:
+            for i, e in enumerate(entries):
+                q = "%s.%d." % (bname, i)
+                if e[0] == "F":
+                    t = self._fire(run, q, t, e[3], self.bypass == "simple")
+                elif e[0] == "FN":
+                    t = self._fire(run, q, t, e[3], False)
+                elif e[0] == "S":
+                    t = E.se_layer(run, t, q, out_pad=(1, 1))
+                else:
+                    t = E.max_pool(run, t, e[1], ceil=False, out_pad=(1, 1))
+        E.global_avg(run, t, feat, ld, off)  # adaptive_avg_pool2d outside the encoder (lidar_feat_nets.py:84-85)
+
+
+# ----------------------------------------------------------------------------- siamese pair as one autograd node
+class _EncoderPair(torch.autograd.Function):
+    """encoder1(xyz) (+|-|cat) encoder2(normals) -> [N, C] (or [N, 2C]); forward records a tape per encoder,
+    backward replays them."""
+
+    @staticmethod
+    def forward(ctx, net, record, xyz, normals, *params):
+        enc = (net.encoder1, net.encoder2)
+        names = net._param_names
+        n1 = len(names[0])
+        groups = (params[:n1], params[n1:])
+        dev = xyz.device
+        c = enc[0].out_channels
+        cat = net.fusion == "cat"
+        n = xyz.shape[0]
+        feats = [torch.empty((n, 2 * c if cat else c), device=dev, dtype=torch.float32)]
+        feats.append(feats[0] if cat else torch.empty((n, c), device=dev, dtype=torch.float32))
+        runs = []
+        for e, view in enumerate((xyz, normals)):
+            pd = dict(zip(names[e], groups[e]))
+            bufs = dict(enc[e].named_buffers())
+            run = E.Run(pd, bufs, dev, net.training, record)
+            x0 = E.pack_input(run, view, 8, *enc[e].first_pad)
+            enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)
+            runs.append(run)
+        if cat:
+            y = feats[0]
+        else:
+            y = torch.empty_like(feats[0])
+            L.axpby(ptr(feats[0]), 1.0, ptr(feats[1]), 1.0 if net.fusion == "add" else -1.0, ptr(y), y.numel(),
+                    E.stream())
+        if record:
+            ctx.runs, ctx.feats, ctx.fusion, ctx.names = runs, feats, net.fusion, names
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        runs, feats = ctx.runs, ctx.feats
+        grads = []
+        for e, run in enumerate(runs):
+            d = dy
+            if e == 1 and ctx.fusion not in ("cat", "add"):
+                d = torch.empty_like(dy)
+                L.axpby(ptr(dy), -1.0, ptr(dy), 0.0, ptr(d), dy.numel(), E.stream())
+            run.fgrad[id(feats[e])] = d
+            run.backward()
+            grads.extend(run.pgrad.get(k) for k in ctx.names[e])
+        ctx.runs = None
+        return (None, None, None, None, *grads)
+
+
+class BaseLidarFeatNet(BaseNet):
+    """Common part of the four LiDAR feature nets (lidar_feat_nets.py:12-43)."""
+    tail = "relu_then_drop"   # pointseg / flownet: drop(relu(fc1(x)))
+
+    def __init__(self, input_shape, cfg):
+        super().__init__()
+        self.p = cfg["dropout"]
+        self.fusion = cfg["fusion"]
+        self.cfg_container = get_config_container()
+        self.seq_size = self.cfg_container.seq_size
+        self.timestamps = self.cfg_container.timestamps
+        self.combinations = self.cfg_container.combinations
+        self.input_shape = input_shape
+
+    def _finish(self, width):
+        self.fc1 = nn.Linear(width * (2 if self.fusion == "cat" else 1), 128)
+        self._param_names = tuple(tuple(k for k, _ in e.named_parameters()) for e in (self.encoder1, self.encoder2))
+        self.output_shape = torch.Size([1, self.seq_size, 128])
+
+    def forward(self, x):
+        imgs_xyz, imgs_normals = x[0], x[1]
+        require_cuda(imgs_xyz, "lidar input")
+        b, s, t, c, h, w = imgs_xyz.shape
+        if imgs_xyz.dtype != torch.float32 or imgs_normals.dtype != torch.float32:
+            raise RuntimeError("deeplio_b200: lidar inputs must be float32")
+
+        def as5(v):  # [B,S,T,C,H,W] -> [B*S,T,C,H,W] without copying when (b, s) collapse
+            if v.stride(0) != s * v.stride(1):
+                v = v.contiguous()
+            return v.as_strided((b * s, t, c, h, w), (v.stride(1),) + tuple(v.stride()[2:]), v.storage_offset())
+        params = [p for e in (self.encoder1, self.encoder2) for _, p in e.named_parameters()]
+        record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        y = _EncoderPair.apply(self, record, as5(imgs_xyz), as5(imgs_normals), *params)
+        y = self._tail(y)
+        return y.view(b, s, -1)
+
+    def _tail(self, y):
+        if self.tail == "drop_then_leaky":      # Simple-1 (lidar_feat_nets.py:230-233)
+            return Fn.linear(Fn.dropout(y, self.p, self.training), self.fc1.weight, self.fc1.bias, "leaky_relu")
+        if self.tail == "drop_then_relu":       # ResNet (lidar_feat_nets.py:182-185)
+            return Fn.linear(Fn.dropout(y, self.p, self.training), self.fc1.weight, self.fc1.bias, "relu")
+        return Fn.dropout(Fn.linear(y, self.fc1.weight, self.fc1.bias, "relu"), self.p, self.training)
+
+
+class LidarSimpleFeat1(BaseLidarFeatNet):
+    tail = "drop_then_leaky"
+
+    def __init__(self, input_shape, cfg):
+        super().__init__(input_shape, cfg)
+        c = input_shape[0]
+        self.encoder1 = Simple1Encoder(2 * c, cfg["bypass"])
+        self.encoder2 = Simple1Encoder(2 * c, cfg["bypass"])
+        self._finish(512)
+
+
+class LidarFlowNetFeat(BaseLidarFeatNet):
+    def __init__(self, input_shape, cfg):
+        super().__init__(input_shape, cfg)
+        c = input_shape[0]
+        self.encoder1 = FlowNetEncoder(2 * c)
+        self.encoder2 = FlowNetEncoder(2 * c)
+        self._finish(1024)
+
+
+class LidarResNetFeat(BaseLidarFeatNet):
+    tail = "drop_then_relu"
+
+    def __init__(self, input_shape, cfg):
+        super().__init__(input_shape, cfg)
+        c = input_shape[0]
+        self.encoder1 = ResNetEncoder(2 * c)
+        self.encoder2 = ResNetEncoder(2 * c)
+        self._finish(512)
+
+
+class LidarPointSegFeat(BaseLidarFeatNet):
+    def __init__(self, input_shape, cfg, bn_d=0.1):
+        super().__init__(input_shape, cfg)
+        self.part = cfg["part"].lower()
+        self.bn_d = bn_d
+        c = input_shape[0]
+        self.encoder1 = PointSegEncoder(2 * c, cfg.get("bypass"), bn_d)
+        self.encoder2 = PointSegEncoder(2 * c, cfg.get("bypass"), bn_d)
+        self._finish(768)

@@ -1,0 +1,239 @@
+/*
+ * deeplio_b200 -- C ABI of the B200-native (sm_100a) DeepLIO training hot path.
+ *
+ * The reference (ArashJavan/DeepLIO) has no FFI: its hot path is four nn.Module subsystems under
+ * deeplio/models/nets that dispatch to ATen / cuDNN / cuBLAS.  Each entry point below replaces one
+ * family of those implicit library calls; the reference call sites are cited per function.  The
+ * Python host side (deeplio_b200/nets.py) mirrors the reference's module interface on top of this
+ * ABI; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - all floating-point data is IEEE fp32; statistics accumulators are fp64;
+ *   - activations are "padded NHWC": memory [n][h + 2*ph][w + 2*pw][c] with ZERO pad rows / columns,
+ *     described by dlio_tensor4 (the pads are those of the convolution that consumes the tensor);
+ *   - convolution weights are OHWI: [cout][kh][kw][cin] (a channels_last nn.Conv2d weight, zero-copy);
+ *   - no allocation, no ownership transfer, no host synchronisation inside any call: work is enqueued
+ *     on `stream` (a cudaStream_t passed as void*); scratch memory is passed in by the caller;
+ *   - return value: 0 on success, a negative dlio_status otherwise; dlio_last_error() gives the text.
+ */
+#ifndef DEEPLIO_B200_H
+#define DEEPLIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLIO_ABI_VERSION 1
+
+typedef enum {
+    DLIO_OK = 0,
+    DLIO_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    DLIO_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+    DLIO_ERR_WORKSPACE = -3,   /* caller-provided scratch too small */
+    DLIO_ERR_UNSUPPORTED = -4  /* device is not sm_100 */
+} dlio_status;
+
+/* activation / epilogue functions (torch.nn.functional names) */
+typedef enum {
+    DLIO_ACT_NONE = 0,
+    DLIO_ACT_RELU = 1,
+    DLIO_ACT_LEAKY = 2,   /* leaky_relu, slope 0.01 */
+    DLIO_ACT_SIGMOID = 3,
+    DLIO_ACT_TANH = 4
+} dlio_act;
+
+/* padded NHWC activation descriptor */
+typedef struct {
+    int n, h, w, c; /* logical extent */
+    int ph, pw;     /* zero rows / columns stored on each side */
+} dlio_tensor4;
+
+/* 2-D convolution (cross-correlation, dilation 1, groups 1) */
+typedef struct {
+    int kh, kw; /* kernel */
+    int sh, sw; /* stride */
+    int ph, pw; /* zero padding */
+} dlio_conv;
+
+/* ------------------------------------------------------------------ library */
+int dlio_abi_version(void);
+const char *dlio_last_error(void);                 /* host string, thread-local */
+int dlio_device_check(int device);                 /* DLIO_OK iff compute capability 10.x */
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+long long dlio_launch_count(void);
+
+/* ------------------------------------------------------------------ input staging
+ * Replaces imgs.reshape(b*s, t*c, h, w) (lidar_feat_nets.py:216-218): gathers the strided
+ * [N, T, C, H, W] view (element strides sn, st, sc; h and w contiguous) into padded NHWC with
+ * `dst.c` >= T*C channels (extra channels zero), channel order (t0:c0..c2, t1:c0..c2). */
+int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
+                    dlio_tensor4 dst, float *dst_ptr, void *stream);
+
+/* ------------------------------------------------------------------ convolution
+ * Replaces aten::conv2d forward / dgrad / wgrad behind every nn.Conv2d on the path
+ * (lidar_feat_nets.py:248-257,279-301; pointseg_net.py:18; pointseg_modules.py:96-104; resnet.py:36;
+ * torchvision resnet.py:40-56).
+ *
+ * forward:  y = act(conv(x, w) + bias); optionally accumulates per-channel sum / sum-of-squares of y
+ *           over the logical (n,h,w) extent into stats[0:cout] / stats[cout:2*cout] (fp64, caller
+ *           zeroes) -- the batch statistics nn.BatchNorm2d needs (train mode).
+ *           x_lo / w_lo: optional low-order TF32 split planes.  When all of (x_lo, w_lo) are given,
+ *           the stride is 1, cin % 32 == 0 and cout % 64 == 0, x.ph/pw == conv pads and y has x's
+ *           geometry, the tcgen05 (3xTF32) implicit-GEMM kernel is used; otherwise the generic fp32
+ *           kernel runs on x (+ x_lo if given) and w.
+ */
+int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x_lo,
+                    const float *w_hi, const float *w_lo, const float *bias,
+                    dlio_conv cv, int act,
+                    dlio_tensor4 y, float *y_ptr, double *stats, void *stream);
+
+/* dgrad: dx = conv_transpose(dy, w).  dx pads are written as zeros when dx is padded. */
+int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const float *dy_lo,
+                         const float *w_hi, const float *w_lo, dlio_conv cv,
+                         dlio_tensor4 dx, float *dx_ptr, void *stream);
+
+/* wgrad: dw[cout][kh][kw][cin] = sum_{n,h,w} dy * x (overwrites dw). */
+int dlio_conv2d_bwd_weight(dlio_tensor4 x, const float *x_hi, const float *x_lo,
+                           dlio_tensor4 dy, const float *dy_hi, const float *dy_lo,
+                           dlio_conv cv, float *dw, void *stream);
+
+/* OIHW (torch default) <-> OHWI with channel padding cin -> cin_pad (zeros); optional hi/lo split */
+int dlio_weight_to_ohwi(const float *w_oihw, int cout, int cin, int kh, int kw, int cin_pad,
+                        float *w_hi, float *w_lo, void *stream);
+int dlio_weight_grad_to_oihw(const float *dw_ohwi, int cout, int cin, int kh, int kw, int cin_pad,
+                             float *dw_oihw, void *stream);
+/* dgrad operand for the tcgen05 path: wt[cin][kh'][kw'][cout] = w[cout][kh-1-kh'][kw-1-kw'][cin] */
+int dlio_weight_flip_transpose(const float *w_ohwi, int cout, int cin, int kh, int kw,
+                               float *wt_hi, float *wt_lo, void *stream);
+
+/* ------------------------------------------------------------------ batch-norm / activation / pooling
+ * Replaces aten::batch_norm (train + eval), relu, max_pool2d_with_indices, adaptive_avg_pool2d and the
+ * residual / bypass adds around them (lidar_feat_nets.py:306-342; base_net.py:55-71; pointseg_modules.py
+ * :110-141; torchvision resnet.py:88-103).
+ *
+ * dlio_bn_finalize: from the fp64 sums over `count` elements per channel computes
+ *   mean, invstd = 1/sqrt(biased_var + eps), scale = gamma*invstd, shift = beta - mean*scale and updates
+ *   running_mean / running_var (unbiased var, `momentum`).  With use_running != 0 (eval mode) scale/shift
+ *   come from the running statistics and nothing is updated.  Outputs are [c] fp32 each.
+ */
+int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma, const float *beta,
+                     float *running_mean, float *running_var, float momentum, float eps, int use_running,
+                     float *mean, float *invstd, float *scale, float *shift, void *stream);
+
+typedef struct {
+    int relu;       /* 1: apply ReLU after scale*y + shift (+ residual if res_mode == 1) */
+    int res_mode;   /* 0 none; 1 residual added BEFORE the ReLU (torchvision BasicBlock, resnet.py:101);
+                       2 residual added AFTER it (Fire bypass, pointseg_modules.py:138-140) */
+    int pool_k;     /* 1 = no pooling, 3 = 3x3 max pool (pad 1; the output extent carries ceil_mode) */
+    int pool_sh, pool_sw;
+    int c_off;      /* channel offset inside the output (and residual) tensor (Fire concat) */
+} dlio_bnpool;
+
+/* out[n,ho,wo,c_off+c] = maxpool(act(scale[c]*y + shift[c] (+res)) (+res)); writes out's pads as zeros for
+ * the channel range.  scale == shift == NULL means identity (plain max-pool / copy into a padded tensor).
+ * out_lo (optional): TF32 split planes (out_hi = rna_tf32(v), out_lo = v - out_hi); when out_lo is NULL
+ * out_hi receives the full fp32 value.  pool_idx (uint8 [n,ho,wo,c], required when pooling is
+ * differentiated): window-relative arg-max, first maximum wins (torch tie-break). */
+int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
+                         dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
+                         float *out_hi, float *out_lo, uint8_t *pool_idx, void *stream);
+
+typedef enum { DLIO_GRAD_DIRECT = 0, DLIO_GRAD_POOL = 1, DLIO_GRAD_AVG = 2 } dlio_grad_src;
+
+/* backward pass 1: dz = relu'(.) * pool_backward(dout) at every (n,h,w,c) of y; writes dz (unpadded
+ * [n,h,w,c]) and accumulates sums[0:c] += sum dz, sums[c:2c] += sum dz * yhat (fp64, caller zeroes; NULL
+ * when there is no BN).  grad_src: DIRECT / POOL  dout is an (unpadded or padded) NHWC gradient of the
+ * op's output, read at channel c_off; AVG  dout is [n, ld_dout] read at c_off and spread as 1/(h*w).
+ * dres (optional, unpadded [n,h,w,dres_c], written at channel c_off): gradient of the residual input;
+ * overwritten, or added to when dres_accumulate != 0. */
+int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
+                                const float *mean, const float *invstd,
+                                dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, int grad_src,
+                                dlio_tensor4 dout, const float *dout_ptr, int ld_dout, const uint8_t *pool_idx,
+                                float *dz, float *dres, int dres_c, int dres_accumulate, double *sums,
+                                void *stream);
+
+/* backward pass 2: dy = scale * (dz - mean(dz) - yhat * mean(dz*yhat)) (batch_stats != 0) or scale * dz
+ * (eval-mode BN); if pre_relu (conv -> ReLU -> BN, lidar_feat_nets.py:308-309) dy *= (y > 0).  Writes dy
+ * (geometry dy_t, zero pads, optional TF32 split), dgamma[c], dbeta[c] and accumulates
+ * dbias_sums[c] += sum dy (fp64, caller zeroes; may be NULL). */
+int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
+                      long long count, const float *scale, const float *mean, const float *invstd,
+                      int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
+                      float *dgamma, float *dbeta, double *dbias_sums, void *stream);
+int dlio_f64_to_f32(const double *src, float *dst, int n, void *stream);
+
+/* global average pooling (adaptive_avg_pool2d((1,1)), lidar_feat_nets.py:84-85,131,175,340; SE squeeze,
+ * pointseg_modules.py:217): out[n, c_off + c] = mean_{h,w} act(scale*x + shift)  (scale/shift may be NULL) */
+int dlio_spatial_mean_fwd(dlio_tensor4 x, const float *x_ptr, const float *scale, const float *shift,
+                          int relu, float *out, int ld_out, int c_off, void *stream);
+/* out[n, c] = sum_{h,w} a * b   (gradient of the SE gate) */
+int dlio_spatial_dot(dlio_tensor4 a, const float *a_ptr, dlio_tensor4 b, const float *b_ptr, float *out,
+                     void *stream);
+/* SE layer (pointseg_modules.py:203-221): out = x * gate[n,c];
+ * backward: dx = dout * gate[n,c] + dmean[n,c] / hw  (dout, dx unpadded [n,hw,c]; dmean may be NULL) */
+int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const float *gate, dlio_tensor4 out,
+                           float *out_hi, float *out_lo, void *stream);
+int dlio_channel_scale_bwd(const float *dout, const float *gate, const float *dmean, int n, int hw, int c,
+                           float *dx, void *stream);
+/* element-wise helpers: out = alpha*a + beta*b (16-byte aligned; out may alias a or b), out = a * b,
+ * out[a,c] = sum_t x[a,t,c] (ImuFeatFC time sum, imu_feat_nets.py:50), Bernoulli keep mask scaled by 1/(1-p) */
+int dlio_axpby(const float *a, float alpha, const float *b, float beta, float *out, long long n, void *stream);
+int dlio_sum_mid(const float *x, float *out, long long a, int t, int c, void *stream);
+int dlio_mul(const float *a, const float *b, float *out, long long n, void *stream);
+int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed, void *stream);
+
+/* ------------------------------------------------------------------ dense layers (small M)
+ * Replaces aten::linear / addmm behind nn.Linear (fc1, IMU-FC stack, soft fusion, Odom-FC, heads:
+ * lidar_feat_nets.py:97,144,185,233; imu_feat_nets.py:47; fusion_nets.py:68-69; odom_feat_nets.py:34;
+ * deeplio_nets.py:88-89).
+ *   y[m, ldy] = act(x[m, ldx] . w[n, k]^T + b)                        (forward)
+ *   dz = dy * act'(y);  dx = dz . w;  dw = dz^T . x;  db = sum_m dz   (backward; dx/dw/db may be NULL)
+ * `scratch` for the backward: m*n floats. */
+int dlio_linear_fwd(const float *x, int ldx, const float *w, const float *b, int m, int n, int k, int act,
+                    float *y, int ldy, void *stream);
+int dlio_linear_bwd(const float *x, int ldx, const float *w, const float *y, int ldy, const float *dy, int lddy,
+                    int m, int n, int k, int act, float *dx, int lddx, float *dw, float *db,
+                    float *scratch, void *stream);
+
+/* ------------------------------------------------------------------ recurrent layers
+ * Replaces aten::lstm / aten::gru (cuDNN RNN) behind nn.LSTM / nn.GRU, batch_first, multi-layer,
+ * optionally bidirectional (imu_feat_nets.py:64-82; odom_feat_nets.py:61-80).
+ *
+ * kind: 0 = LSTM (gates i,f,g,o), 1 = GRU (gates r,z,n).  G = 4 or 3, D = 1 or 2.
+ * weights: array (HOST memory) of 4*L*D device pointers in torch order
+ *          [w_ih, w_hh, b_ih, b_hh] for (l0,fwd), (l0,rev), (l1,fwd), ...
+ * x [B,T,I]; h0/c0 [L*D,B,H] (NULL = zeros); out [B,T,D*H]; hn/cn [L*D,B,H].
+ * reserve: caller scratch kept from forward to backward, dlio_rnn_reserve_floats() floats.
+ * drop_mask: optional [L-1, B, T, D*H] pre-scaled keep mask applied to inter-layer activations.
+ */
+size_t dlio_rnn_reserve_floats(int kind, int L, int D, int B, int T, int I, int H);
+int dlio_rnn_fwd(int kind, int L, int D, int B, int T, int I, int H, const float *const *weights,
+                 const float *x, const float *h0, const float *c0, const float *drop_mask,
+                 float *out, float *hn, float *cn, float *reserve, void *stream);
+/* grads: array (HOST) of 4*L*D device pointers, same order as weights; each is OVERWRITTEN.
+ * dout [B,T,D*H] (NULL = zeros); dhn/dcn [L*D,B,H] (NULL = zeros); dx [B,T,I] (may be NULL);
+ * dh0/dc0 [L*D,B,H] are outputs (and serve as the recurrent accumulators). */
+int dlio_rnn_bwd(int kind, int L, int D, int B, int T, int I, int H, const float *const *weights,
+                 const float *x, const float *drop_mask, const float *dout, const float *dhn,
+                 const float *dcn, const float *reserve, float *const *grads, float *dx, float *dh0,
+                 float *dc0, float *scratch, size_t scratch_floats, void *stream);
+size_t dlio_rnn_bwd_scratch_floats(int kind, int L, int D, int B, int T, int I, int H);
+
+
+/* ------------------------------------------------------------------ optimizer
+ * Fused Adam with L2 weight decay over a flat fp32 arena (torch.optim.Adam semantics; the reference builds it
+ * at deeplio/models/optimizer.py:10): g = grad*grad_scale + wd*p; m,v moments; bias-corrected update.
+ * `step` is the 1-based step count. */
+int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPLIO_B200_H */

@@ -1,0 +1,280 @@
+"""Per-kernel numerics: each C-ABI op against a plain PyTorch fp32 CPU computation of the same op.
+
+Tolerances (stated per test) are fp32 round-off bounds: the kernels accumulate in fp32 (BN statistics in
+fp64), in a different order than ATen's CPU kernels.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _lib():
+    from deeplio_b200 import _lib as L
+    return L
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_padded_nhwc(x, ph, pw, c_pad=None):
+    """NCHW cpu -> padded NHWC cuda (zero pads / zero extra channels)."""
+    n, c, h, w = x.shape
+    c_pad = c_pad or c
+    out = torch.zeros(n, h + 2 * ph, w + 2 * pw, c_pad)
+    out[:, ph:ph + h, pw:pw + w, :c] = x.permute(0, 2, 3, 1)
+    return out.to(DEV).contiguous()
+
+
+def from_nhwc(t):
+    return t.cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def relerr(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+CONV_CASES = [
+    # n, cin, cout, h, w, (kh, kw), (sh, sw), bias, act
+    (2, 6, 64, 12, 40, (5, 7), (1, 2), True, 1),
+    (2, 64, 128, 9, 33, (3, 5), (1, 1), True, 1),
+    (1, 128, 128, 8, 17, (3, 3), (1, 1), False, 0),
+    (2, 32, 48, 10, 21, (3, 3), (2, 2), False, 0),
+    (2, 64, 16, 7, 19, (1, 1), (1, 1), True, 0),
+    (1, 16, 64, 6, 10, (1, 1), (1, 2), False, 0),
+    (1, 256, 80, 5, 9, (3, 5), (1, 2), True, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(case):
+    L = _lib()
+    n, cin, cout, h, w, (kh, kw), (sh, sw), bias, act = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g) if bias else None
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    ref = F.conv2d(x, wt, b, (sh, sw), (ph, pw))
+    if act:
+        ref = F.relu(ref)
+    ho, wo = ref.shape[2:]
+    cin_pad = (cin + 3) // 4 * 4
+    xp = to_padded_nhwc(x, ph, pw, cin_pad)
+    wd = wt.to(DEV)
+    w_ohwi = torch.empty(cout, kh, kw, cin_pad, device=DEV)
+    L.weight_to_ohwi(wd.data_ptr(), cout, cin, kh, kw, cin_pad, w_ohwi.data_ptr(), None, _st())
+    assert torch.equal(w_ohwi[..., :cin].cpu(), wt.permute(0, 2, 3, 1))
+    y = torch.empty(n, ho, wo, cout, device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    xt4, yt4 = L.Tensor4(n, h, w, cin_pad, ph, pw), L.Tensor4(n, ho, wo, cout, 0, 0)
+    cv = L.Conv(kh, kw, sh, sw, ph, pw)
+    L.conv2d_fwd(xt4, xp.data_ptr(), None, w_ohwi.data_ptr(), None, b.to(DEV).data_ptr() if bias else None, cv, act,
+                 yt4, y.data_ptr(), stats.data_ptr(), _st())
+    got = from_nhwc(y)
+    assert relerr(got, ref) < 2e-6                                   # fp32 accumulation-order noise
+    s = stats.cpu()
+    assert torch.allclose(s[:cout], ref.double().sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(s[cout:], (ref.double() ** 2).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+
+    # backward (no activation in the backward test: dy is the gradient at the conv output)
+    dy = torch.randn(n, cout, ho, wo, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, (sh, sw), (ph, pw)).backward(dy)
+    dyd = to_padded_nhwc(dy, 0, 0)
+    dx = torch.empty(n, h, w, cin_pad, device=DEV)
+    L.conv2d_bwd_data(yt4, dyd.data_ptr(), None, w_ohwi.data_ptr(), None, cv, L.Tensor4(n, h, w, cin_pad, 0, 0),
+                      dx.data_ptr(), _st())
+    assert relerr(from_nhwc(dx)[:, :cin], xr.grad) < 3e-6
+    dw_ohwi = torch.empty(cout, kh, kw, cin_pad, device=DEV)
+    L.conv2d_bwd_weight(xt4, xp.data_ptr(), None, yt4, dyd.data_ptr(), None, cv, dw_ohwi.data_ptr(), _st())
+    dw = torch.empty(cout, cin, kh, kw, device=DEV)
+    L.weight_grad_to_oihw(dw_ohwi.data_ptr(), cout, cin, kh, kw, cin_pad, dw.data_ptr(), _st())
+    assert relerr(dw.cpu(), wr.grad) < 1e-5                          # split-K atomics: order varies
+
+
+@pytest.mark.parametrize("cfg", [
+    # c, h, w, pre_relu, relu, pool, ceil, res_mode
+    (64, 9, 20, True, False, (1, 2), True, 0),
+    (128, 10, 33, False, True, (2, 2), True, 0),
+    (48, 8, 16, False, True, (1, 2), False, 0),
+    (64, 7, 11, False, True, None, False, 1),
+    (32, 6, 9, False, True, None, False, 2),
+    (16, 5, 8, False, False, None, False, 0),
+])
+def test_conv_bn_block_vs_torch(cfg):
+    """engine.conv_bn (conv + BN(train) + residual + ReLU + max-pool, forward and backward) against the
+    same block written with torch.nn.functional on the CPU.  Tolerance 2e-5 relative (BN divides by a
+    batch std computed in a different summation order)."""
+    from deeplio_b200 import engine as E
+    c, h, w, pre_relu, relu, pool, ceil, res_mode = cfg
+    n, cin = 2, 32
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = (torch.randn(c, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    b = torch.randn(c, generator=g) * 0.1
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    rm, rv = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5
+    res = torch.randn(n, c, h, w, generator=g) if res_mode else None
+
+    def ref_block(x, wt, b, gamma, beta, res, rm, rv):
+        y = F.conv2d(x, wt, b, 1, 1)
+        if pre_relu:
+            y = F.relu(y)
+        y = F.batch_norm(y, rm, rv, gamma, beta, True, 0.1, 1e-5)
+        if res_mode == 1:
+            y = y + res
+        if relu:
+            y = F.relu(y)
+        if res_mode == 2:
+            y = y + res
+        if pool:
+            y = F.max_pool2d(y, 3, pool, 1, ceil_mode=ceil)
+        return y
+    leaves = [t.clone().requires_grad_(True) for t in (x, wt, b, gamma, beta)] + ([res.clone().requires_grad_(True)] if res_mode else [None])
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = ref_block(*leaves, rm_ref, rv_ref)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+
+    params = {"cv.weight": wt.to(DEV), "cv.bias": b.to(DEV), "bn.weight": gamma.to(DEV), "bn.bias": beta.to(DEV)}
+    bufs = {"bn.running_mean": rm.to(DEV), "bn.running_var": rv.to(DEV),
+            "bn.num_batches_tracked": torch.zeros((), dtype=torch.long, device=DEV)}
+    run = E.Run(params, bufs, torch.device(DEV), True, True)
+    xa = E.Act(n, h, w, cin, 1, 1, t=to_padded_nhwc(x, 1, 1))
+    ra = E.Act(n, h, w, c, 0, 0, t=to_padded_nhwc(res, 0, 0)) if res_mode else None
+    out = E.conv_bn(run, xa, "cv", "bn", (1, 1), pre_relu=pre_relu, relu=relu, pool=pool, ceil=ceil, res=ra,
+                    res_mode=res_mode, out_pad=(1, 2))
+    got = from_nhwc(out.t[:, 1:1 + out.h, 2:2 + out.w])
+    assert got.shape == ref.shape
+    assert relerr(got, ref.detach()) < 2e-5
+    assert out.t[:, 0].abs().max().item() == 0 and out.t[:, :, :2].abs().max().item() == 0   # zero pads
+    assert torch.allclose(bufs["bn.running_mean"].cpu(), rm_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bufs["bn.running_var"].cpu(), rv_ref, rtol=1e-5, atol=1e-6)
+    assert int(bufs["bn.num_batches_tracked"]) == 1
+    run.agrad[id(out)] = to_padded_nhwc(dout, 0, 0)
+    run.backward()
+    tol = 5e-5
+    assert relerr(from_nhwc(run.agrad[id(xa)]), leaves[0].grad) < tol
+    assert relerr(run.pgrad["cv.weight"].cpu(), leaves[1].grad) < tol
+    assert (run.pgrad["cv.bias"].cpu() - leaves[2].grad).abs().max() < tol * leaves[1].grad.abs().max() * 10
+    assert relerr(run.pgrad["bn.weight"].cpu(), leaves[3].grad) < tol
+    assert relerr(run.pgrad["bn.bias"].cpu(), leaves[4].grad) < tol
+    if res_mode:
+        assert relerr(from_nhwc(run.agrad[id(ra)]), leaves[5].grad) < tol
+
+
+def test_bn_eval_mode_uses_running_stats():
+    from deeplio_b200 import engine as E
+    n, cin, c, h, w = 2, 16, 32, 6, 10
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(c, cin, 3, 3, generator=g) * 0.1
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    rm, rv = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5
+    ref = F.relu(F.batch_norm(F.conv2d(x, wt, None, 1, 1), rm.clone(), rv.clone(), gamma, beta, False, 0.1, 1e-5))
+    params = {"cv.weight": wt.to(DEV), "bn.weight": gamma.to(DEV), "bn.bias": beta.to(DEV)}
+    bufs = {"bn.running_mean": rm.to(DEV), "bn.running_var": rv.to(DEV)}
+    run = E.Run(params, bufs, torch.device(DEV), False, False)
+    out = E.conv_bn(run, E.Act(n, h, w, cin, 1, 1, t=to_padded_nhwc(x, 1, 1)), "cv", "bn")
+    assert relerr(from_nhwc(out.t), ref) < 1e-5
+    assert torch.equal(bufs["bn.running_mean"].cpu(), rm)
+
+
+@pytest.mark.parametrize("m,n,k,act", [(16, 128, 512, "leaky_relu"), (240, 128, 6, "leaky_relu"), (7, 3, 1024, None),
+                                       (16, 4096, 256, None), (33, 130, 257, "sigmoid"), (5, 64, 64, "relu")])
+def test_linear_fwd_bwd(m, n, k, act):
+    from deeplio_b200 import functional as Fn
+    g = torch.Generator().manual_seed(m * 131 + n)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** 0.5, torch.randn(n, generator=g)
+    acts = {None: lambda t: t, "relu": F.relu, "leaky_relu": lambda t: F.leaky_relu(t, 0.01), "sigmoid": torch.sigmoid}
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = acts[act](F.linear(xr, wr, br))
+    dy = torch.randn(m, n, generator=g)
+    ref.backward(dy)
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    got = Fn.linear(xd, wd, bd, act)
+    got.backward(dy.to(DEV))
+    tol = 1e-5   # fp32 dot products of length <= 4096
+    assert relerr(got.detach().cpu(), ref.detach()) < tol
+    assert relerr(xd.grad.cpu(), xr.grad) < tol
+    assert relerr(wd.grad.cpu(), wr.grad) < tol
+    assert relerr(bd.grad.cpu(), br.grad) < tol
+
+
+@pytest.mark.parametrize("kind,B,T,I,H,L_,bi", [("lstm", 3, 7, 6, 128, 2, True), ("gru", 2, 5, 6, 64, 2, True),
+                                                  ("lstm", 9, 3, 40, 32, 1, False), ("gru", 11, 2, 24, 48, 2, False),
+                                                  ("lstm", 2, 2, 256, 1024, 2, True)])
+def test_rnn_matches_torch(kind, B, T, I, H, L_, bi):
+    """Two chained calls with carried state (the IMU net's usage) against nn.LSTM / nn.GRU on the CPU.
+    Tolerance 2e-5 relative: fp32 recurrences, different summation order."""
+    from deeplio_b200 import functional as Fn
+    torch.manual_seed(B * 100 + T)
+    cls = torch.nn.LSTM if kind == "lstm" else torch.nn.GRU
+    ref = cls(I, H, L_, bidirectional=bi, batch_first=True)
+    x1, x2 = torch.randn(B, T, I), torch.randn(B, T, I)
+    x1r, x2r = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    o1, s = ref(x1r)
+    o2, s2 = ref(x2r, s)
+    wsum = torch.randn(B, T, (2 if bi else 1) * H)
+    loss = (o1 * wsum).sum() + (o2 * wsum).sum() + (s2[0] if kind == "lstm" else s2).sum()
+    loss.backward()
+    ws = [p.detach().clone().to(DEV).requires_grad_(True) for p in ref._flat_weights]
+    x1d, x2d = x1.to(DEV).requires_grad_(True), x2.to(DEV).requires_grad_(True)
+    g1, st = Fn.rnn(x1d, None, kind, L_, bi, H, ws)
+    g2, st2 = Fn.rnn(x2d, st, kind, L_, bi, H, ws)
+    wd = wsum.to(DEV)
+    lossd = (g1 * wd).sum() + (g2 * wd).sum() + (st2[0] if kind == "lstm" else st2).sum()
+    lossd.backward()
+    tol = 2e-5
+    assert relerr(g1.detach().cpu(), o1.detach()) < tol
+    assert relerr(g2.detach().cpu(), o2.detach()) < tol
+    assert relerr(x1d.grad.cpu(), x1r.grad) < 10 * tol
+    assert relerr(x2d.grad.cpu(), x2r.grad) < 10 * tol
+    for w, p in zip(ws, ref._flat_weights):
+        assert relerr(w.grad.cpu(), p.grad) < 10 * tol
+
+
+def test_adam_matches_torch():
+    L = _lib()
+    n = 10007
+    g = torch.Generator().manual_seed(5)
+    p0, grads = torch.randn(n, generator=g), [torch.randn(n, generator=g) for _ in range(3)]
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3, weight_decay=1e-4)
+    # arenas are 16-byte aligned slices of a padded buffer
+    pd, m, v = p0.to(DEV).clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step, gr in enumerate(grads, 1):
+        pr.grad = gr.clone()
+        opt.step()
+        gd = gr.to(DEV)
+        L.adam_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-4, step,
+                    1.0, _st())
+    assert (pd.cpu() - pr.detach()).abs().max().item() < 1e-6
+
+
+def test_dropout_mask_statistics_and_repeatability():
+    from deeplio_b200 import functional as Fn
+    torch.manual_seed(123)
+    Fn._drop_counter[0] = 0
+    a = Fn.dropout_mask((1 << 20,), 0.25, torch.device(DEV))
+    Fn._drop_counter[0] = 0
+    b = Fn.dropout_mask((1 << 20,), 0.25, torch.device(DEV))
+    assert torch.equal(a, b)
+    keep = (a > 0).float().mean().item()
+    assert abs(keep - 0.75) < 3e-3
+    assert abs(a.max().item() - 1 / 0.75) < 1e-6
+    c = Fn.dropout_mask((1 << 20,), 0.25, torch.device(DEV))
+    assert not torch.equal(a, c)
+
+
+def test_cpu_tensors_are_rejected():
+    """No CPU fallback: the product path fails loudly instead of computing on the host."""
+    from deeplio_b200 import functional as Fn
+    with pytest.raises(RuntimeError):
+        Fn.linear(torch.randn(2, 4), torch.randn(3, 4))
