@@ -41,6 +41,8 @@ _PROTOS = {
     "dlio_last_error": (C.c_char_p, []),
     "dlio_device_check": (I, [I]),
     "dlio_launch_count": (LL, []),
+    "dlio_profile_enable": (I, [I]),
+    "dlio_profile_read": (I, [I, P, P]),
     "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P]),
     "dlio_conv2d_fwd": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
     "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, P]),
@@ -67,6 +69,7 @@ _PROTOS = {
     "dlio_rnn_bwd_scratch_floats": (SZ, [I, I, I, I, I, I, I]),
     "dlio_rnn_fwd": (I, [I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
     "dlio_rnn_bwd": (I, [I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "dlio_hws_loss": (I, [P, P, P, P, I, F, F, P, P, P, P]),
     "dlio_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
 }
 EXPORTS = sorted(_PROTOS)
@@ -106,6 +109,22 @@ for _name, (_res, _args) in _PROTOS.items():
 rnn_reserve_floats = _lib.dlio_rnn_reserve_floats
 rnn_bwd_scratch_floats = _lib.dlio_rnn_bwd_scratch_floats
 abi_version = _lib.dlio_abi_version
+
+
+PROF_KINDS = ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc", "conv_wgrad_tc")
+
+
+def profile_read():
+    """{kernel class: (total ms, launches)} since the last profile_enable(1)."""
+    out = {}
+    for k, name in enumerate(PROF_KINDS):
+        ms, n = C.c_double(0.0), C.c_longlong(0)
+        rc = _lib.dlio_profile_read(k, C.byref(ms), C.byref(n))
+        if rc != 0:
+            raise DlioError("dlio_profile_read failed (%d): %s" % (rc, last_error()))
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out
 
 
 def ptr(t):

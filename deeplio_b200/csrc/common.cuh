@@ -10,6 +10,15 @@ namespace dlio {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// kernel classes timed by dlio_profile_* (see deeplio_b200.h)
+int prof_begin(int kind, cudaStream_t st);
+void prof_end(int idx, cudaStream_t st);
+struct ProfScope {
+    int idx;
+    cudaStream_t st;
+    ProfScope(int kind, cudaStream_t s) : idx(prof_begin(kind, s)), st(s) {}
+    ~ProfScope() { prof_end(idx, st); }
+};
 
 #define DLIO_CHECK_ARG(cond, ...)            \
     do {                                     \

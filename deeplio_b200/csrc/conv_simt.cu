@@ -383,6 +383,7 @@ extern "C" int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x
     a.out = y_ptr; a.stats = stats; a.p_chunk = 0;
     rc = conv_tc_fwd(a, st);
     if (rc != 0) return rc < 0 ? rc : DLIO_OK;
+    ProfScope prof(DLIO_PROF_CONV_FWD_SIMT, st);
     if (y.ph > 0 || y.pw > 0) DLIO_CUDA(cudaMemsetAsync(y_ptr, 0, a.y.numel() * sizeof(float), st));
     long long M = (long long)y.n * y.h * y.w;
     dim3 grid(ceil_div(M, BM), ceil_div(y.c, BN));
@@ -404,6 +405,7 @@ extern "C" int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const f
     a.cin = dx.c; a.cout = dy.c; a.act = 0;
     a.x_hi = dy_hi; a.x_lo = dy_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = nullptr;
     a.out = dx_ptr; a.stats = nullptr; a.p_chunk = 0;
+    ProfScope prof(DLIO_PROF_CONV_DGRAD_SIMT, st);
     if (dx.ph > 0 || dx.pw > 0) DLIO_CUDA(cudaMemsetAsync(dx_ptr, 0, a.o.numel() * sizeof(float), st));
     long long M = (long long)dx.n * dx.h * dx.w;
     dim3 grid(ceil_div(M, BM), ceil_div(dx.c, BN));
@@ -428,6 +430,7 @@ extern "C" int dlio_conv2d_bwd_weight(dlio_tensor4 x, const float *x_hi, const f
     const int KW = cv.kh * cv.kw * x.c;
     rc = conv_tc_wgrad(a, st);
     if (rc != 0) return rc < 0 ? rc : DLIO_OK;
+    ProfScope prof(DLIO_PROF_CONV_WGRAD_SIMT, st);
     DLIO_CUDA(cudaMemsetAsync(dw, 0, (size_t)dy.c * KW * sizeof(float), st));
     long long P = (long long)dy.n * dy.h * dy.w;
     int tiles = ceil_div(dy.c, BM) * ceil_div(KW, BN);

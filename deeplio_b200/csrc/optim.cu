@@ -60,3 +60,46 @@ extern "C" int dlio_adam_step(float *param, const float *grad, float *exp_avg, f
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
+
+// ------------------------------------------------------------------ pose loss (HWSLoss, frame-to-frame part)
+namespace dlio {
+// loss = mse(pos, gt_pos) * exp(-sx) + sx + mse(ori, gt_ori) * exp(-sq) + sq   (losses.py:68-86, "local" terms)
+// single block: the tensors are [B, S, 3]
+__global__ void __launch_bounds__(256) hws_loss_kernel(const float *__restrict__ pos, const float *__restrict__ ori,
+                                                       const float *__restrict__ gpos, const float *__restrict__ gori,
+                                                       int n, float sx, float sq, float *loss, float *dpos, float *dori) {
+    __shared__ float red[2][8];
+    const float wx = expf(-sx), wq = expf(-sq);
+    float st = 0.f, sw = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float a = pos[i] - gpos[i], b = ori[i] - gori[i];
+        st += a * a;
+        sw += b * b;
+        if (dpos) dpos[i] = 2.f * a * wx / (float)n;
+        if (dori) dori[i] = 2.f * b * wq / (float)n;
+    }
+    st = warp_sum(st);
+    sw = warp_sum(sw);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = st;
+        red[1][threadIdx.x >> 5] = sw;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) {
+            a += red[0][w];
+            b += red[1][w];
+        }
+        loss[0] = a / (float)n * wx + sx + b / (float)n * wq + sq;
+    }
+}
+}  // namespace dlio
+
+extern "C" int dlio_hws_loss(const float *pos, const float *ori, const float *gt_pos, const float *gt_ori, int n,
+                             float sx, float sq, float *loss, float *dpos, float *dori, void *stream) {
+    DLIO_CHECK_ARG(pos && ori && gt_pos && gt_ori && loss && n > 0, "hws_loss: bad argument");
+    dlio::hws_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pos, ori, gt_pos, gt_ori, n, sx, sq, loss, dpos, dori);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}

@@ -219,3 +219,25 @@ def rnn(x, state, kind, num_layers, bidirectional, hidden_size, weights, dropout
         mask = dropout_mask((num_layers - 1, B, T, D * hidden_size), dropout_p, x.device)
     out, hn, cn = _Rnn.apply(x, h0, c0, k, num_layers, D, hidden_size, mask, *weights)
     return out, ((hn, cn) if k == 0 else hn)
+
+
+class _HwsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, ori, gt_pos, gt_ori, sx, sq):
+        pos, ori, gt_pos, gt_ori = (t.contiguous() for t in (pos, ori, gt_pos, gt_ori))
+        loss = torch.empty((1,), device=pos.device, dtype=torch.float32)
+        dpos, dori = torch.empty_like(pos), torch.empty_like(ori)
+        L.hws_loss(ptr(pos), ptr(ori), ptr(gt_pos), ptr(gt_ori), pos.numel(), sx, sq, ptr(loss), ptr(dpos), ptr(dori),
+                   _stream())
+        ctx.save_for_backward(dpos, dori)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, d):
+        dpos, dori = ctx.saved_tensors
+        return mul(dpos, d.expand_as(dpos).contiguous()), mul(dori, d.expand_as(dori).contiguous()), None, None, None, None
+
+
+def hws_loss(pos, ori, gt_pos, gt_ori, sx=0.0, sq=-3.0):
+    """Frame-to-frame HWSLoss with fixed weights (losses.py:68-86): one launch for the loss and its gradient."""
+    return _HwsLoss.apply(pos, ori, gt_pos, gt_ori, float(sx), float(sq))

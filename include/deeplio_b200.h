@@ -65,6 +65,15 @@ const char *dlio_last_error(void);                 /* host string, thread-local 
 int dlio_device_check(int device);                 /* DLIO_OK iff compute capability 10.x */
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 long long dlio_launch_count(void);
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, every launch of a profiled class
+ * is bracketed by CUDA events on its stream.  dlio_profile_enable clears earlier records;
+ * dlio_profile_read synchronises the recorded events of one class and returns their summed duration. */
+typedef enum {
+    DLIO_PROF_CONV_FWD_SIMT = 0, DLIO_PROF_CONV_DGRAD_SIMT = 1, DLIO_PROF_CONV_WGRAD_SIMT = 2,
+    DLIO_PROF_CONV_FWD_TC = 3, DLIO_PROF_CONV_DGRAD_TC = 4, DLIO_PROF_CONV_WGRAD_TC = 5
+} dlio_prof_kind;
+int dlio_profile_enable(int on);
+int dlio_profile_read(int kind, double *total_ms, long long *launches);
 
 /* ------------------------------------------------------------------ input staging
  * Replaces imgs.reshape(b*s, t*c, h, w) (lidar_feat_nets.py:216-218): gathers the strided
@@ -232,6 +241,11 @@ size_t dlio_rnn_bwd_scratch_floats(int kind, int L, int D, int B, int T, int I, 
 int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    float grad_scale, void *stream);
+/* Frame-to-frame part of HWSLoss (deeplio/losses/losses.py:68-86) with fixed sx, sq, and its gradient:
+ * loss = mse(pos, gt_pos) e^-sx + sx + mse(ori, gt_ori) e^-sq + sq over n = B*S*3 elements; dpos / dori
+ * (optional) receive d loss / d pos, d loss / d ori. */
+int dlio_hws_loss(const float *pos, const float *ori, const float *gt_pos, const float *gt_ori, int n,
+                  float sx, float sq, float *loss, float *dpos, float *dori, void *stream);
 
 #ifdef __cplusplus
 }
