@@ -45,7 +45,7 @@ _PROTOS = {
     "dlio_profile_read": (I, [I, P, P]),
     "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P]),
     "dlio_conv2d_fwd": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
-    "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, P]),
+    "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, P, P, Conv, Tensor4, P, P]),
     "dlio_conv2d_bwd_weight": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
     "dlio_weight_to_ohwi": (I, [P, I, I, I, I, I, P, P, P]),
     "dlio_weight_grad_to_oihw": (I, [P, I, I, I, I, I, P, P]),

@@ -72,21 +72,20 @@ __device__ __forceinline__ float tf32_rna(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
-// split v = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits zero)
+// TF32 operand split used by the tcgen05 kernels: the "hi" plane keeps the FULL fp32 value (kind::tf32 reads
+// the top 19 bits of each 32-bit container, i.e. trunc_tf32(v)); the "lo" plane holds the residual
+// v - trunc_tf32(v), itself rounded to TF32.  hi*hi + lo*hi + hi*lo then reproduces the fp32 product to ~2^-20.
 __device__ __forceinline__ void tf32_split(float v, float &hi, float &lo) {
-    hi = tf32_rna(v);
-    lo = v - hi;  // exact in fp32; the tensor core reads its top 19 bits
+    hi = v;
+    lo = tf32_rna(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
 }
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
-__device__ __forceinline__ float4 ld4_sum(const float *hi, const float *lo, size_t off) {
-    float4 v = ld4(hi + off);
-    if (lo) v = add4(v, ld4(lo + off));
-    return v;
-}
+// fp32 value of a (possibly split) tensor: the hi plane already holds it
+__device__ __forceinline__ float4 ld4_sum(const float *hi, const float *, size_t off) { return ld4(hi + off); }
 __device__ __forceinline__ void st4_split(float *hi, float *lo, size_t off, const float4 &v) {
     if (lo) {
         float4 h, l;

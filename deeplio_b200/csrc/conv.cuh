@@ -1,0 +1,25 @@
+// Argument block shared by the generic (conv_simt.cu) and tcgen05 (conv_tc.cu) convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dlio {
+
+struct ConvArgs {
+    Geo x, y;            // x: conv input geometry, y: conv output geometry (dy for backward)
+    int kh, kw, sh, sw, ph, pw;
+    int cin, cout;
+    int act;
+    const float *x_hi, *x_lo;
+    const float *w_hi, *w_lo;
+    const float *bias;
+    float *out;          // y (fwd), dx (dgrad), dw (wgrad)
+    double *stats;
+    Geo o;               // geometry of `out` for dgrad (dx)
+    long long p_chunk;   // wgrad: pixels per z-slice
+};
+
+// conv_tc.cu: return 1 if the tcgen05 kernel took the problem, 0 if it does not apply, < 0 on error
+int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st);
+int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st);
+
+}  // namespace dlio

@@ -8,24 +8,11 @@
 // Tiling: 64 x 64 output tile per CTA, K step 16, 256 threads, 4 x 4 register tile per thread,
 // operands staged in shared memory with a register prefetch of the next K step.
 #include "common.cuh"
+#include "conv.cuh"
 
 namespace dlio {
 
 constexpr int BM = 64, BN = 64, BK = 16, NT = 256, LDS = BM + 4;
-
-struct ConvArgs {
-    Geo x, y;            // x: conv input geometry, y: conv output geometry (dy for backward)
-    int kh, kw, sh, sw, ph, pw;
-    int cin, cout;
-    int act;
-    const float *x_hi, *x_lo;
-    const float *w_hi, *w_lo;
-    const float *bias;
-    float *out;          // y (fwd), dx (dgrad), dw (wgrad)
-    double *stats;
-    Geo o;               // geometry of `out` for dgrad (dx)
-    long long p_chunk;   // wgrad: pixels per z-slice
-};
 
 __device__ __forceinline__ void mma_tile(const float (*As)[LDS], const float (*Bs)[LDS], float (&acc)[4][4],
                                          int ty, int tx) {
@@ -350,10 +337,6 @@ __global__ void weight_flip_transpose_kernel(const float *__restrict__ w, int co
     }
 }
 
-// implemented in conv_tc.cu; returns 1 if it took the problem, 0 if not applicable, <0 on error
-int conv_tc_fwd(const ConvArgs &a, cudaStream_t st);
-int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st);
-
 static int check_conv(const dlio_tensor4 &x, const dlio_tensor4 &y, const dlio_conv &cv) {
     DLIO_CHECK_ARG(valid_t4(x) && valid_t4(y), "conv: bad tensor descriptor");
     DLIO_CHECK_ARG(cv.kh > 0 && cv.kw > 0 && cv.sh > 0 && cv.sw > 0 && cv.ph >= 0 && cv.pw >= 0, "conv: bad conv descriptor");
@@ -381,7 +364,7 @@ extern "C" int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x
     a.cin = x.c; a.cout = y.c; a.act = act;
     a.x_hi = x_hi; a.x_lo = x_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias;
     a.out = y_ptr; a.stats = stats; a.p_chunk = 0;
-    rc = conv_tc_fwd(a, st);
+    rc = conv_tc_fwd(a, DLIO_PROF_CONV_FWD_TC, st);
     if (rc != 0) return rc < 0 ? rc : DLIO_OK;
     ProfScope prof(DLIO_PROF_CONV_FWD_SIMT, st);
     if (y.ph > 0 || y.pw > 0) DLIO_CUDA(cudaMemsetAsync(y_ptr, 0, a.y.numel() * sizeof(float), st));
@@ -393,11 +376,23 @@ extern "C" int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x
 }
 
 extern "C" int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const float *dy_lo, const float *w_hi,
-                                    const float *w_lo, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, void *stream) {
+                                    const float *w_lo, const float *wt_hi, const float *wt_lo, dlio_conv cv,
+                                    dlio_tensor4 dx, float *dx_ptr, void *stream) {
     int rc = check_conv(dx, dy, cv);
     if (rc) return rc;
     DLIO_CHECK_ARG(dy_hi && w_hi && dx_ptr, "conv_bwd_data: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (wt_hi && wt_lo && dy_lo) {
+        // dgrad as a stride-1 convolution of the padded dy with the flipped / transposed weights (tcgen05 path)
+        ConvArgs t;
+        t.x = Geo(dy); t.y = Geo(dx); t.o = Geo(dx);
+        t.kh = cv.kh; t.kw = cv.kw; t.sh = cv.sh; t.sw = cv.sw; t.ph = cv.kh - 1 - cv.ph; t.pw = cv.kw - 1 - cv.pw;
+        t.cin = dy.c; t.cout = dx.c; t.act = 0;
+        t.x_hi = dy_hi; t.x_lo = dy_lo; t.w_hi = wt_hi; t.w_lo = wt_lo; t.bias = nullptr;
+        t.out = dx_ptr; t.stats = nullptr; t.p_chunk = 0;
+        rc = conv_tc_fwd(t, DLIO_PROF_CONV_DGRAD_TC, st);
+        if (rc != 0) return rc < 0 ? rc : DLIO_OK;
+    }
     ConvArgs a;
     a.x = Geo(dx); a.x.ph = 0; a.x.pw = 0;  // logical extent only; addressing of dx goes through a.o
     a.y = Geo(dy); a.o = Geo(dx);

@@ -17,6 +17,12 @@ from ._lib import ptr
 
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+# tcgen05 (3xTF32) convolution path: stride-1 convolutions whose input has a multiple of 32 channels
+USE_TC = True
+
+
+def tc_ok(cin, cout, stride):
+    return USE_TC and tuple(stride) == (1, 1) and cin % 32 == 0 and cout % 16 == 0
 
 
 def stream():
@@ -36,12 +42,15 @@ def pool_out(n, s, ceil_mode):
 
 class Act:
     """Padded NHWC fp32 activation: memory [n][h+2ph][w+2pw][c], zero pads."""
-    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "needs_grad")
+    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "lo", "needs_grad")
 
-    def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True):
+    def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True, split=False, lo=None):
+        """``split``: also allocate the low-order TF32 plane ``lo`` = x - trunc_tf32(x).  ``t`` always holds the
+        full fp32 values (the tensor core reads their top 19 bits), so every other consumer just reads ``t``."""
         self.n, self.h, self.w, self.c, self.ph, self.pw = n, h, w, c, ph, pw
         self.t = t if t is not None else torch.empty((n, h + 2 * ph, w + 2 * pw, c), device=device,
                                                      dtype=torch.float32)
+        self.lo = lo if lo is not None else (torch.empty_like(self.t) if split else None)
         self.needs_grad = needs_grad
 
     @property
@@ -132,12 +141,14 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     ho, wo = (x.h + 2 * cph - kh) // sh + 1, (x.w + 2 * cpw - kw) // sw + 1
     cv = L.Conv(kh, kw, sh, sw, cph, cpw)
     n = x.n
+    fwd_tc = x.lo is not None and tc_ok(cin_pad, cout, stride) and x.ph >= cph and x.pw >= cpw
     w_ohwi = run.empty(cout, kh, kw, cin_pad)
-    L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), None, st)
+    w_lo = torch.empty_like(w_ohwi) if fwd_tc else None    # low-order TF32 plane of the weights
+    L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), ptr(w_lo), st)
     y = Act(n, ho, wo, cout, device=run.device)
     stats = run.zeros(2 * cout, dtype=torch.float64) if run.training else None
-    L.conv2d_fwd(x.t4, ptr(x.t), None, ptr(w_ohwi), None, ptr(b), cv, L.ACT_RELU if pre_relu else L.ACT_NONE,
-                 y.t4, ptr(y.t), ptr(stats), st)
+    L.conv2d_fwd(x.t4, ptr(x.t), ptr(x.lo), ptr(w_ohwi), ptr(w_lo), ptr(b), cv,
+                 L.ACT_RELU if pre_relu else L.ACT_NONE, y.t4, ptr(y.t), ptr(stats), st)
     bnv = run.empty(4, cout)  # mean, invstd, scale, shift
     count = n * ho * wo
     L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), BN_MOMENTUM, BN_EPS,
@@ -157,12 +168,13 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     else:
         oh, ow = (pool_out(ho, pool[0], ceil), pool_out(wo, pool[1], ceil)) if pool else (ho, wo)
         if out is None:
-            out = Act(n, oh, ow, out_c or cout, out_pad[0], out_pad[1], device=run.device)
+            oc = out_c or cout
+            out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, split=USE_TC and oc % 32 == 0)
         assert out.h == oh and out.w == ow and out.n == n
         if pool and run.record:
             idx = run.empty(n, oh, ow, cout, dtype=torch.uint8)
         L.bn_act_pool_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), res.t4 if res is not None else dummy,
-                          ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), None, ptr(idx), st)
+                          ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(idx), st)
         result = out
     if not run.record:
         return result
@@ -189,11 +201,15 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                                  res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
                                  bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
                                  ptr(sums), st)
-        dy = run.empty(n, ho, wo, cout)
+        # dgrad on the tensor cores: dy is produced in padded split form and convolved with the flipped weights
+        dgrad_tc = x.needs_grad and tc_ok(cout, cin_pad, stride)
+        dya = Act(n, ho, wo, cout, kh - 1 - cph if dgrad_tc else 0, kw - 1 - cpw if dgrad_tc else 0,
+                  device=run.device, split=dgrad_tc)
+        dy = dya.t
         dgb = run.empty(2, cout)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
         L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
-                       1 if pre_relu else 0, 1 if run.training else 0, y.t4, ptr(dy), None, ptr(dgb[0]),
+                       1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dy), ptr(dya.lo), ptr(dgb[0]),
                        ptr(dgb[1]), ptr(dbs), st)
         del dz
         run.pgrad[bname + ".weight"] = dgb[0]
@@ -203,13 +219,17 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             L.f64_to_f32(ptr(dbs), ptr(db), cout, st)
             run.pgrad[cname + ".bias"] = db
         dw_ohwi = run.empty(cout, kh, kw, cin_pad)
-        L.conv2d_bwd_weight(x.t4, ptr(x.t), None, y.t4, ptr(dy), None, cv, ptr(dw_ohwi), st)
+        L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo), dya.t4, ptr(dy), ptr(dya.lo), cv, ptr(dw_ohwi), st)
         dw = torch.empty_like(w)
         L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
         run.pgrad[cname + ".weight"] = dw
         if x.needs_grad:
-            run.add_grad(x, lambda buf: L.conv2d_bwd_data(y.t4, ptr(dy), None, ptr(w_ohwi), None, cv,
-                                                          x.t4_unpadded, ptr(buf), st))
+            wt_hi = wt_lo = None
+            if dgrad_tc:
+                wt_hi, wt_lo = torch.empty_like(w_ohwi), torch.empty_like(w_ohwi)
+                L.weight_flip_transpose(ptr(w_ohwi), cout, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
+            run.add_grad(x, lambda buf: L.conv2d_bwd_data(dya.t4, ptr(dy), ptr(dya.lo), ptr(w_ohwi), ptr(w_lo),
+                                                          ptr(wt_hi), ptr(wt_lo), cv, x.t4_unpadded, ptr(buf), st))
 
     run.tape.append(bwd)
     run.keep.append((x, y, out, res))
@@ -227,8 +247,8 @@ def se_layer(run, x, prefix, out_pad=(0, 0)):
     L.linear_fwd(ptr(m), c, ptr(w1), None, n, cr, c, L.ACT_RELU, ptr(hid), cr, st)
     gate = run.empty(n, c)
     L.linear_fwd(ptr(hid), cr, ptr(w2), None, n, c, cr, L.ACT_SIGMOID, ptr(gate), c, st)
-    out = Act(n, x.h, x.w, c, out_pad[0], out_pad[1], device=run.device)
-    L.channel_scale_fwd(x.t4, ptr(x.t), ptr(gate), out.t4, ptr(out.t), None, st)
+    out = Act(n, x.h, x.w, c, out_pad[0], out_pad[1], device=run.device, split=USE_TC and c % 32 == 0)
+    L.channel_scale_fwd(x.t4, ptr(x.t), ptr(gate), out.t4, ptr(out.t), ptr(out.lo), st)
     if not run.record:
         return out
 
@@ -256,10 +276,10 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
     """MaxPool2d(3, stride, padding=1) on its own (PointSeg pools, pointseg_net.py:28,35,43,50)."""
     st = stream()
     oh, ow = pool_out(x.h, stride[0], ceil), pool_out(x.w, stride[1], ceil)
-    out = Act(x.n, oh, ow, x.c, out_pad[0], out_pad[1], device=run.device)
+    out = Act(x.n, oh, ow, x.c, out_pad[0], out_pad[1], device=run.device, split=USE_TC and x.c % 32 == 0)
     bp = L.BnPool(0, 0, 3, stride[0], stride[1], 0)
     idx = run.empty(x.n, oh, ow, x.c, dtype=torch.uint8) if run.record else None
-    L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), None, ptr(idx), st)
+    L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(idx), st)
     if not run.record:
         return out
 

@@ -90,20 +90,23 @@ int dlio_pack_input(const float *src, long long sn, long long st, long long sc, 
  * forward:  y = act(conv(x, w) + bias); optionally accumulates per-channel sum / sum-of-squares of y
  *           over the logical (n,h,w) extent into stats[0:cout] / stats[cout:2*cout] (fp64, caller
  *           zeroes) -- the batch statistics nn.BatchNorm2d needs (train mode).
- *           x_lo / w_lo: optional low-order TF32 split planes.  When all of (x_lo, w_lo) are given,
- *           the stride is 1, cin % 32 == 0 and cout % 64 == 0, x.ph/pw == conv pads and y has x's
- *           geometry, the tcgen05 (3xTF32) implicit-GEMM kernel is used; otherwise the generic fp32
- *           kernel runs on x (+ x_lo if given) and w.
+ *           x_lo / w_lo: optional low-order TF32 planes (v - trunc_tf32(v); the *_hi planes always hold the
+ *           full fp32 values).  When both are given, the stride is 1, cin % 32 == 0, cout % 16 == 0, the
+ *           kernel is "same" (k = 2*pad + 1) and x is stored with pads >= the conv pads, the tcgen05
+ *           (3xTF32) implicit-GEMM kernel is used; otherwise the generic fp32 kernel runs on x_hi and w_hi.
  */
 int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x_lo,
                     const float *w_hi, const float *w_lo, const float *bias,
                     dlio_conv cv, int act,
                     dlio_tensor4 y, float *y_ptr, double *stats, void *stream);
 
-/* dgrad: dx = conv_transpose(dy, w).  dx pads are written as zeros when dx is padded. */
+/* dgrad: dx = conv_transpose(dy, w).  dx pads are written as zeros when dx is padded.
+ * wt_hi / wt_lo (optional): the flipped / transposed weights of dlio_weight_flip_transpose as TF32 split
+ * planes; when they and dy_lo are given, the stride is 1, dy is stored with pads >= (kh-1-ph, kw-1-pw) and
+ * cout % 32 == 0, cin % 16 == 0, the dgrad runs on the tcgen05 kernel as a convolution of dy with wt. */
 int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const float *dy_lo,
-                         const float *w_hi, const float *w_lo, dlio_conv cv,
-                         dlio_tensor4 dx, float *dx_ptr, void *stream);
+                         const float *w_hi, const float *w_lo, const float *wt_hi, const float *wt_lo,
+                         dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, void *stream);
 
 /* wgrad: dw[cout][kh][kw][cin] = sum_{n,h,w} dy * x (overwrites dw). */
 int dlio_conv2d_bwd_weight(dlio_tensor4 x, const float *x_hi, const float *x_lo,
@@ -144,8 +147,7 @@ typedef struct {
 
 /* out[n,ho,wo,c_off+c] = maxpool(act(scale[c]*y + shift[c] (+res)) (+res)); writes out's pads as zeros for
  * the channel range.  scale == shift == NULL means identity (plain max-pool / copy into a padded tensor).
- * out_lo (optional): TF32 split planes (out_hi = rna_tf32(v), out_lo = v - out_hi); when out_lo is NULL
- * out_hi receives the full fp32 value.  pool_idx (uint8 [n,ho,wo,c], required when pooling is
+ * out_lo (optional): low-order TF32 plane, v - trunc_tf32(v) (out_hi always receives the full fp32 value).  pool_idx (uint8 [n,ho,wo,c], required when pooling is
  * differentiated): window-relative arg-max, first maximum wins (torch tie-break). */
 int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                          dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,

@@ -88,14 +88,95 @@ def test_conv_fwd_dgrad_wgrad(case):
     F.conv2d(xr, wr, None, (sh, sw), (ph, pw)).backward(dy)
     dyd = to_padded_nhwc(dy, 0, 0)
     dx = torch.empty(n, h, w, cin_pad, device=DEV)
-    L.conv2d_bwd_data(yt4, dyd.data_ptr(), None, w_ohwi.data_ptr(), None, cv, L.Tensor4(n, h, w, cin_pad, 0, 0),
-                      dx.data_ptr(), _st())
+    L.conv2d_bwd_data(yt4, dyd.data_ptr(), None, w_ohwi.data_ptr(), None, None, None, cv,
+                      L.Tensor4(n, h, w, cin_pad, 0, 0), dx.data_ptr(), _st())
     assert relerr(from_nhwc(dx)[:, :cin], xr.grad) < 3e-6
     dw_ohwi = torch.empty(cout, kh, kw, cin_pad, device=DEV)
     L.conv2d_bwd_weight(xt4, xp.data_ptr(), None, yt4, dyd.data_ptr(), None, cv, dw_ohwi.data_ptr(), _st())
     dw = torch.empty(cout, cin, kh, kw, device=DEV)
     L.weight_grad_to_oihw(dw_ohwi.data_ptr(), cout, cin, kh, kw, cin_pad, dw.data_ptr(), _st())
     assert relerr(dw.cpu(), wr.grad) < 1e-5                          # split-K atomics: order varies
+
+
+def split_padded(L, x, ph, pw):
+    """NCHW cpu -> (full, lo) padded NHWC planes, produced by the library's own copy kernel."""
+    n, c, h, w = x.shape
+    src = to_padded_nhwc(x, 0, 0)
+    hi = torch.empty(n, h + 2 * ph, w + 2 * pw, c, device=DEV)
+    lo = torch.empty_like(hi)
+    t_src, t_dst = L.Tensor4(n, h, w, c, 0, 0), L.Tensor4(n, h, w, c, ph, pw)
+    L.bn_act_pool_fwd(t_src, src.data_ptr(), None, None, t_src, None, L.BnPool(0, 0, 1, 1, 1, 0), t_dst, hi.data_ptr(),
+                      lo.data_ptr(), None, _st())
+    return hi, lo
+
+
+TC_CASES = [
+    # n, cin, cout, h, w, (kh, kw), bias, act, extra tensor pad
+    (2, 64, 128, 9, 33, (3, 5), True, 1, 0),
+    (1, 128, 128, 8, 17, (3, 3), False, 0, 0),
+    (2, 32, 64, 7, 19, (1, 1), True, 0, 1),
+    (1, 256, 192, 5, 9, (3, 3), True, 1, 0),
+    (2, 128, 256, 6, 11, (3, 3), False, 0, 0),
+    (3, 512, 512, 17, 65, (3, 3), True, 1, 0),
+    (1, 64, 48, 4, 6, (3, 3), False, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_fwd_and_dgrad(case):
+    """tcgen05 3xTF32 implicit-GEMM convolution against F.conv2d in fp32.  Tolerance 1e-5 relative to the largest
+    output: the split drops the lo*lo term (~2^-20 per product) and the tensor core's truncating accumulation
+    adds ~1e-9 * K (measured 3.6e-6 at K = 4608, the same level as the fp32 CUDA-core kernel)."""
+    L = _lib()
+    n, cin, cout, h, w, (kh, kw), bias, act, extra = case
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g) if bias else None
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    ref = F.conv2d(x, wt, b, 1, (ph, pw))
+    if act:
+        ref = F.relu(ref)
+    tph, tpw = ph + extra, pw + extra
+    x_hi, x_lo = split_padded(L, x, tph, tpw)
+    assert torch.equal(x_hi[:, tph:tph + h, tpw:tpw + w].cpu(), x.permute(0, 2, 3, 1))      # hi plane = full fp32
+    wd = wt.to(DEV)
+    w_hi, w_lo = torch.empty(cout, kh, kw, cin, device=DEV), torch.empty(cout, kh, kw, cin, device=DEV)
+    L.weight_to_ohwi(wd.data_ptr(), cout, cin, kh, kw, cin, w_hi.data_ptr(), w_lo.data_ptr(), _st())
+    y = torch.full((n, h, w, cout), float("nan"), device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    xt4, yt4 = L.Tensor4(n, h, w, cin, tph, tpw), L.Tensor4(n, h, w, cout, 0, 0)
+    cv = L.Conv(kh, kw, 1, 1, ph, pw)
+    L.profile_enable(1)
+    L.conv2d_fwd(xt4, x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
+                 b.to(DEV).data_ptr() if bias else None, cv, act, yt4, y.data_ptr(), stats.data_ptr(), _st())
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert "conv_fwd_tc" in prof and "conv_fwd_simt" not in prof, prof      # the tensor-core kernel really ran
+    got = from_nhwc(y)
+    assert relerr(got, ref) < 1e-5
+    s = stats.cpu()   # the truncating accumulation biases every output the same way, so sums keep ~1e-5 of it
+    assert torch.allclose(s[:cout], ref.double().sum((0, 2, 3)), rtol=5e-5, atol=1e-4)
+    assert torch.allclose(s[cout:], (ref.double() ** 2).sum((0, 2, 3)), rtol=5e-5, atol=1e-4)
+
+    # dgrad: convolution of the padded dy with the flipped / transposed weights
+    dy = torch.randn(n, cout, h, w, generator=g)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, wt, None, 1, (ph, pw)).backward(dy)
+    dy_hi, dy_lo = split_padded(L, dy, kh - 1 - ph, kw - 1 - pw)
+    wt_hi, wt_lo = torch.empty(cin, kh, kw, cout, device=DEV), torch.empty(cin, kh, kw, cout, device=DEV)
+    L.weight_flip_transpose(w_hi.data_ptr(), cout, cin, kh, kw, wt_hi.data_ptr(), wt_lo.data_ptr(), _st())
+    dx = torch.full((n, h, w, cin), float("nan"), device=DEV)
+    L.profile_enable(1)
+    L.conv2d_bwd_data(L.Tensor4(n, h, w, cout, kh - 1 - ph, kw - 1 - pw), dy_hi.data_ptr(), dy_lo.data_ptr(),
+                      w_hi.data_ptr(), w_lo.data_ptr(), wt_hi.data_ptr(), wt_lo.data_ptr(), cv,
+                      L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), _st())
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert ("conv_dgrad_tc" if cout % 32 == 0 else "conv_dgrad_simt") in prof, prof
+    assert relerr(from_nhwc(dx), xr.grad) < 1e-5
 
 
 @pytest.mark.parametrize("cfg", [
