@@ -297,7 +297,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map: rows x cols (cols contiguous), box box_rows x 32, 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap *m, const float *base, long long rows, long long cols, int box_rows) {
+static int make_map(CUtensorMap *m, const float *base, long long rows, long long cols, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -308,7 +309,7 @@ static int make_map(CUtensorMap *m, const float *base, long long rows, long long
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r, rows, cols, box_rows);
@@ -369,6 +370,213 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     return 1;
 }
 
-int conv_tc_wgrad(const ConvArgs &, cudaStream_t) { return 0; }
+// ==================================================================== wgrad
+// dw[co, tap, ci] = sum_q dy[q, co] * x[q + shift(tap), ci] over the padded grid that x and dy share (dy's pad
+// rows are zero, so they add nothing).  GEMM with M = co (128 per CTA), N = ci (BN per CTA), K = q.  Both
+// operands are read pixel-major exactly as they lie in HBM, i.e. "MN-major" for the tensor core.  MN-major TF32
+// operands exist only in the "128-byte swizzle with 32-byte atoms" layout (UMMA layout type 1, TMA swizzle
+// 128B_ATOM_32B): an atom is 32 channels x 4 pixel rows (512 bytes).  A stage holds 32 pixel rows; each TMA box
+// is [32 rows x 32 channels]; boxes of consecutive 32-channel groups are 4096 bytes apart (LBO), 4-row groups
+// 512 bytes apart (SBO); one K = 8 MMA step spans two row groups (1024 bytes).
+// grid = (K splits, taps * Cin/BN, Cout/128); partial tiles are combined with fp32 atomic adds into dw.
+struct TcWgradArgs {
+    int kh, kw, ph, pw, wp;
+    int cin, cout, bn, stages;
+    long long rows, rows_per_split;
+    float *dw;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;              // leading byte offset: next 32-channel atom along M / N
+    d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset: next 4-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_constant__ CUtensorMap tm_dylo,
+                const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * 8 + 1];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = TC_BM * TC_BK * 4;             // dy tile: 32 rows x 128 channels
+    const uint32_t b_bytes = (uint32_t)a.bn * TC_BK * 4;    // x tile:  32 rows x BN channels
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int S = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
+
+    const int nblk = a.cin / a.bn;
+    const int tap = blockIdx.y / nblk, ci0 = (blockIdx.y - tap * nblk) * a.bn;
+    const int co0 = blockIdx.z * TC_BM;
+    const int dy_ = tap / a.kw, dx_ = tap - dy_ * a.kw;
+    const long long shift = (long long)(dy_ - a.ph) * a.wp + (dx_ - a.pw);
+    const long long k_begin = (long long)blockIdx.x * a.rows_per_split;
+    long long k_end = k_begin + a.rows_per_split;
+    if (k_end > a.rows) k_end = a.rows;
+    const int iters = k_end > k_begin ? (int)((k_end - k_begin + TC_BK - 1) / TC_BK) : 0;
+    const int tmem_cols = 4 * a.bn <= 64 ? 64 : (4 * a.bn <= 128 ? 128 : (4 * a.bn <= 256 ? 256 : 512));
+    const int nmain = iters < 3 ? iters : 3;
+    if (iters == 0) return;   // uniform for the whole CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int nb_boxes = a.bn / 32;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const long long q = k_begin + (long long)it * TC_BK;
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, stage_bytes);
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_2d(sa + j * 4096, &tm_dyhi, fb, co0 + 32 * j, (int)q);
+                    tma_load_2d(sa + a_bytes + j * 4096, &tm_dylo, fb, co0 + 32 * j, (int)q);
+                }
+                for (int j = 0; j < nb_boxes; ++j) {
+                    tma_load_2d(sa + 2 * a_bytes + j * 4096, &tm_xhi, fb, ci0 + 32 * j, (int)(q + shift));
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * 4096, &tm_xlo, fb, ci0 + 32 * j, (int)(q + shift));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // both operands MN-major: bits 15 and 16 of the instruction descriptor
+            const uint32_t idesc = make_idesc_tf32(a.bn) | (1u << 15) | (1u << 16);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t d_ahi = make_mnmajor_desc(sa), d_alo = make_mnmajor_desc(sa + a_bytes);
+                const uint64_t d_bhi = make_mnmajor_desc(sa + 2 * a_bytes), d_blo = make_mnmajor_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t ko = (uint64_t)(k * (1024 >> 4));   // next 8-row group
+                    umma_tf32(tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
+                    umma_tf32(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
+                    umma_tf32(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int co = co0 + quad * 32 + lane;
+        const int taps = a.kh * a.kw;
+        float *orow = a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c0 = 0; c0 < a.bn; c0 += 32) {
+            uint32_t v[32], u[32];
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+            tmem_ld32(trow, v);
+            for (int m = 1; m < nmain; ++m) {
+                tmem_ld32(trow + m * a.bn, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            tmem_ld32(trow + 3 * a.bn, u);
+            const int ncol = min(32, a.bn - c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < ncol)
+                    atomicAdd(reinterpret_cast<float4 *>(orow + c0 + j),
+                              make_float4(__uint_as_float(v[j]) + __uint_as_float(u[j]),
+                                          __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]),
+                                          __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]),
+                                          __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3])));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+    }
+}
+
+int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
+    // a.x: padded input (x_hi / x_lo); a.y: dy geometry (w_hi / w_lo carry dy); a.out = dw [cout][kh][kw][cin]
+    if (!a.x_lo || !a.w_lo) return 0;
+    if (a.sh != 1 || a.sw != 1) return 0;
+    if (a.kh != 2 * a.ph + 1 || a.kw != 2 * a.pw + 1) return 0;
+    if (a.cout % TC_BM != 0 || a.cin % 32 != 0) return 0;
+    // x and dy must share one padded grid, with pads covering the kernel reach
+    if (a.x.n != a.y.n || a.x.h != a.y.h || a.x.w != a.y.w || a.x.ph != a.y.ph || a.x.pw != a.y.pw) return 0;
+    if (a.x.ph < a.ph || a.x.pw < a.pw) return 0;
+    int bn = 0;
+    for (int c : {128, 64, 32})
+        if (a.cin % c == 0) { bn = c; break; }
+    if (!bn) return 0;
+    const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
+    if (rows >= (1LL << 31) - 4096) return 0;
+    if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out) & 15) != 0) return 0;
+
+    const int taps = a.kh * a.kw;
+    const int tiles = taps * (a.cin / bn) * (a.cout / TC_BM);
+    int splits = (3 * 148 + tiles - 1) / tiles;
+    const long long max_splits = (rows + 64 * TC_BK - 1) / (64 * TC_BK);   // at least 64 K chunks per CTA
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    long long rps = (rows + splits - 1) / splits;
+    rps = (rps + TC_BK - 1) / TC_BK * TC_BK;
+    splits = (int)((rows + rps - 1) / rps);
+
+    TcWgradArgs t;
+    t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw; t.wp = a.x.wp;
+    t.cin = a.cin; t.cout = a.cout; t.bn = bn;
+    t.rows = rows; t.rows_per_split = rps; t.dw = a.out;
+    const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
+    int stages = TC_SMEM_LIMIT / stage_bytes;
+    if (stages > 6) stages = 6;
+    t.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+
+    CUtensorMap mdh, mdl, mxh, mxl;
+    int rc;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map(&mdh, a.w_hi, rows, a.cout, TC_BK, sw))) return rc;
+    if ((rc = make_map(&mdl, a.w_lo, rows, a.cout, TC_BK, sw))) return rc;
+    if ((rc = make_map(&mxh, a.x_hi, rows, a.cin, TC_BK, sw))) return rc;
+    if ((rc = make_map(&mxl, a.x_lo, rows, a.cin, TC_BK, sw))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+        attr_set = true;
+    }
+    ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
+    DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
+    dim3 grid((unsigned)splits, (unsigned)(taps * (a.cin / bn)), (unsigned)(a.cout / TC_BM));
+    wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
+    DLIO_LAUNCH_CHECK();
+    return 1;
+}
 
 }  // namespace dlio

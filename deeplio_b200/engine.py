@@ -201,10 +201,12 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                                  res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
                                  bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
                                  ptr(sums), st)
-        # dgrad on the tensor cores: dy is produced in padded split form and convolved with the flipped weights
+        # backward on the tensor cores: dy is produced as padded split planes.  wgrad wants dy on x's padded grid,
+        # dgrad wants pads >= (k - 1 - pad); x's pads satisfy both for the "same" stride-1 convolutions.
         dgrad_tc = x.needs_grad and tc_ok(cout, cin_pad, stride)
-        dya = Act(n, ho, wo, cout, kh - 1 - cph if dgrad_tc else 0, kw - 1 - cpw if dgrad_tc else 0,
-                  device=run.device, split=dgrad_tc)
+        wgrad_tc = fwd_tc and cout % 128 == 0
+        dpad = (x.ph, x.pw) if wgrad_tc else ((kh - 1 - cph, kw - 1 - cpw) if dgrad_tc else (0, 0))
+        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, split=dgrad_tc or wgrad_tc)
         dy = dya.t
         dgb = run.empty(2, cout)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None

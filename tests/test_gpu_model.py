@@ -50,14 +50,24 @@ def test_model_matches_oracle_and_golden(name):
     opos, oori, ograds, osd = oracle_train_step(cfg, sd, inputs)
     assert rel_err(pos.detach().cpu(), opos) < FWD_TOL
     assert rel_err(ori.detach().cpu(), oori) < FWD_TOL
-    # gradients: every parameter.  Some gradients of the deep nets are ill-conditioned in fp32 (ReLU / arg-max
-    # decisions flip with round-off; BN over a few hundred samples): the reference's OWN fp32 result is up to
-    # 3e-2 away from an fp64 evaluation for those tensors.  So each gradient is held to the fp64 oracle with a
-    # bar of max(GRAD_TOL, 4 x the fp32 reference's own distance from fp64) -- two fp32 evaluations of a chaotic
-    # quantity differ by a small random factor, and ours is not bit-reproducible (atomics); well-conditioned
-    # tensors (the vast majority) are thereby held to GRAD_TOL against both.
-    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    _, _, g64, _ = oracle_train_step(cfg, sd64, tuple(t.double() for t in inputs))
+    # gradients: every parameter, against an fp64 evaluation of the oracle.  Most tensors are held to GRAD_TOL
+    # (2e-4 of the tensor's largest entry).  A few are ill-conditioned in ANY fp32 arithmetic: ReLU / arg-max
+    # decisions flip with round-off, and in these small fixtures BatchNorm runs over as few as 32 samples, so a
+    # near-constant channel multiplies noise by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5
+    # turns a 1e-6 input change into a 30 % change of its weight gradient).  The bar per tensor is therefore
+    # max(GRAD_TOL, 4 x its measured sensitivity), where the sensitivity is the larger of (a) the fp32
+    # reference's own distance from fp64 and (b) the change of the fp64 gradient when every weight and input is
+    # perturbed by 2e-6 relative (the size of fp32 / 3xTF32 round-off).
+    def f64(t):
+        return t.double() if t.is_floating_point() else t
+    sd64 = {k: f64(v) for k, v in sd.items()}
+    in64 = tuple(t.double() for t in inputs)
+    _, _, g64, _ = oracle_train_step(cfg, sd64, in64)
+    gen = torch.Generator().manual_seed(99)
+
+    def jitter(t):
+        return t * (1.0 + 2e-6 * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
+    _, _, gpert, _ = oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))
     gmax = max(float(n) for n, _ in rec["grads"].values())
     params = dict(model.named_parameters())
     assert set(params) == set(ograds)
@@ -66,11 +76,13 @@ def test_model_matches_oracle_and_golden(name):
         g = p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])
         scale = g64[k].abs().max().item()
         e_ref = (ograds[k].double() - g64[k]).abs().max().item()
+        e_pert = (gpert[k] - g64[k]).abs().max().item()
         e_ours = (g.double() - g64[k]).abs().max().item()
-        assert e_ours <= max(GRAD_TOL * scale, 4 * e_ref) + 1e-5 * gmax, (k, e_ours, e_ref, scale)
+        sens = max(e_ref, e_pert)
+        assert e_ours <= max(GRAD_TOL * scale, 4 * sens) + 1e-5 * gmax, (k, e_ours, e_ref, e_pert, scale)
         n_tight += e_ours <= GRAD_TOL * scale + 1e-5 * gmax
         norm, head = rec["grads"][k]
-        bar = GRAD_TOL + 4 * e_ref / (scale + 1e-30)
+        bar = GRAD_TOL + 4 * sens / (scale + 1e-30)
         assert abs(g.double().norm().item() - float(norm)) <= bar * float(norm) + 1e-5 * gmax, k
     assert n_tight >= 0.5 * len(params)
     # dead-direction RNN parameters still get (zero) gradient tensors, so Adam + L2 decay updates them

@@ -119,6 +119,12 @@ TC_CASES = [
     (2, 128, 256, 6, 11, (3, 3), False, 0, 0),
     (3, 512, 512, 17, 65, (3, 3), True, 1, 0),
     (1, 64, 48, 4, 6, (3, 3), False, 0, 0),
+    # PointSeg Fire shapes: squeeze 1x1 to a narrow tensor, expand 1x1 / 3x3 from it (dgrad on 80 / 48 channels)
+    (2, 768, 80, 6, 10, (1, 1), True, 0, 1),
+    (2, 80, 384, 6, 10, (1, 1), True, 0, 1),
+    (2, 80, 384, 6, 10, (3, 3), True, 0, 0),
+    (2, 48, 192, 7, 9, (3, 3), True, 0, 0),
+    (4, 64, 256, 8, 16, (3, 3), True, 0, 0),
 ]
 
 
@@ -153,7 +159,8 @@ def test_conv_tcgen05_fwd_and_dgrad(case):
     torch.cuda.synchronize()
     prof = L.profile_read()
     L.profile_enable(0)
-    assert "conv_fwd_tc" in prof and "conv_fwd_simt" not in prof, prof      # the tensor-core kernel really ran
+    fwd_tc = cin % 32 == 0 and cout % 16 == 0
+    assert ("conv_fwd_tc" if fwd_tc else "conv_fwd_simt") in prof and len(prof) == 1, prof   # which kernel really ran
     got = from_nhwc(y)
     assert relerr(got, ref) < 1e-5
     s = stats.cpu()   # the truncating accumulation biases every output the same way, so sums keep ~1e-5 of it
@@ -175,8 +182,22 @@ def test_conv_tcgen05_fwd_and_dgrad(case):
     torch.cuda.synchronize()
     prof = L.profile_read()
     L.profile_enable(0)
-    assert ("conv_dgrad_tc" if cout % 32 == 0 else "conv_dgrad_simt") in prof, prof
+    assert ("conv_dgrad_tc" if (cout % 32 == 0 and cin % 16 == 0) else "conv_dgrad_simt") in prof, prof
     assert relerr(from_nhwc(dx), xr.grad) < 1e-5
+
+    # wgrad: dy on the same padded grid as x, both operands read pixel-major (MN-major tcgen05 operands)
+    wr = wt.clone().requires_grad_(True)
+    F.conv2d(x, wr, None, 1, (ph, pw)).backward(dy)
+    dyp_hi, dyp_lo = split_padded(L, dy, tph, tpw)
+    dw_ohwi = torch.full((cout, kh, kw, cin), float("nan"), device=DEV)
+    L.profile_enable(1)
+    L.conv2d_bwd_weight(xt4, x_hi.data_ptr(), x_lo.data_ptr(), L.Tensor4(n, h, w, cout, tph, tpw), dyp_hi.data_ptr(),
+                        dyp_lo.data_ptr(), cv, dw_ohwi.data_ptr(), _st())
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert ("conv_wgrad_tc" if (cout % 128 == 0 and cin % 32 == 0) else "conv_wgrad_simt") in prof, prof
+    assert relerr(dw_ohwi.permute(0, 3, 1, 2).cpu(), wr.grad) < 1e-5
 
 
 @pytest.mark.parametrize("cfg", [
