@@ -30,24 +30,28 @@ LR, WD = 1e-3, 1e-4                   # reference defaults (deeplio/train.py:39,
 
 # ----------------------------------------------------------------------------- workload description
 def conv_flops_simple1(n_images):
-    """Algorithmic conv FLOPs of ONE Simple-1 encoder over n_images 64x2048 images:
-    returns (fwd, dgrad, wgrad); conv1 needs no dgrad (the input has no gradient)."""
+    """Algorithmic conv FLOPs of ONE Simple-1 encoder over n_images 64x2048 images, split by
+    the kernel class that runs each layer: {class: flops}.  conv1 (Cin = 6) runs on the CUDA-core kernels and
+    needs no dgrad (the input has no gradient); conv2..conv7 (stride 1, Cin % 32 == 0) run on tcgen05."""
     from deeplio_b200.engine import pool_out
     spec = [(6, 64, 5, 7, (1, 2), (1, 2)), (64, 128, 3, 5, (1, 1), (1, 2)), (128, 128, 3, 3, (1, 1), None),
             (128, 256, 3, 3, (1, 1), (2, 2)), (256, 256, 3, 3, (1, 1), None), (256, 512, 3, 3, (1, 1), (2, 2)),
             (512, 512, 3, 3, (1, 1), None)]
     h, w = H, W
-    fwd = dgrad = 0.0
+    out = {k: 0.0 for k in ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc",
+                            "conv_wgrad_tc")}
     for i, (ci, co, kh, kw, (sh, sw), pool) in enumerate(spec):
         ho, wo = (h + 2 * ((kh - 1) // 2) - kh) // sh + 1, (w + 2 * ((kw - 1) // 2) - kw) // sw + 1
         f = 2.0 * co * ho * wo * ci * kh * kw * n_images
-        fwd += f
+        tc = (sh, sw) == (1, 1) and ci % 32 == 0
+        out["conv_fwd_tc" if tc else "conv_fwd_simt"] += f
+        out["conv_wgrad_tc" if (tc and co % 128 == 0) else "conv_wgrad_simt"] += f
         if i > 0:
-            dgrad += f
+            out["conv_dgrad_tc" if ((sh, sw) == (1, 1) and co % 32 == 0 and ci % 16 == 0) else "conv_dgrad_simt"] += f
         h, w = ho, wo
         if pool:
             h, w = pool_out(h, pool[0], True), pool_out(w, pool[1], True)
-    return fwd, dgrad, fwd
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -236,8 +240,7 @@ def run_b200(args):
     e2e = pairs_per_step * args.steps / (ms_e2e / 1e3)
 
     # roofline of the dominant kernel class (largest share of the step among the profiled conv classes)
-    fwd, dgrad, wgrad = conv_flops_simple1(B * S)
-    flops = {"conv_fwd": 2 * fwd, "conv_dgrad": 2 * dgrad, "conv_wgrad": 2 * wgrad}    # two encoders
+    flops = {k: 2 * v for k, v in conv_flops_simple1(B * S).items()}    # two encoders
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -249,18 +252,22 @@ def run_b200(args):
         bf16_peak, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained bf16)"
     classes = {}
     for name, (ms, n) in prof.items():
-        base = name.rsplit("_", 1)[0]
         per_step_ms = ms / args.steps
         classes[name] = {"ms_per_step": per_step_ms, "launches_per_step": n / args.steps,
                          "share_of_step": per_step_ms / (ms_total / args.steps),
-                         "tflops": flops[base] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None}
+                         "gflop_per_step": flops[name] / 1e9,
+                         "tflops": flops[name] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None}
     roofline = None
     if classes:
         dom = max(classes, key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
+        tc = dom.endswith("_tc")
+        # the tcgen05 kernels issue 3 TF32 MMAs per algorithmic FLOP pair; TF32 runs at half the bf16 rate, so the
+        # tensor-pipe ceiling for fp32-equivalent FLOPs is bf16_peak / 6 (shown as frac_of_3xtf32_ceiling)
         roofline = {"bound": "tensor", "kernel": dom, "achieved": c["tflops"], "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": c["tflops"] / bf16_peak, "traffic": None, "peak_source": peak_src,
-                    "math": "fp32 FMA (CUDA cores)" if dom.endswith("simt") else "3xTF32 tcgen05 (fp32-equivalent FLOPs)",
+                    "frac_of_3xtf32_ceiling": (c["tflops"] / (bf16_peak / 6.0)) if tc else None,
+                    "math": "3xTF32 tcgen05 (fp32-equivalent algorithmic FLOPs)" if tc else "fp32 FMA (CUDA cores)",
                     "launch_ms": c["ms_per_step"] / c["launches_per_step"], "classes": classes}
 
     cpu_baseline = None
