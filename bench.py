@@ -254,12 +254,13 @@ def run_b200(args):
     for name, (ms, n) in prof.items():
         per_step_ms = ms / args.steps
         classes[name] = {"ms_per_step": per_step_ms, "launches_per_step": n / args.steps,
-                         "share_of_step": per_step_ms / (ms_total / args.steps),
-                         "gflop_per_step": flops[name] / 1e9,
-                         "tflops": flops[name] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None}
+                         "share_of_step": per_step_ms / (ms_total / args.steps)}
+        if name in flops:
+            classes[name]["gflop_per_step"] = flops[name] / 1e9
+            classes[name]["tflops"] = flops[name] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None
     roofline = None
     if classes:
-        dom = max(classes, key=lambda k: classes[k]["ms_per_step"])
+        dom = max((k for k in classes if k in flops), key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
         tc = dom.endswith("_tc")
         # the tcgen05 kernels issue 3 TF32 MMAs per algorithmic FLOP pair; TF32 runs at half the bf16 rate, so the

@@ -111,7 +111,8 @@ rnn_bwd_scratch_floats = _lib.dlio_rnn_bwd_scratch_floats
 abi_version = _lib.dlio_abi_version
 
 
-PROF_KINDS = ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc", "conv_wgrad_tc")
+PROF_KINDS = ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc", "conv_wgrad_tc",
+              "elementwise", "dense", "rnn", "optim")
 
 
 def profile_read():

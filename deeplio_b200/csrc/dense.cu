@@ -183,6 +183,7 @@ using namespace dlio;
 
 extern "C" int dlio_linear_fwd(const float *x, int ldx, const float *w, const float *b, int m, int n, int k, int act,
                                float *y, int ldy, void *stream) {
+    ProfScope prof_(DLIO_PROF_DENSE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(x && w && y && m > 0 && n > 0 && k > 0 && ldx >= k && ldy >= n, "linear_fwd: bad argument");
     return linear_fwd_launch(x, ldx, w, b, nullptr, m, n, k, act, y, ldy, (cudaStream_t)stream);
 }
@@ -190,6 +191,7 @@ extern "C" int dlio_linear_fwd(const float *x, int ldx, const float *w, const fl
 extern "C" int dlio_linear_bwd(const float *x, int ldx, const float *w, const float *y, int ldy, const float *dy,
                                int lddy, int m, int n, int k, int act, float *dx, int lddx, float *dw, float *db,
                                float *scratch, void *stream) {
+    ProfScope prof_(DLIO_PROF_DENSE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(x && w && dy && m > 0 && n > 0 && k > 0, "linear_bwd: bad argument");
     DLIO_CHECK_ARG(act == DLIO_ACT_NONE || (y && scratch), "linear_bwd: activation backward needs y and scratch");
     cudaStream_t st = (cudaStream_t)stream;

@@ -489,6 +489,7 @@ using namespace dlio;
 
 extern "C" int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
                                dlio_tensor4 dst, float *dst_ptr, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(src && dst_ptr && valid_t4(dst) && dst.c % 4 == 0 && dst.c >= T * C, "pack_input: bad argument");
     Geo d(dst);
     long long total = (long long)d.n * d.hp * d.wp;
@@ -501,6 +502,7 @@ extern "C" int dlio_bn_finalize(const double *stats, long long count, int c, con
                                 const float *beta, float *running_mean, float *running_var, float momentum,
                                 float eps, int use_running, float *mean, float *invstd, float *scale,
                                 float *shift, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(c > 0 && mean && invstd && scale && shift, "bn_finalize: bad argument");
     DLIO_CHECK_ARG(use_running ? (running_mean && running_var) : (stats && count > 0), "bn_finalize: missing statistics");
     bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(
@@ -518,6 +520,7 @@ static int check_cg(int c, const char *who) {
 extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                                     dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
                                     float *out_hi, float *out_lo, uint8_t *pool_idx, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(y) && valid_t4(out) && y_ptr && out_hi, "bn_act_pool_fwd: bad argument");
     int rc = check_cg(y.c, "bn_act_pool_fwd");
     if (rc) return rc;
@@ -545,6 +548,7 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
                                            dlio_tensor4 dout, const float *dout_ptr, int ld_dout,
                                            const uint8_t *pool_idx, float *dz, float *dres, int dres_c,
                                            int dres_accumulate, double *sums, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(y) && y_ptr && dout_ptr && dz, "bn_act_pool_bwd_reduce: bad argument");
     int rc = check_cg(y.c, "bn_act_pool_bwd_reduce");
     if (rc) return rc;
@@ -571,6 +575,7 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
                                  long long count, const float *scale, const float *mean, const float *invstd,
                                  int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
                                  float *dgamma, float *dbeta, double *dbias_sums, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && dz && dy_hi, "bn_bwd_apply: bad argument");
     DLIO_CHECK_ARG(dy_t.n == y.n && dy_t.h == y.h && dy_t.w == y.w && dy_t.c == y.c, "bn_bwd_apply: dy geometry");
     int rc = check_cg(y.c, "bn_bwd_apply");
@@ -588,6 +593,7 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
 }
 
 extern "C" int dlio_f64_to_f32(const double *src, float *dst, int n, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(src && dst && n > 0, "f64_to_f32: bad argument");
     f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
     DLIO_LAUNCH_CHECK();
@@ -617,6 +623,7 @@ static int launch_spatial(SpatialRed &a, cudaStream_t st) {
 
 extern "C" int dlio_spatial_mean_fwd(dlio_tensor4 x, const float *x_ptr, const float *scale, const float *shift,
                                      int relu, float *out, int ld_out, int c_off, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(x) && x_ptr && out && ld_out >= c_off + x.c, "spatial_mean_fwd: bad argument");
     SpatialRed a;
     a.x = Geo(x); a.other = a.x; a.xp = x_ptr; a.otherp = nullptr; a.scale = scale; a.shift = shift;
@@ -626,6 +633,7 @@ extern "C" int dlio_spatial_mean_fwd(dlio_tensor4 x, const float *x_ptr, const f
 
 extern "C" int dlio_spatial_dot(dlio_tensor4 a_t, const float *a_ptr, dlio_tensor4 b_t, const float *b_ptr,
                                 float *out, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(a_t) && valid_t4(b_t) && a_ptr && b_ptr && out, "spatial_dot: bad argument");
     DLIO_CHECK_ARG(a_t.n == b_t.n && a_t.h == b_t.h && a_t.w == b_t.w && a_t.c == b_t.c, "spatial_dot: geometry mismatch");
     SpatialRed a;
@@ -636,6 +644,7 @@ extern "C" int dlio_spatial_dot(dlio_tensor4 a_t, const float *a_ptr, dlio_tenso
 
 extern "C" int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const float *gate, dlio_tensor4 out,
                                       float *out_hi, float *out_lo, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(x) && valid_t4(out) && x_ptr && gate && out_hi, "channel_scale_fwd: bad argument");
     DLIO_CHECK_ARG(x.n == out.n && x.h == out.h && x.w == out.w && x.c == out.c && x.c % 4 == 0, "channel_scale_fwd: geometry");
     Geo xg(x), og(out);
@@ -647,6 +656,7 @@ extern "C" int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const 
 
 extern "C" int dlio_channel_scale_bwd(const float *dout, const float *gate, const float *dmean, int n, int hw,
                                       int c, float *dx, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(dout && gate && dx && c % 4 == 0 && n > 0 && hw > 0, "channel_scale_bwd: bad argument");
     long long total = (long long)n * hw * (c / 4);
     channel_scale_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dout, gate, dmean, 1.f / (float)hw, dx, n, hw, c / 4);
@@ -656,6 +666,7 @@ extern "C" int dlio_channel_scale_bwd(const float *dout, const float *gate, cons
 
 extern "C" int dlio_axpby(const float *a, float alpha, const float *b, float beta, float *out, long long n,
                           void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(a && b && out && n > 0, "axpby: bad argument");
     DLIO_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "axpby: pointers must be 16-byte aligned");
     axpby_kernel<<<grid_for((n + 3) / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n);
@@ -663,18 +674,21 @@ extern "C" int dlio_axpby(const float *a, float alpha, const float *b, float bet
     return DLIO_OK;
 }
 extern "C" int dlio_sum_mid(const float *x, float *out, long long a, int t, int c, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(x && out && a > 0 && t > 0 && c > 0, "sum_mid: bad argument");
     sum_mid_kernel<<<ceil_div(a * c, 256), 256, 0, (cudaStream_t)stream>>>(x, out, a, t, c);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
 extern "C" int dlio_mul(const float *a, const float *b, float *out, long long n, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(a && b && out && n > 0, "mul: bad argument");
     mul_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
 extern "C" int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(mask && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad argument");
     dropout_mask_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed);
     DLIO_LAUNCH_CHECK();

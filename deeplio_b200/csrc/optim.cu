@@ -47,6 +47,7 @@ using namespace dlio;
 extern "C" int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                               float grad_scale, void *stream) {
+    ProfScope prof_(DLIO_PROF_OPTIM, (cudaStream_t)stream);
     DLIO_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad argument");
     DLIO_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                    "adam_step: pointers must be 16-byte aligned");
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) hws_loss_kernel(const float *__restrict__
 
 extern "C" int dlio_hws_loss(const float *pos, const float *ori, const float *gt_pos, const float *gt_ori, int n,
                              float sx, float sq, float *loss, float *dpos, float *dori, void *stream) {
+    ProfScope prof_(DLIO_PROF_OPTIM, (cudaStream_t)stream);
     DLIO_CHECK_ARG(pos && ori && gt_pos && gt_ori && loss && n > 0, "hws_loss: bad argument");
     dlio::hws_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pos, ori, gt_pos, gt_ori, n, sx, sq, loss, dpos, dori);
     DLIO_LAUNCH_CHECK();

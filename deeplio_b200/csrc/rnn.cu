@@ -220,6 +220,7 @@ extern "C" size_t dlio_rnn_bwd_scratch_floats(int kind, int L, int D, int B, int
 extern "C" int dlio_rnn_fwd(int kind, int L, int D, int B, int T, int I, int H, const float *const *weights,
                             const float *x, const float *h0, const float *c0, const float *drop_mask, float *out,
                             float *hn, float *cn, float *reserve, void *stream) {
+    ProfScope prof_(DLIO_PROF_RNN, (cudaStream_t)stream);
     int rc = check_rnn(kind, L, D, B, T, I, H);
     if (rc) return rc;
     DLIO_CHECK_ARG(weights && x && out && hn && reserve && (kind == 1 || cn), "rnn_fwd: null pointer");
@@ -286,6 +287,7 @@ extern "C" int dlio_rnn_bwd(int kind, int L, int D, int B, int T, int I, int H, 
                             const float *x, const float *drop_mask, const float *dout, const float *dhn,
                             const float *dcn, const float *reserve_c, float *const *grads, float *dx, float *dh0,
                             float *dc0, float *scratch, size_t scratch_floats, void *stream) {
+    ProfScope prof_(DLIO_PROF_RNN, (cudaStream_t)stream);
     int rc = check_rnn(kind, L, D, B, T, I, H);
     if (rc) return rc;
     DLIO_CHECK_ARG(weights && x && reserve_c && grads && dh0 && scratch && (kind == 1 || dc0), "rnn_bwd: null pointer");

@@ -70,7 +70,9 @@ long long dlio_launch_count(void);
  * dlio_profile_read synchronises the recorded events of one class and returns their summed duration. */
 typedef enum {
     DLIO_PROF_CONV_FWD_SIMT = 0, DLIO_PROF_CONV_DGRAD_SIMT = 1, DLIO_PROF_CONV_WGRAD_SIMT = 2,
-    DLIO_PROF_CONV_FWD_TC = 3, DLIO_PROF_CONV_DGRAD_TC = 4, DLIO_PROF_CONV_WGRAD_TC = 5
+    DLIO_PROF_CONV_FWD_TC = 3, DLIO_PROF_CONV_DGRAD_TC = 4, DLIO_PROF_CONV_WGRAD_TC = 5,
+    DLIO_PROF_ELEMENTWISE = 6, /* BN / pool / SE / packing / element-wise passes (norm_pool.cu) */
+    DLIO_PROF_DENSE = 7, DLIO_PROF_RNN = 8, DLIO_PROF_OPTIM = 9
 } dlio_prof_kind;
 int dlio_profile_enable(int on);
 int dlio_profile_read(int kind, double *total_ms, long long *launches);

@@ -1,0 +1,119 @@
+"""BASELINE.json-size checks (64x2048 frame pairs) for every LiDAR net: forward parity with the CPU oracle at full
+resolution, plus size-independent properties -- eval-mode batch-split consistency and train-mode permutation
+equivariance (BatchNorm batch statistics do not depend on the sample order)."""
+import argparse
+
+import pytest
+import torch
+
+from oracle import deeplio_oracle as O
+from oracle.configs import make_cfg
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+H, W = 64, 2048
+
+NETS = [dict(lidar="lidar-feat-simple-1"), dict(lidar="lidar-feat-pointseg"),
+        dict(lidar="lidar-feat-resnet", rnn_type="gru", lidar_fusion="cat"),      # BASELINE configs[3] (needs patch P3)
+        dict(lidar="lidar-feat-flownet")]
+
+
+def build(cfg, B, sd):
+    from deeplio_b200 import nets
+    from deeplio_b200.config import build_config_container
+    build_config_container(cfg, argparse.Namespace(device=DEV, batch_size=B))
+    model = nets.get_model((3, H, W), cfg, DEV)
+    model.load_state_dict(sd)
+    return model
+
+
+def dev(inputs):
+    xyz, normals, imus = inputs
+    return [[xyz.to(DEV), normals.to(DEV)], imus.to(DEV)]
+
+
+@pytest.mark.parametrize("kw", NETS, ids=lambda k: k["lidar"])
+def test_full_resolution_forward_parity_and_properties(kw):
+    B, S, T = 2, 2, 15
+    cfg = make_cfg(height=H, width=W, seq=S, odom_hidden=256, **kw)
+    sd = O.synthetic_state(cfg, seed=21)
+    inputs = O.synthetic_batch(B, S, H, W, T, seed=21)
+    model = build(cfg, B, sd)
+
+    # train-mode forward (batch statistics) against the oracle at full size; north_star gate: 1e-4 relative
+    model.train()
+    pos, ori = model(dev(inputs))
+    sdo = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        opos, oori = O.deeplio_forward(sdo, cfg, *inputs, training=True)
+    assert rel_err(pos.detach().cpu(), opos) < 2e-5
+    assert rel_err(ori.detach().cpu(), oori) < 2e-5
+    ((pos ** 2).sum() + (ori ** 2).sum()).backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+    # permutation equivariance in train mode
+    perm = torch.tensor([1, 0])
+    model.load_state_dict(sd)
+    p2, o2 = model(dev(tuple(t[perm] for t in inputs)))
+    assert rel_err(p2.detach()[perm].cpu(), pos.detach().cpu()) < 1e-5
+    assert rel_err(o2.detach()[perm].cpu(), ori.detach().cpu()) < 1e-5
+
+    # eval mode: a batch equals its samples run one by one (running statistics, no cross-sample op)
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        pb, ob = model(dev(inputs))
+        parts = [model(dev(tuple(t[i:i + 1] for t in inputs))) for i in range(B)]
+    assert rel_err(torch.cat([p for p, _ in parts]).cpu(), pb.cpu()) < 1e-5
+    assert rel_err(torch.cat([o for _, o in parts]).cpu(), ob.cpu()) < 1e-5
+
+
+def test_one_adam_step_matches_oracle():
+    """Full train step (forward, loss, backward, fused flat-arena Adam with L2 decay) against torch.optim.Adam on
+    the oracle: parameters after one step agree to 1e-6 absolute (lr = 1e-3, so the update itself is ~1e-3)."""
+    from deeplio_b200 import functional as Fn
+    from deeplio_b200.optim import FlatAdam
+    B, S, T, h, w = 2, 2, 6, 16, 128
+    cfg = make_cfg(height=h, width=w, seq=S, odom_hidden=64)
+    sd = O.synthetic_state(cfg, seed=5)
+    inputs = O.synthetic_batch(B, S, h, w, T, seed=5)
+    g = torch.Generator().manual_seed(2)
+    gt_pos, gt_ori = torch.randn(B, S, 3, generator=g) * 0.1, torch.randn(B, S, 3, generator=g) * 0.01
+    from deeplio_b200 import nets
+    from deeplio_b200.config import build_config_container
+    build_config_container(cfg, argparse.Namespace(device=DEV, batch_size=B))
+    model = nets.get_model((3, h, w), cfg, DEV)
+    model.load_state_dict(sd)
+    model.train()
+    opt = FlatAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt.zero_grad()
+    pos, ori = model(dev(inputs))
+    loss = Fn.hws_loss(pos, ori, gt_pos.to(DEV), gt_ori.to(DEV))
+    loss.backward()
+    opt.step(1.0)
+
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k}
+    state = dict({k: v.clone() for k, v in sd.items()})
+    state.update(leaves)
+    ropt = torch.optim.Adam(list(leaves.values()), lr=1e-3, weight_decay=1e-4)
+    opos, oori = O.deeplio_forward(state, cfg, *inputs, training=True)
+    mse = torch.nn.functional.mse_loss
+    oloss = mse(opos, gt_pos) + mse(oori, gt_ori) * float(torch.exp(torch.tensor(3.0))) - 3.0
+    assert abs(float(loss) - float(oloss)) < 1e-5 * max(1.0, abs(float(oloss)))
+    ropt.zero_grad()
+    oloss.backward()
+    ropt.step()
+    # Adam normalises each gradient entry by its own magnitude, so entries whose gradient is round-off-sized
+    # (|g| ~ 1e-9: BN-cancelled conv biases, the dead direction of the last RNN layer) may move by +-lr in either
+    # direction; compare where the oracle's gradient is meaningfully non-zero and bound the rest by lr.
+    worst = 0.0
+    for k, p in model.named_parameters():
+        ref, g0 = leaves[k].detach(), leaves[k].grad
+        d = (p.detach().cpu() - ref).abs()
+        solid = g0.abs() > 1e-3 * g0.abs().max().clamp_min(1e-12) + 1e-9
+        if solid.any():
+            worst = max(worst, float(d[solid].max()))
+        assert float(d.max()) <= 2.1e-3, k
+    assert worst < 2e-5
