@@ -22,6 +22,14 @@ static inline int grid_for(long long total, int block, int per_sm = 8) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// Pixel loop with a FIXED channel group per thread (blockDim.x is a multiple of cg): 32-bit index arithmetic
+// only -- the first version of these kernels decoded a 64-bit flat index with five 64-bit divisions per
+// element and was instruction-bound (ncu: 780 instructions per element, 14 % of HBM bandwidth).
+#define DLIO_PIX_LOOP(pix, npix, cg)                                                              \
+    for (unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) / (unsigned)(cg),                 \
+                  pix##_step = (gridDim.x * blockDim.x) / (unsigned)(cg);                         \
+         pix < (unsigned)(npix); pix += pix##_step)
+
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
 __device__ __forceinline__ float4 fma4(const float4 &a, const float4 &b, const float4 &c) {
     return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
@@ -36,13 +44,12 @@ __device__ __forceinline__ float4 relu4(const float4 &a) {
 // ------------------------------------------------------------------ input packing
 __global__ void pack_input_kernel(const float *__restrict__ src, long long sn, long long st, long long sc, int T,
                                   int C, Geo d, float *__restrict__ dst) {
-    long long total = (long long)d.n * d.hp * d.wp;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int xx = (int)(i % d.wp);
-        long long t = i / d.wp;
-        int yy = (int)(t % d.hp);
-        int n = (int)(t / d.hp);
+    const unsigned total = (unsigned)d.n * d.hp * d.wp;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int xx = (int)(i % (unsigned)d.wp);
+        unsigned t = i / (unsigned)d.wp;
+        int yy = (int)(t % (unsigned)d.hp);
+        int n = (int)(t / (unsigned)d.hp);
         int h = yy - d.ph, w = xx - d.pw;
         float *o = dst + (size_t)i * d.c;
         bool in = h >= 0 && h < d.h && w >= 0 && w < d.w;
@@ -114,15 +121,12 @@ __device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, in
 }
 
 __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
-    const long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % a.cg) * 4;
-        long long pix = i / a.cg;
-        int xx = (int)(pix % a.out.wp);
-        long long t = pix / a.out.wp;
-        int yy = (int)(t % a.out.hp);
-        int n = (int)(t / a.out.hp);
+    const int c = (int)(threadIdx.x % a.cg) * 4;
+    DLIO_PIX_LOOP(pix, a.out.n * a.out.hp * a.out.wp, a.cg) {
+        int xx = (int)(pix % (unsigned)a.out.wp);
+        unsigned t = pix / (unsigned)a.out.wp;
+        int yy = (int)(t % (unsigned)a.out.hp);
+        int n = (int)(t / (unsigned)a.out.hp);
         size_t o = (size_t)pix * a.out.c + a.c_off + c;
         int ho = yy - a.out.ph, wo = xx - a.out.pw;
         if (ho < 0 || ho >= a.out.h || wo < 0 || wo >= a.out.w) {
@@ -178,12 +182,51 @@ struct BnBwd {
     double *sums;
 };
 
+// Gradient of a 3x3 max-pool (pad 1, stride SH x SW) gathered at input position (h, w): the sum of dout over
+// the windows that contain (h, w) and whose arg-max is (h, w).  Strides are compile-time so the candidate set
+// (3 windows along a stride-1 axis, 1 or 2 along a stride-2 axis) and the window-relative position fold into
+// constants; all candidate loads are issued unconditionally on clamped addresses and masked afterwards.
+template <int SH, int SW>
+__device__ __forceinline__ float4 unpool_gather(const BnBwd &a, int n, int h, int w, int c, int C) {
+    constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;
+    const int ho0 = SH == 1 ? h - 1 : h >> 1, wo0 = SW == 1 ? w - 1 : w >> 1;
+    float4 g = f4(0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const int ho = ho0 + i;
+        const bool okh = ho >= 0 && ho < a.pooled_h && (SH == 1 || i == 0 || (h & 1));
+        const int rh = SH == 1 ? 2 - i : h + 1 - 2 * ho;
+        const int hoc = okh ? ho : 0;
+        const uint8_t *irow = a.idx + ((size_t)(n * a.pooled_h + hoc) * a.pooled_w) * C + c;
+        const float *drow = a.doutp + a.dout.off(n, hoc, 0) + a.c_off + c;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int wo = wo0 + j;
+            const bool ok = okh && wo >= 0 && wo < a.pooled_w && (SW == 1 || j == 0 || (w & 1));
+            const int rw = SW == 1 ? 2 - j : w + 1 - 2 * wo;
+            const int woc = ok ? wo : 0;
+            const unsigned bi = *reinterpret_cast<const unsigned *>(irow + woc * C);
+            const float4 d = ld4(drow + woc * a.dout.c);
+            const unsigned r = ok ? (unsigned)(rh * 3 + rw) : 255u;
+            const unsigned m = __vcmpeq4(bi, r * 0x01010101u);   // 0xFF in every byte whose arg-max is (h, w)
+            if (m & 0x000000FFu) g.x += d.x;
+            if (m & 0x0000FF00u) g.y += d.y;
+            if (m & 0x00FF0000u) g.z += d.z;
+            if (m & 0xFF000000u) g.w += d.w;
+        }
+    }
+    return g;
+}
+template <>
+__device__ __forceinline__ float4 unpool_gather<0, 0>(const BnBwd &, int, int, int, int, int) { return f4(0.f); }
+
+// SH = SW = 0: no pooling (direct or global-average gradient source)
+template <int SH, int SW>
 __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
     __shared__ float red[2 * MAX_C];
     const int C = a.cg * 4;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    const long long total = (long long)a.y.n * a.y.h * a.y.w * a.cg;
     const int c = (int)(threadIdx.x % a.cg) * 4;  // fixed per thread: blockDim.x % cg == 0
     float4 sc = f4(1.f), sf = f4(0.f), mu = f4(0.f), is = f4(1.f);
     if (a.scale) {
@@ -196,13 +239,11 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
     }
     const float inv_hw = 1.f / (float)(a.y.h * a.y.w);
     float4 s1 = f4(0.f), s2 = f4(0.f);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long pix = i / a.cg;
-        int w = (int)(pix % a.y.w);
-        long long t = pix / a.y.w;
-        int h = (int)(t % a.y.h);
-        int n = (int)(t / a.y.h);
+    DLIO_PIX_LOOP(pix, a.y.n * a.y.h * a.y.w, a.cg) {
+        int w = (int)(pix % (unsigned)a.y.w);
+        unsigned t = pix / (unsigned)a.y.w;
+        int h = (int)(t % (unsigned)a.y.h);
+        int n = (int)(t / (unsigned)a.y.h);
         float4 g = f4(0.f);
         if (a.grad_src == DLIO_GRAD_AVG) {
             g = ld4(a.doutp + (size_t)n * a.ld_dout + a.c_off + c);
@@ -210,24 +251,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
         } else if (a.pk == 1) {
             g = ld4(a.doutp + a.dout.off(n, h, w) + a.c_off + c);
         } else {
-            // windows (ho, wo) that contain (h, w): ho*sh - 1 <= h <= ho*sh + 1
-            int ho_lo = (h - 1 + a.sh - 1) / a.sh, ho_hi = (h + 1) / a.sh;
-            int wo_lo = (w - 1 + a.sw - 1) / a.sw, wo_hi = (w + 1) / a.sw;
-            if (h - 1 < 0) ho_lo = 0;
-            if (w - 1 < 0) wo_lo = 0;
-            if (ho_hi >= a.pooled_h) ho_hi = a.pooled_h - 1;
-            if (wo_hi >= a.pooled_w) wo_hi = a.pooled_w - 1;
-            for (int ho = ho_lo; ho <= ho_hi; ++ho)
-                for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-                    unsigned char r = (unsigned char)((h - (ho * a.sh - 1)) * 3 + (w - (wo * a.sw - 1)));
-                    uchar4 bi = *reinterpret_cast<const uchar4 *>(
-                        a.idx + (((size_t)n * a.pooled_h + ho) * a.pooled_w + wo) * C + c);
-                    float4 d = ld4(a.doutp + a.dout.off(n, ho, wo) + a.c_off + c);
-                    if (bi.x == r) g.x += d.x;
-                    if (bi.y == r) g.y += d.y;
-                    if (bi.z == r) g.z += d.z;
-                    if (bi.w == r) g.w += d.w;
-                }
+            g = unpool_gather<SH, SW>(a, n, h, w, c, C);
         }
         const size_t yo = a.y.off(n, h, w) + c;
         float4 y = ld4(a.yp + yo);
@@ -299,14 +323,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
         }
     }
     float4 sb = f4(0.f);
-    const long long total = (long long)a.dy.n * a.dy.hp * a.dy.wp * a.cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long pix = i / a.cg;
-        int xx = (int)(pix % a.dy.wp);
-        long long t = pix / a.dy.wp;
-        int yy = (int)(t % a.dy.hp);
-        int n = (int)(t / a.dy.hp);
+    DLIO_PIX_LOOP(pix, a.dy.n * a.dy.hp * a.dy.wp, a.cg) {
+        int xx = (int)(pix % (unsigned)a.dy.wp);
+        unsigned t = pix / (unsigned)a.dy.wp;
+        int yy = (int)(t % (unsigned)a.dy.hp);
+        int n = (int)(t / (unsigned)a.dy.hp);
         int h = yy - a.dy.ph, w = xx - a.dy.pw;
         size_t o = (size_t)pix * C + c;
         if (h < 0 || h >= a.dy.h || w < 0 || w >= a.dy.w) {
@@ -397,15 +418,12 @@ __global__ void zero_strided_kernel(float *p, int rows, int cols, int ld) {
 __global__ void __launch_bounds__(256) channel_scale_fwd_kernel(Geo x, const float *__restrict__ xp,
                                                                 const float *__restrict__ gate, Geo o,
                                                                 float *out_hi, float *out_lo, int cg) {
-    const long long total = (long long)o.n * o.hp * o.wp * cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cg) * 4;
-        long long pix = i / cg;
-        int xx = (int)(pix % o.wp);
-        long long t = pix / o.wp;
-        int yy = (int)(t % o.hp);
-        int n = (int)(t / o.hp);
+    const int c = (int)(threadIdx.x % cg) * 4;
+    DLIO_PIX_LOOP(pix, o.n * o.hp * o.wp, cg) {
+        int xx = (int)(pix % (unsigned)o.wp);
+        unsigned t = pix / (unsigned)o.wp;
+        int yy = (int)(t % (unsigned)o.hp);
+        int n = (int)(t / (unsigned)o.hp);
         int h = yy - o.ph, w = xx - o.pw;
         size_t oo = (size_t)pix * o.c + c;
         if (h < 0 || h >= o.h || w < 0 || w >= o.w) {
@@ -423,12 +441,9 @@ __global__ void __launch_bounds__(256) channel_scale_bwd_kernel(const float *__r
                                                                 const float *__restrict__ gate,
                                                                 const float *__restrict__ dmean, float inv,
                                                                 float *__restrict__ dx, int n, int hw, int cg) {
-    const long long total = (long long)n * hw * cg;
     const int C = cg * 4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cg) * 4;
-        long long pix = i / cg;
+    const int c = (int)(threadIdx.x % cg) * 4;
+    DLIO_PIX_LOOP(pix, n * hw, cg) {
         int in = (int)(pix / hw);
         float4 g = ld4(gate + (size_t)in * C + c);
         float4 v = mul4(ld4(dout + (size_t)pix * C + c), g);
@@ -537,7 +552,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     a.c_off = p.c_off; a.cg = y.c / 4;
     a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx;
     long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
-    bn_act_pool_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(a);
+    bn_act_pool_fwd_kernel<<<grid_for(total, block_for_cg(a.cg), 16), block_for_cg(a.cg), 0, (cudaStream_t)stream>>>(a);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
@@ -566,7 +581,17 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
     a.idx = pool_idx; a.dz = dz; a.dres = dres; a.dres_c = dres_c; a.dres_acc = dres_accumulate; a.sums = sums;
     int block = block_for_cg(a.cg);
     long long total = (long long)y.n * y.h * y.w * a.cg;
-    bn_act_pool_bwd_reduce_kernel<<<grid_for(total, block, 8), block, 0, (cudaStream_t)stream>>>(a);
+    const int grid = grid_for(total, block, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.pk == 1) bn_act_pool_bwd_reduce_kernel<0, 0><<<grid, block, 0, st>>>(a);
+    else if (a.sh == 1 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<1, 2><<<grid, block, 0, st>>>(a);
+    else if (a.sh == 2 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<2, 2><<<grid, block, 0, st>>>(a);
+    else if (a.sh == 1 && a.sw == 1) bn_act_pool_bwd_reduce_kernel<1, 1><<<grid, block, 0, st>>>(a);
+    else if (a.sh == 2 && a.sw == 1) bn_act_pool_bwd_reduce_kernel<2, 1><<<grid, block, 0, st>>>(a);
+    else {
+        set_error("bn_act_pool_bwd_reduce: unsupported pool stride %dx%d", a.sh, a.sw);
+        return DLIO_ERR_INVALID;
+    }
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
@@ -649,7 +674,7 @@ extern "C" int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const 
     DLIO_CHECK_ARG(x.n == out.n && x.h == out.h && x.w == out.w && x.c == out.c && x.c % 4 == 0, "channel_scale_fwd: geometry");
     Geo xg(x), og(out);
     long long total = (long long)og.n * og.hp * og.wp * (x.c / 4);
-    channel_scale_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(xg, x_ptr, gate, og, out_hi, out_lo, x.c / 4);
+    channel_scale_fwd_kernel<<<grid_for(total, block_for_cg(x.c / 4), 16), block_for_cg(x.c / 4), 0, (cudaStream_t)stream>>>(xg, x_ptr, gate, og, out_hi, out_lo, x.c / 4);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
@@ -659,7 +684,7 @@ extern "C" int dlio_channel_scale_bwd(const float *dout, const float *gate, cons
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(dout && gate && dx && c % 4 == 0 && n > 0 && hw > 0, "channel_scale_bwd: bad argument");
     long long total = (long long)n * hw * (c / 4);
-    channel_scale_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dout, gate, dmean, 1.f / (float)hw, dx, n, hw, c / 4);
+    channel_scale_bwd_kernel<<<grid_for(total, block_for_cg(c / 4), 16), block_for_cg(c / 4), 0, (cudaStream_t)stream>>>(dout, gate, dmean, 1.f / (float)hw, dx, n, hw, c / 4);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
