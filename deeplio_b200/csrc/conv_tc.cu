@@ -38,6 +38,7 @@ struct TcArgs {
     int cin, cout, bn;  // bn: output channels per CTA (multiple of 16, <= 256)
     int act;
     int stages;
+    int cluster;       // 1, or 2: CTA pairs along M share the weight tile through TMA multicast
     const float *bias;
     float *out;
     double *stats;
@@ -72,12 +73,51 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask`, and each of those
+// CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// A-operand collector reuse: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` reads it
+// from there instead of shared memory (the two MMAs that share A_hi read it from smem once).
+__device__ __forceinline__ void umma_tf32_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_alast(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
@@ -137,11 +177,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const int n0 = blockIdx.y * a.bn;
     const int tmem_cols = 4 * a.bn <= 64 ? 64 : (4 * a.bn <= 128 ? 128 : (4 * a.bn <= 256 ? 256 : 512));
     const int nmain = iters < 3 ? iters : 3;
+    uint32_t cta_rank = 0;
+    if (a.cluster == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, (uint32_t)a.cluster);   // freed when every CTA of the pair has consumed it
         }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,7 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (a.cluster == 2) cluster_sync_all();   // peer barriers must exist before multicast traffic / remote arrives
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -173,8 +216,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 mbar_expect_tx(fb, stage_bytes);
                 tma_load_2d(sa, &tm_xhi, fb, cc * TC_BK, (int)row);
                 tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * TC_BK, (int)row);
-                tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, tap * a.cin + cc * TC_BK, n0);
-                tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, tap * a.cin + cc * TC_BK, n0);
+                if (a.cluster == 2) {   // each CTA fetches half of the weight tile for both
+                    const uint32_t half = b_bytes / 2;
+                    const int nh = n0 + (int)cta_rank * (a.bn / 2);
+                    tma_load_2d_mc(sa + 2 * a_bytes + cta_rank * half, &tm_whi, fb, tap * a.cin + cc * TC_BK, nh, 3);
+                    tma_load_2d_mc(sa + 2 * a_bytes + b_bytes + cta_rank * half, &tm_wlo, fb, tap * a.cin + cc * TC_BK, nh, 3);
+                } else {
+                    tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, tap * a.cin + cc * TC_BK, n0);
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, tap * a.cin + cc * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -193,10 +243,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
                     umma_tf32(tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma_tf32(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma_tf32(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                    umma_tf32_afill(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
+                    umma_tf32_alast(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
-                umma_commit(empty0 + 8 * s);   // frees the smem stage when these MMAs retire
+                // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                if (a.cluster == 2) umma_commit_mc(empty0 + 8 * s, 3);
+                else umma_commit(empty0 + 8 * s);
             }
             umma_commit(tfull);                // accumulator complete
         }
@@ -271,7 +323,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (a.cluster == 2) cluster_sync_all();   // no CTA may exit while its peer can still signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
     }
@@ -354,8 +407,15 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     int rc;
     if ((rc = make_map(&mxh, a.x_hi, rows, a.cin, TC_BM))) return rc;
     if ((rc = make_map(&mxl, a.x_lo, rows, a.cin, TC_BM))) return rc;
-    if ((rc = make_map(&mwh, a.w_hi, a.cout, K, bn))) return rc;
-    if ((rc = make_map(&mwl, a.w_lo, a.cout, K, bn))) return rc;
+    const long long mtiles = (rows + TC_BM - 1) / TC_BM;
+    // CTA pairs that share the weight tile through TMA multicast are implemented and tested (set to 2), but
+    // measured 6 % SLOWER (fwd 8.32 -> 8.81 ms / step): ncu sampling shows the producer waiting on `empty`, i.e.
+    // the loop is bound by the tensor pipe reading its SS operands from shared memory (8 KB per 64-cycle MMA =
+    // the full 128 B/clk), not by L2 -> SM traffic, and pairing adds lock-step between the two CTAs.
+    constexpr bool kPairMulticast = false;
+    t.cluster = (kPairMulticast && mtiles >= 2 && bn % 16 == 0) ? 2 : 1;
+    if ((rc = make_map(&mwh, a.w_hi, a.cout, K, bn / t.cluster))) return rc;
+    if ((rc = make_map(&mwl, a.w_lo, a.cout, K, bn / t.cluster))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -364,8 +424,20 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     }
     ProfScope prof(prof_kind, st);
     if (a.o.ph > 0 || a.o.pw > 0) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
-    dim3 grid((unsigned)((rows + TC_BM - 1) / TC_BM), (unsigned)(a.cout / bn));
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, t);
+    dim3 grid((unsigned)((mtiles + t.cluster - 1) / t.cluster * t.cluster), (unsigned)(a.cout / bn));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = t.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DLIO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mxh, mxl, mwh, mwl, t));
     DLIO_LAUNCH_CHECK();
     return 1;
 }
@@ -480,8 +552,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t ko = (uint64_t)(k * (1024 >> 4));   // next 8-row group
                     umma_tf32(tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma_tf32(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma_tf32(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                    umma_tf32_afill(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
+                    umma_tf32_alast(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
             }
@@ -541,13 +613,23 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
 
     const int taps = a.kh * a.kw;
     const int tiles = taps * (a.cin / bn) * (a.cout / TC_BM);
-    int splits = (3 * 148 + tiles - 1) / tiles;
-    const long long max_splits = (rows + 64 * TC_BK - 1) / (64 * TC_BK);   // at least 64 K chunks per CTA
-    if (splits > max_splits) splits = (int)max_splits;
-    if (splits < 1) splits = 1;
+    // K splits: one CTA per SM (192 KB of smem), so the grid should fill whole waves of 148 CTAs -- a grid of
+    // 450 CTAs (3.04 waves) ran at 76 % of a 444-CTA one.  Pick the split count whose total is closest below a
+    // multiple of 148 among 2..4 waves, keeping at least 64 K chunks per CTA.
+    const long long max_splits = (rows + 64 * TC_BK - 1) / (64 * TC_BK);
+    int splits = 1;
+    double best_fill = 0.0;
+    for (int waves = 2; waves <= 4; ++waves) {
+        int s = waves * 148 / tiles;
+        if (s > max_splits) s = (int)max_splits;
+        if (s < 1) s = 1;
+        const long long ctas = (long long)s * tiles;
+        const double fill = (double)ctas / (double)(((ctas + 147) / 148) * 148);
+        if (fill > best_fill + 1e-9) { best_fill = fill; splits = s; }
+    }
     long long rps = (rows + splits - 1) / splits;
     rps = (rps + TC_BK - 1) / TC_BK * TC_BK;
-    splits = (int)((rows + rps - 1) / rps);
+    if ((rows + rps - 1) / rps < splits) splits = (int)((rows + rps - 1) / rps);
 
     TcWgradArgs t;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw; t.wp = a.x.wp;
