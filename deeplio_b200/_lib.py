@@ -43,7 +43,10 @@ _PROTOS = {
     "dlio_launch_count": (LL, []),
     "dlio_profile_enable": (I, [I]),
     "dlio_profile_read": (I, [I, P, P]),
-    "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P]),
+    "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P, P]),
+    "dlio_weight_to_s2d": (I, [P, I, I, I, I, I, P, P, P]),
+    "dlio_weight_grad_from_s2d": (I, [P, I, I, I, I, I, P, P]),
+    "dlio_fold_stats": (I, [P, I, I, P, P]),
     "dlio_conv2d_fwd": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
     "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, P, P, Conv, Tensor4, P, P]),
     "dlio_conv2d_bwd_weight": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),

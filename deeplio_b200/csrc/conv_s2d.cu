@@ -1,0 +1,102 @@
+// First-layer convolutions on the tensor cores through a space-to-depth reinterpretation.
+//
+// The first convolution of every encoder has 6 (padded 8) input channels and a wide kernel (5x7 or 3x5, stride
+// (1,2) or (1,1)); as an implicit GEMM it has K = kh*kw*8 with 8-channel rows, which the tcgen05 kernel (32-float
+// K chunks) cannot take.  Grouping FOUR consecutive pixels of a row gives a [n, h, w/4, 32] view of the SAME
+// padded-NHWC memory (row pads of 4 pixels become 1), and grouping the R = 4/stride outputs computed from them
+// gives a [n, h, w/4, R*cout] view of the SAME output memory.  In these views the layer is an ordinary
+// stride-1 "same" convolution with kernel kh x 3, Cin = 32, Cout = R*cout -- only the weights are rearranged:
+//     W4[(r, co)][dy][t][(p, c)] = W[co][dy][dx][c]   with dx = 4 t' + p - stride*r + pad_w,  t' = t - 1,
+// zero where dx falls outside [0, kw).  2.3x more MACs than the direct form, but on the tensor pipe.
+#include "common.cuh"
+
+namespace dlio {
+
+__global__ void weight_to_s2d_kernel(const float *__restrict__ w, int cout, int cin, int kh, int kw, int sw,
+                                     float *__restrict__ hi, float *__restrict__ lo) {
+    const int R = 4 / sw, pw = (kw - 1) / 2;
+    const long long total = (long long)R * cout * kh * 3 * 32;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int pc = (int)(i % 32);
+    long long t1 = i / 32;
+    int t = (int)(t1 % 3);
+    t1 /= 3;
+    int dy = (int)(t1 % kh);
+    int rco = (int)(t1 / kh);
+    int p = pc / 8, c = pc % 8;
+    int r = rco / cout, co = rco - r * cout;
+    int dx = 4 * (t - 1) + p - sw * r + pw;
+    float v = 0.f;
+    if (c < cin && dx >= 0 && dx < kw) v = w[(((size_t)co * cin + c) * kh + dy) * kw + dx];   // OIHW
+    float h, l;
+    tf32_split(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+}
+
+// dw[co][c][dy][dx] (OIHW) = sum over the (r, t, p) that map to dx of dw4[(r, co)][dy][t][(p, c)]
+__global__ void weight_grad_from_s2d_kernel(const float *__restrict__ dw4, int cout, int cin, int kh, int kw, int sw,
+                                            float *__restrict__ dw) {
+    const int R = 4 / sw, pw = (kw - 1) / 2;
+    const long long total = (long long)cout * cin * kh * kw;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int dx = (int)(i % kw);
+    long long t1 = i / kw;
+    int dy = (int)(t1 % kh);
+    t1 /= kh;
+    int c = (int)(t1 % cin);
+    int co = (int)(t1 / cin);
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) {
+        int off = dx + sw * r - pw;          // = 4 t' + p
+        int tq = (off + 8) / 4 - 2;          // floor(off / 4) for off >= -8
+        int p = off - 4 * tq;
+        int t = tq + 1;
+        if (t >= 0 && t < 3) s += dw4[((((size_t)(r * cout + co)) * kh + dy) * 3 + t) * 32 + p * 8 + c];
+    }
+    dw[i] = s;
+}
+
+// out[j*c + k] = sum_r in[j*R*c + r*c + k]   (j = 0: sums, j = 1: sums of squares)
+__global__ void fold_stats_kernel(const double *__restrict__ in, int R, int c, double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * c) return;
+    int j = i / c, k = i - j * c;
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) s += in[(size_t)j * R * c + r * c + k];
+    out[i] = s;
+}
+
+}  // namespace dlio
+
+using namespace dlio;
+
+extern "C" int dlio_weight_to_s2d(const float *w_oihw, int cout, int cin, int kh, int kw, int sw, float *w4_hi,
+                                  float *w4_lo, void *stream) {
+    DLIO_CHECK_ARG(w_oihw && w4_hi && cout > 0 && cin > 0 && cin <= 8 && (sw == 1 || sw == 2) && kw >= 1 && kw <= 7 &&
+                       (kw & 1),
+                   "weight_to_s2d: bad argument");
+    long long total = (long long)(4 / sw) * cout * kh * 3 * 32;
+    weight_to_s2d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, kh, kw, sw, w4_hi, w4_lo);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_weight_grad_from_s2d(const float *dw4, int cout, int cin, int kh, int kw, int sw, float *dw_oihw,
+                                         void *stream) {
+    DLIO_CHECK_ARG(dw4 && dw_oihw && cout > 0 && cin > 0 && cin <= 8 && (sw == 1 || sw == 2) && kw <= 7 && (kw & 1),
+                   "weight_grad_from_s2d: bad argument");
+    long long total = (long long)cout * cin * kh * kw;
+    weight_grad_from_s2d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(dw4, cout, cin, kh, kw, sw, dw_oihw);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_fold_stats(const double *in, int r, int c, double *out, void *stream) {
+    DLIO_CHECK_ARG(in && out && r >= 1 && c > 0, "fold_stats: bad argument");
+    fold_stats_kernel<<<ceil_div(2 * c, 128), 128, 0, (cudaStream_t)stream>>>(in, r, c, out);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}

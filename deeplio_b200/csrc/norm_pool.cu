@@ -43,7 +43,7 @@ __device__ __forceinline__ float4 relu4(const float4 &a) {
 
 // ------------------------------------------------------------------ input packing
 __global__ void pack_input_kernel(const float *__restrict__ src, long long sn, long long st, long long sc, int T,
-                                  int C, Geo d, float *__restrict__ dst) {
+                                  int C, Geo d, float *__restrict__ dst, float *__restrict__ dst_lo) {
     const unsigned total = (unsigned)d.n * d.hp * d.wp;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int xx = (int)(i % (unsigned)d.wp);
@@ -51,7 +51,6 @@ __global__ void pack_input_kernel(const float *__restrict__ src, long long sn, l
         int yy = (int)(t % (unsigned)d.hp);
         int n = (int)(t / (unsigned)d.hp);
         int h = yy - d.ph, w = xx - d.pw;
-        float *o = dst + (size_t)i * d.c;
         bool in = h >= 0 && h < d.h && w >= 0 && w < d.w;
         for (int c0 = 0; c0 < d.c; c0 += 4) {
             float v[4];
@@ -65,7 +64,7 @@ __global__ void pack_input_kernel(const float *__restrict__ src, long long sn, l
                 }
                 v[j] = x;
             }
-            st4(o + c0, make_float4(v[0], v[1], v[2], v[3]));
+            st4_split(dst, dst_lo, (size_t)i * d.c + c0, make_float4(v[0], v[1], v[2], v[3]));
         }
     }
 }
@@ -503,12 +502,12 @@ __global__ void dropout_mask_kernel(float *mask, long long n, float p, unsigned 
 using namespace dlio;
 
 extern "C" int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
-                               dlio_tensor4 dst, float *dst_ptr, void *stream) {
+                               dlio_tensor4 dst, float *dst_ptr, float *dst_lo, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(src && dst_ptr && valid_t4(dst) && dst.c % 4 == 0 && dst.c >= T * C, "pack_input: bad argument");
     Geo d(dst);
     long long total = (long long)d.n * d.hp * d.wp;
-    pack_input_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, sn, st, sc, T, C, d, dst_ptr);
+    pack_input_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, sn, st, sc, T, C, d, dst_ptr, dst_lo);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

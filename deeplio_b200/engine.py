@@ -116,8 +116,8 @@ def pack_input(run, view, c_pad, ph, pw):
     n, t, c, h, w = view.shape
     if view.stride(4) != 1 or view.stride(3) != w:
         view = view.contiguous()
-    x = Act(n, h, w, c_pad, ph, pw, device=run.device, needs_grad=False)
-    L.pack_input(ptr(view), view.stride(0), view.stride(1), view.stride(2), t, c, x.t4, ptr(x.t), stream())
+    x = Act(n, h, w, c_pad, ph, pw, device=run.device, needs_grad=False, split=USE_TC)
+    L.pack_input(ptr(view), view.stride(0), view.stride(1), view.stride(2), t, c, x.t4, ptr(x.t), ptr(x.lo), stream())
     run.keep.append((x, view))
     return x
 
@@ -142,13 +142,31 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     cv = L.Conv(kh, kw, sh, sw, cph, cpw)
     n = x.n
     fwd_tc = x.lo is not None and tc_ok(cin_pad, cout, stride) and x.ph >= cph and x.pw >= cpw
-    w_ohwi = run.empty(cout, kh, kw, cin_pad)
-    w_lo = torch.empty_like(w_ohwi) if fwd_tc else None    # low-order TF32 plane of the weights
-    L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), ptr(w_lo), st)
+    # first layer (8-channel input): stride-1 kh x 3 convolution over the space-to-depth views (csrc/conv_s2d.cu)
+    s2d = (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7 and x.w % 4 == 0
+           and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0 and not x.needs_grad)
     y = Act(n, ho, wo, cout, device=run.device)
     stats = run.zeros(2 * cout, dtype=torch.float64) if run.training else None
-    L.conv2d_fwd(x.t4, ptr(x.t), ptr(x.lo), ptr(w_ohwi), ptr(w_lo), ptr(b), cv,
-                 L.ACT_RELU if pre_relu else L.ACT_NONE, y.t4, ptr(y.t), ptr(stats), st)
+    act = L.ACT_RELU if pre_relu else L.ACT_NONE
+    w_ohwi = w_lo = None
+    if s2d:
+        R = 4 // sw
+        x4_t4 = L.Tensor4(n, x.h, x.w // 4, 32, x.ph, 1)
+        y4_t4 = L.Tensor4(n, ho, x.w // 4, R * cout, 0, 0)
+        cv4 = L.Conv(kh, 3, 1, 1, cph, 1)
+        w4, w4_lo = run.empty(R * cout, kh, 3, 32), run.empty(R * cout, kh, 3, 32)
+        L.weight_to_s2d(ptr(w), cout, cin, kh, kw, sw, ptr(w4), ptr(w4_lo), st)
+        bias4 = b.repeat(R) if b is not None else None
+        stats4 = run.zeros(2 * R * cout, dtype=torch.float64) if run.training else None
+        L.conv2d_fwd(x4_t4, ptr(x.t), ptr(x.lo), ptr(w4), ptr(w4_lo), ptr(bias4), cv4, act, y4_t4, ptr(y.t),
+                     ptr(stats4), st)
+        if run.training:
+            L.fold_stats(ptr(stats4), R, cout, ptr(stats), st)
+    else:
+        w_ohwi = run.empty(cout, kh, kw, cin_pad)
+        w_lo = torch.empty_like(w_ohwi) if fwd_tc else None    # low-order TF32 plane of the weights
+        L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), ptr(w_lo), st)
+        L.conv2d_fwd(x.t4, ptr(x.t), ptr(x.lo), ptr(w_ohwi), ptr(w_lo), ptr(b), cv, act, y.t4, ptr(y.t), ptr(stats), st)
     bnv = run.empty(4, cout)  # mean, invstd, scale, shift
     count = n * ho * wo
     L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), BN_MOMENTUM, BN_EPS,
@@ -206,7 +224,9 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dgrad_tc = x.needs_grad and tc_ok(cout, cin_pad, stride)
         wgrad_tc = fwd_tc and cout % 128 == 0
         dpad = (x.ph, x.pw) if wgrad_tc else ((kh - 1 - cph, kw - 1 - cpw) if dgrad_tc else (0, 0))
-        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, split=dgrad_tc or wgrad_tc)
+        if s2d:
+            dpad = (x.ph, 4 // sw)    # x's padded grid expressed in output pixels
+        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, split=dgrad_tc or wgrad_tc or s2d)
         dy = dya.t
         dgb = run.empty(2, cout)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
@@ -220,10 +240,16 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             db = run.empty(cout)
             L.f64_to_f32(ptr(dbs), ptr(db), cout, st)
             run.pgrad[cname + ".bias"] = db
-        dw_ohwi = run.empty(cout, kh, kw, cin_pad)
-        L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo), dya.t4, ptr(dy), ptr(dya.lo), cv, ptr(dw_ohwi), st)
         dw = torch.empty_like(w)
-        L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
+        if s2d:
+            dw4 = run.empty(R * cout, kh, 3, 32)
+            L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dy),
+                                ptr(dya.lo), cv4, ptr(dw4), st)
+            L.weight_grad_from_s2d(ptr(dw4), cout, cin, kh, kw, sw, ptr(dw), st)
+        else:
+            dw_ohwi = run.empty(cout, kh, kw, cin_pad)
+            L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo), dya.t4, ptr(dy), ptr(dya.lo), cv, ptr(dw_ohwi), st)
+            L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
         run.pgrad[cname + ".weight"] = dw
         if x.needs_grad:
             wt_hi = wt_lo = None

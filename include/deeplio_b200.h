@@ -80,9 +80,10 @@ int dlio_profile_read(int kind, double *total_ms, long long *launches);
 /* ------------------------------------------------------------------ input staging
  * Replaces imgs.reshape(b*s, t*c, h, w) (lidar_feat_nets.py:216-218): gathers the strided
  * [N, T, C, H, W] view (element strides sn, st, sc; h and w contiguous) into padded NHWC with
- * `dst.c` >= T*C channels (extra channels zero), channel order (t0:c0..c2, t1:c0..c2). */
+ * `dst.c` >= T*C channels (extra channels zero), channel order (t0:c0..c2, t1:c0..c2).  dst_lo (optional): the
+ * low-order TF32 plane for the tensor-core first layer. */
 int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
-                    dlio_tensor4 dst, float *dst_ptr, void *stream);
+                    dlio_tensor4 dst, float *dst_ptr, float *dst_lo, void *stream);
 
 /* ------------------------------------------------------------------ convolution
  * Replaces aten::conv2d forward / dgrad / wgrad behind every nn.Conv2d on the path
@@ -120,6 +121,15 @@ int dlio_weight_to_ohwi(const float *w_oihw, int cout, int cin, int kh, int kw, 
                         float *w_hi, float *w_lo, void *stream);
 int dlio_weight_grad_to_oihw(const float *dw_ohwi, int cout, int cin, int kh, int kw, int cin_pad,
                              float *dw_oihw, void *stream);
+/* First-layer convolutions (cin <= 8, kw <= 7 odd, stride_w 1 or 2) as a stride-1 kh x 3 convolution over the
+ * space-to-depth views [n, h, w/4, 32] -> [n, h, w/4, R*cout], R = 4/stride_w, of the same memory (the input must
+ * be stored with 8 channels and row pads of 4 pixels; see csrc/conv_s2d.cu): weights rearranged to
+ * [R*cout][kh][3][32] (+ lo plane), their gradient folded back to OIHW, and the R-fold BN statistics summed. */
+int dlio_weight_to_s2d(const float *w_oihw, int cout, int cin, int kh, int kw, int sw, float *w4_hi, float *w4_lo,
+                       void *stream);
+int dlio_weight_grad_from_s2d(const float *dw4, int cout, int cin, int kh, int kw, int sw, float *dw_oihw,
+                              void *stream);
+int dlio_fold_stats(const double *in, int r, int c, double *out, void *stream);
 /* dgrad operand for the tcgen05 path: wt[cin][kh'][kw'][cout] = w[cout][kh-1-kh'][kw-1-kw'][cin] */
 int dlio_weight_flip_transpose(const float *w_ohwi, int cout, int cin, int kh, int kw,
                                float *wt_hi, float *wt_lo, void *stream);

@@ -104,17 +104,16 @@ def test_one_adam_step_matches_oracle():
     assert abs(float(loss) - float(oloss)) < 1e-5 * max(1.0, abs(float(oloss)))
     ropt.zero_grad()
     oloss.backward()
+    # (1) the gradient arena holds the model's gradients: whole-model relative L2 error against the oracle
+    ours = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    num = sum(float(((ours[k] - leaves[k].grad) ** 2).sum()) for k in ours)
+    den = sum(float((leaves[k].grad ** 2).sum()) for k in ours)
+    assert (num / den) ** 0.5 < 1e-3
+    # (2) the fused flat-arena step == torch.optim.Adam fed the SAME gradients (single entries of the conv
+    # gradients are ill-conditioned in this 16x128 fixture and Adam's first step is lr * sign(g), so the
+    # optimizer is checked on identical gradients; gradient parity itself is tests/test_gpu_model.py)
+    for k in ours:
+        leaves[k].grad = ours[k].clone()
     ropt.step()
-    # Adam normalises each gradient entry by its own magnitude, so entries whose gradient is round-off-sized
-    # (|g| ~ 1e-9: BN-cancelled conv biases, the dead direction of the last RNN layer) may move by +-lr in either
-    # direction; compare where the oracle's gradient is meaningfully non-zero and bound the rest by lr.
-    worst = 0.0
     for k, p in model.named_parameters():
-        ref, g0 = leaves[k].detach(), leaves[k].grad
-        d = (p.detach().cpu() - ref).abs()
-        # |g| >> eps = 1e-8, so that the first Adam update is lr * sign(g) and not lr * g / eps
-        solid = g0.abs() > torch.maximum(1e-3 * g0.abs().max(), torch.tensor(1e-5))
-        if solid.any():
-            worst = max(worst, float(d[solid].max()))
-        assert float(d.max()) <= 2.1e-3, k
-    assert worst < 2e-5
+        assert (p.detach().cpu() - leaves[k].detach()).abs().max().item() < 2e-6, k
