@@ -1,5 +1,6 @@
 // Shared helpers for the deeplio_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -98,6 +99,54 @@ __device__ __forceinline__ void st4_split(float *hi, float *lo, size_t off, cons
     } else {
         st4(hi + off, v);
     }
+}
+
+// ---------------------------------------------------------------- fp16 operand split ("3xF16", conv_tc.cu)
+// A tensor that feeds the fp16 tensor-core kernels is stored as ONE packed plane of halves, row-major over
+// pixels (or output channels for weights): row r = [C hi halves | C lo halves], with
+//     hi = fp16(s * v),   lo = fp16((s * v - hi) * 2^11),   s = f16_scale_from_bound(bound)
+// where `bound` >= max |v| over the tensor lives in device memory next to it (one float, written by the
+// producer's statistics kernel -- no host round trip).  s is a power of two, so scaling is exact; s * bound lies
+// in (2^13, 2^14], far below the fp16 maximum, and values down to 2^-14 / s keep full 2 x 11-bit precision
+// (smaller ones degrade gracefully to an ABSOLUTE error of 2^-36 / s, ~2^-50 of the tensor's bound).
+// hi*hi + (lo*hi + hi*lo) * 2^-11 reproduces the fp32 product to ~2^-22.
+__host__ __device__ __forceinline__ float f16_scale_from_bound(float bound) {
+    if (!(bound > 0.f) || bound > 3.0e38f) return 1.f;
+    int e;
+    frexpf(bound, &e);          // bound = m * 2^e, m in [0.5, 1)
+    int k = 14 - e;
+    k = k > 80 ? 80 : (k < -80 ? -80 : k);
+    return ldexpf(1.f, k);
+}
+__device__ __forceinline__ void f16_split(float v, __half &hi, __half &lo) {   // v already scaled
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+// stores 4 consecutive channels (c % 4 == 0) of packed row `row` (C channels per half-row)
+__device__ __forceinline__ void st4_h2(__half *base, size_t row, int C, int c, const float4 &v, float s) {
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
+    f16_split(v.x * s, h[0], l[0]);
+    f16_split(v.y * s, h[1], l[1]);
+    f16_split(v.z * s, h[2], l[2]);
+    f16_split(v.w * s, h[3], l[3]);
+    __half *p = base + row * (size_t)(2 * C) + c;
+    *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(h);
+    *reinterpret_cast<uint2 *>(p + C) = *reinterpret_cast<const uint2 *>(l);
+}
+__device__ __forceinline__ void st4_h2_zero(__half *base, size_t row, int C, int c) {
+    __half *p = base + row * (size_t)(2 * C) + c;
+    *reinterpret_cast<uint2 *>(p) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2 *>(p + C) = make_uint2(0u, 0u);
+}
+// atomic max of non-negative floats (their bit patterns order like unsigned integers)
+__device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
+    atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {

@@ -11,6 +11,10 @@ struct ConvArgs {
     int act;
     const float *x_hi, *x_lo;
     const float *w_hi, *w_lo;
+    // fp16 split mode (x_h2 != nullptr): packed hi|lo planes of halves and the device-resident bounds that
+    // define their power-of-two scales (common.cuh, "fp16 operand split"); x_hi .. w_lo are unused then
+    const __half *x_h2 = nullptr, *w_h2 = nullptr;
+    const float *x_bound = nullptr, *w_bound = nullptr;
     const float *bias;
     float *out;          // y (fwd), dx (dgrad), dw (wgrad)
     double *stats;

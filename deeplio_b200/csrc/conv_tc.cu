@@ -27,7 +27,8 @@
 namespace dlio {
 
 constexpr int TC_BM = 128;       // output rows (padded pixels) per CTA
-constexpr int TC_BK = 32;        // fp32 elements per K chunk = one 128-byte swizzle row
+constexpr int TC_BK = 32;        // fp32 elements per K chunk = one 128-byte swizzle row (64 halves in f16 mode)
+constexpr int TC_BK16 = 64;
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM_LIMIT = 200 * 1024;
 
@@ -43,6 +44,8 @@ struct TcArgs {
     float *out;
     double *stats;
     long long rows;    // R = n * hp * wp
+    int f16;           // 0: 3xTF32 on fp32 planes; 1: 3xF16 on packed half planes (K chunk = 64 halves)
+    const float *xb, *wb;   // f16: device bounds of the two operands (-> power-of-two scales)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -90,37 +93,25 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// A-operand collector reuse: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` reads it
-// from there instead of shared memory (the two MMAs that share A_hi read it from smem once).
-__device__ __forceinline__ void umma_tf32_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_alast(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+// MMA kind and A-collector usage are compile-time; `f16` selects kind::f16 (fp16 operands, K = 16 per
+// instruction) over kind::tf32 (K = 8) -- both consume 32 bytes of every operand row per instruction.
+#define DLIO_UMMA_ASM(KIND, COLL)                                                                         \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                      \
+                 "tcgen05.mma.cta_group::1.kind::" KIND COLL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)                                             \
+                 : "memory")
+// coll: 0 plain, 1 collector::a::fill, 2 collector::a::lastuse
+template <int COLL>
+__device__ __forceinline__ void umma(bool f16, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (f16) {
+        if (COLL == 0) DLIO_UMMA_ASM("f16", "");
+        else if (COLL == 1) DLIO_UMMA_ASM("f16", ".collector::a::fill");
+        else DLIO_UMMA_ASM("f16", ".collector::a::lastuse");
+    } else {
+        if (COLL == 0) DLIO_UMMA_ASM("tf32", "");
+        else if (COLL == 1) DLIO_UMMA_ASM("tf32", ".collector::a::fill");
+        else DLIO_UMMA_ASM("tf32", ".collector::a::lastuse");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -150,9 +141,10 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// fp32 accumulate, both operands K-major, M = 128; operand format TF32 (2) or F16 (0)
+__device__ __forceinline__ uint32_t make_idesc(int n, bool f16) {
+    const uint32_t fmt = f16 ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -171,7 +163,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const int S = a.stages;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
 
-    const int cchunks = a.cin / TC_BK;
+    const bool f16 = a.f16 != 0;
+    const int bk = f16 ? TC_BK16 : TC_BK;                   // elements per 128-byte K chunk
+    const int cchunks = a.cin / bk;
     const int iters = a.kh * a.kw * cchunks;
     const long long q0 = (long long)blockIdx.x * TC_BM;
     const int n0 = blockIdx.y * a.bn;
@@ -214,23 +208,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, stage_bytes);
-                tma_load_2d(sa, &tm_xhi, fb, cc * TC_BK, (int)row);
-                tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * TC_BK, (int)row);
+                tma_load_2d(sa, &tm_xhi, fb, cc * bk, (int)row);
+                tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * bk, (int)row);
                 if (a.cluster == 2) {   // each CTA fetches half of the weight tile for both
                     const uint32_t half = b_bytes / 2;
                     const int nh = n0 + (int)cta_rank * (a.bn / 2);
-                    tma_load_2d_mc(sa + 2 * a_bytes + cta_rank * half, &tm_whi, fb, tap * a.cin + cc * TC_BK, nh, 3);
-                    tma_load_2d_mc(sa + 2 * a_bytes + b_bytes + cta_rank * half, &tm_wlo, fb, tap * a.cin + cc * TC_BK, nh, 3);
+                    tma_load_2d_mc(sa + 2 * a_bytes + cta_rank * half, &tm_whi, fb, tap * a.cin + cc * bk, nh, 3);
+                    tma_load_2d_mc(sa + 2 * a_bytes + b_bytes + cta_rank * half, &tm_wlo, fb, tap * a.cin + cc * bk, nh, 3);
                 } else {
-                    tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, tap * a.cin + cc * TC_BK, n0);
-                    tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, tap * a.cin + cc * TC_BK, n0);
+                    tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, tap * a.cin + cc * bk, n0);
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, tap * a.cin + cc * bk, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(a.bn);
+            const uint32_t idesc = make_idesc(a.bn, f16);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -240,11 +234,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 const uint64_t d_ahi = make_kmajor_desc(sa), d_alo = make_kmajor_desc(sa + a_bytes);
                 const uint64_t d_bhi = make_kmajor_desc(sa + 2 * a_bytes), d_blo = make_kmajor_desc(sa + 2 * a_bytes + b_bytes);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
+                for (int k = 0; k < 4; ++k) {                // 128-byte rows / 32 bytes per MMA K step
                     const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
-                    umma_tf32(tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma_tf32_afill(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma_tf32_alast(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                    umma<0>(f16, tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
+                    umma<1>(f16, tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
+                    umma<2>(f16, tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 // frees the smem stage (in both CTAs of a pair) when these MMAs retire
                 if (a.cluster == 2) umma_commit_mc(empty0 + 8 * s, 3);
@@ -269,6 +263,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             if (valid) obase = a.o.off(n, h, w);
         }
         float *tr = reinterpret_cast<float *>(smem) + (size_t)(warp - 2) * 32 * 33;   // pipeline smem is free now
+        // f16: undo the two power-of-two operand scales; the correction accumulator carries another 2^-11
+        float inv_x = 1.f, inv_w = 1.f, corr = 1.f;
+        if (f16) {
+            inv_x = 1.f / f16_scale_from_bound(*a.xb);
+            inv_w = 1.f / f16_scale_from_bound(*a.wb);
+            corr = 1.f / 2048.f;
+        }
         mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = 0; c0 < a.bn; c0 += 32) {
@@ -285,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                float x = fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv_x * inv_w;
                 if (a.bias && j < ncol) x += a.bias[n0 + c0 + j];
                 if (a.act == DLIO_ACT_RELU) x = fmaxf(x, 0.f);
                 f[j] = valid ? x : 0.f;
@@ -349,26 +350,41 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor map: rows x cols (cols contiguous), box box_rows x 32, 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap *m, const float *base, long long rows, long long cols, int box_rows,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+// 2-D tensor map over `rows` x `cols` elements (cols contiguous, rows `row_stride_elems` apart), box
+// box_rows x (128 bytes of elements), zero OOB fill.  half_elems: fp16 elements (64 per box row) instead of fp32 (32).
+static int make_map(CUtensorMap *m, const void *base, bool half_elems, long long rows, long long cols,
+                    long long row_stride_elems, int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
         return DLIO_ERR_CUDA;
     }
+    const size_t esz = half_elems ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_elems * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, half_elems ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r, rows, cols, box_rows);
+        set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d half=%d", (int)r, rows, cols,
+                  box_rows, (int)half_elems);
         return DLIO_ERR_CUDA;
     }
     return DLIO_OK;
+}
+// hi / lo maps of one operand: two fp32 planes, or the two halves of every row of a packed fp16 plane
+static int make_map_pair(CUtensorMap *hi, CUtensorMap *lo, const float *p_hi, const float *p_lo, const __half *p_h2,
+                         long long rows, long long cols, int box_rows,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    int rc;
+    if (p_h2) {
+        if ((rc = make_map(hi, p_h2, true, rows, cols, 2 * cols, box_rows, swizzle))) return rc;
+        return make_map(lo, p_h2 + cols, true, rows, cols, 2 * cols, box_rows, swizzle);
+    }
+    if ((rc = make_map(hi, p_hi, false, rows, cols, cols, box_rows, swizzle))) return rc;
+    return make_map(lo, p_lo, false, rows, cols, cols, box_rows, swizzle);
 }
 
 static int pick_bn(int cout) {
@@ -379,18 +395,21 @@ static int pick_bn(int cout) {
 
 int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     // applicability: split planes present, stride 1, Cin in 128-byte chunks, pads held in memory
-    if (!a.x_lo || !a.w_lo) return 0;
+    const bool f16 = a.x_h2 != nullptr;
+    if (f16 ? !(a.w_h2 && a.x_bound && a.w_bound) : !(a.x_lo && a.w_lo)) return 0;
     if (a.sh != 1 || a.sw != 1) return 0;
-    if (a.cin % TC_BK != 0 || a.cout % 16 != 0) return 0;
+    if (a.cin % (f16 ? TC_BK16 : TC_BK) != 0 || a.cout % 16 != 0) return 0;
     if (a.x.ph < a.ph || a.x.pw < a.pw) return 0;
     if (a.kh != 2 * a.ph + 1 || a.kw != 2 * a.pw + 1) return 0;   // "same" convolution: output extent == input extent
     const int bn = pick_bn(a.cout);
     if (!bn) return 0;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
     if (rows >= (1LL << 31) - 4096) return 0;
-    if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out) & 15) != 0) return 0;
+    if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out |
+          (uintptr_t)a.x_h2 | (uintptr_t)a.w_h2) & 15) != 0) return 0;
 
     TcArgs t;
+    t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.wb = a.w_bound;
     t.x = a.x; t.o = a.o;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw;
     t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.act = a.act;
@@ -405,8 +424,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     CUtensorMap mxh, mxl, mwh, mwl;
     const long long K = (long long)a.kh * a.kw * a.cin;
     int rc;
-    if ((rc = make_map(&mxh, a.x_hi, rows, a.cin, TC_BM))) return rc;
-    if ((rc = make_map(&mxl, a.x_lo, rows, a.cin, TC_BM))) return rc;
+    if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, TC_BM))) return rc;
     const long long mtiles = (rows + TC_BM - 1) / TC_BM;
     // CTA pairs that share the weight tile through TMA multicast are implemented and tested (set to 2), but
     // measured 6 % SLOWER (fwd 8.32 -> 8.81 ms / step): ncu sampling shows the producer waiting on `empty`, i.e.
@@ -414,8 +432,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     // the full 128 B/clk), not by L2 -> SM traffic, and pairing adds lock-step between the two CTAs.
     constexpr bool kPairMulticast = false;
     t.cluster = (kPairMulticast && mtiles >= 2 && bn % 16 == 0) ? 2 : 1;
-    if ((rc = make_map(&mwh, a.w_hi, a.cout, K, bn / t.cluster))) return rc;
-    if ((rc = make_map(&mwl, a.w_lo, a.cout, K, bn / t.cluster))) return rc;
+    if ((rc = make_map_pair(&mwh, &mwl, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn / t.cluster))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -450,21 +467,26 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
 // 128B_ATOM_32B): an atom is 32 channels x 4 pixel rows (512 bytes).  A stage holds 32 pixel rows; each TMA box
 // is [32 rows x 32 channels]; boxes of consecutive 32-channel groups are 4096 bytes apart (LBO), 4-row groups
 // 512 bytes apart (SBO); one K = 8 MMA step spans two row groups (1024 bytes).
+// MN-major FP16 operands (f16 mode) use the plain 128-byte swizzle (layout type 2 <-> TMA SWIZZLE_128B): an atom
+// is 64 channels x 8 pixel rows (1024 bytes).  A stage holds 64 pixel rows; each TMA box is [64 rows x 64
+// channels] = 8192 bytes (LBO), 8-row groups 1024 bytes apart (SBO); one K = 16 MMA step spans two row groups.
 // grid = (K splits, taps * Cin/BN, Cout/128); partial tiles are combined with fp32 atomic adds into dw.
 struct TcWgradArgs {
     int kh, kw, ph, pw, wp;
     int cin, cout, bn, stages;
     long long rows, rows_per_split;
     float *dw;
+    int f16;
+    const float *xb, *yb;   // f16: device bounds of x and dy
 };
 
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, bool f16) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(4096 >> 4) << 16;              // leading byte offset: next 32-channel atom along M / N
-    d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset: next 4-row group along K
+    d |= (uint64_t)((f16 ? 8192 : 4096) >> 4) << 16;   // leading byte offset: next channel atom along M / N
+    d |= (uint64_t)((f16 ? 1024 : 512) >> 4) << 32;    // stride byte offset: next row group along K
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+    d |= (uint64_t)(f16 ? 2 : 1) << 61;                // SWIZZLE_128B / SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -491,7 +513,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     const long long k_begin = (long long)blockIdx.x * a.rows_per_split;
     long long k_end = k_begin + a.rows_per_split;
     if (k_end > a.rows) k_end = a.rows;
-    const int iters = k_end > k_begin ? (int)((k_end - k_begin + TC_BK - 1) / TC_BK) : 0;
+    const bool f16 = a.f16 != 0;
+    const int krows = f16 ? 64 : 32;                        // pixel rows (K) per stage
+    const int bc = f16 ? 64 : 32;                           // channels per TMA box (128 bytes)
+    const uint32_t box_bytes = (uint32_t)krows * 128;
+    const int iters = k_end > k_begin ? (int)((k_end - k_begin + krows - 1) / krows) : 0;
     const int tmem_cols = 4 * a.bn <= 64 ? 64 : (4 * a.bn <= 128 ? 128 : (4 * a.bn <= 256 ? 256 : 512));
     const int nmain = iters < 3 ? iters : 3;
     if (iters == 0) return;   // uniform for the whole CTA
@@ -517,43 +543,44 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            const int nb_boxes = a.bn / 32;
+            const int na_boxes = TC_BM / bc, nb_boxes = a.bn / bc;
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const long long q = k_begin + (long long)it * TC_BK;
+                const long long q = k_begin + (long long)it * krows;
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, stage_bytes);
-                for (int j = 0; j < 4; ++j) {
-                    tma_load_2d(sa + j * 4096, &tm_dyhi, fb, co0 + 32 * j, (int)q);
-                    tma_load_2d(sa + a_bytes + j * 4096, &tm_dylo, fb, co0 + 32 * j, (int)q);
+                for (int j = 0; j < na_boxes; ++j) {
+                    tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, (int)q);
+                    tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, (int)q);
                 }
                 for (int j = 0; j < nb_boxes; ++j) {
-                    tma_load_2d(sa + 2 * a_bytes + j * 4096, &tm_xhi, fb, ci0 + 32 * j, (int)(q + shift));
-                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * 4096, &tm_xlo, fb, ci0 + 32 * j, (int)(q + shift));
+                    tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, ci0 + bc * j, (int)(q + shift));
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, ci0 + bc * j, (int)(q + shift));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // both operands MN-major: bits 15 and 16 of the instruction descriptor
-            const uint32_t idesc = make_idesc_tf32(a.bn) | (1u << 15) | (1u << 16);
+            const uint32_t idesc = make_idesc(a.bn, f16) | (1u << 15) | (1u << 16);
+            const uint64_t kstep = (uint64_t)((f16 ? 2048 : 1024) >> 4);   // one MMA K step = two row groups
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t d_ahi = make_mnmajor_desc(sa), d_alo = make_mnmajor_desc(sa + a_bytes);
-                const uint64_t d_bhi = make_mnmajor_desc(sa + 2 * a_bytes), d_blo = make_mnmajor_desc(sa + 2 * a_bytes + b_bytes);
+                const uint64_t d_ahi = make_mnmajor_desc(sa, f16), d_alo = make_mnmajor_desc(sa + a_bytes, f16);
+                const uint64_t d_bhi = make_mnmajor_desc(sa + 2 * a_bytes, f16), d_blo = make_mnmajor_desc(sa + 2 * a_bytes + b_bytes, f16);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t ko = (uint64_t)(k * (1024 >> 4));   // next 8-row group
-                    umma_tf32(tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma_tf32_afill(tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma_tf32_alast(tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ko = (uint64_t)k * kstep;
+                    umma<0>(f16, tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
+                    umma<1>(f16, tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
+                    umma<2>(f16, tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
             }
@@ -564,6 +591,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
         const int co = co0 + quad * 32 + lane;
         const int taps = a.kh * a.kw;
         float *orow = a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
+        float inv = 1.f, corr = 1.f;
+        if (f16) {
+            inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.yb));
+            corr = 1.f / 2048.f;
+        }
         mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = 0; c0 < a.bn; c0 += 32) {
@@ -581,10 +613,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
             for (int j = 0; j < 32; j += 4)
                 if (j < ncol)
                     atomicAdd(reinterpret_cast<float4 *>(orow + c0 + j),
-                              make_float4(__uint_as_float(v[j]) + __uint_as_float(u[j]),
-                                          __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]),
-                                          __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]),
-                                          __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3])));
+                              make_float4(fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv,
+                                          fmaf(__uint_as_float(u[j + 1]), corr, __uint_as_float(v[j + 1])) * inv,
+                                          fmaf(__uint_as_float(u[j + 2]), corr, __uint_as_float(v[j + 2])) * inv,
+                                          fmaf(__uint_as_float(u[j + 3]), corr, __uint_as_float(v[j + 3])) * inv));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -596,27 +628,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
 
 int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     // a.x: padded input (x_hi / x_lo); a.y: dy geometry (w_hi / w_lo carry dy); a.out = dw [cout][kh][kw][cin]
-    if (!a.x_lo || !a.w_lo) return 0;
+    // f16 mode: x_h2 / w_h2 are the packed planes of x / dy, x_bound / w_bound their bounds
+    const bool f16 = a.x_h2 != nullptr;
+    if (f16 ? !(a.w_h2 && a.x_bound && a.w_bound) : !(a.x_lo && a.w_lo)) return 0;
     if (a.sh != 1 || a.sw != 1) return 0;
     if (a.kh != 2 * a.ph + 1 || a.kw != 2 * a.pw + 1) return 0;
-    if (a.cout % TC_BM != 0 || a.cin % 32 != 0) return 0;
+    const int krows = f16 ? 64 : 32, bc = f16 ? 64 : 32;
+    if (a.cout % TC_BM != 0 || a.cin % bc != 0) return 0;
     // x and dy must share one padded grid, with pads covering the kernel reach
     if (a.x.n != a.y.n || a.x.h != a.y.h || a.x.w != a.y.w || a.x.ph != a.y.ph || a.x.pw != a.y.pw) return 0;
     if (a.x.ph < a.ph || a.x.pw < a.pw) return 0;
     int bn = 0;
     for (int c : {128, 64, 32})
-        if (a.cin % c == 0) { bn = c; break; }
+        if (a.cin % c == 0 && c % bc == 0) { bn = c; break; }
     if (!bn) return 0;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
     if (rows >= (1LL << 31) - 4096) return 0;
-    if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out) & 15) != 0) return 0;
+    if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out |
+          (uintptr_t)a.x_h2 | (uintptr_t)a.w_h2) & 15) != 0) return 0;
 
     const int taps = a.kh * a.kw;
     const int tiles = taps * (a.cin / bn) * (a.cout / TC_BM);
     // K splits: one CTA per SM (192 KB of smem), so the grid should fill whole waves of 148 CTAs -- a grid of
     // 450 CTAs (3.04 waves) ran at 76 % of a 444-CTA one.  Pick the split count whose total is closest below a
     // multiple of 148 among 2..4 waves, keeping at least 64 K chunks per CTA.
-    const long long max_splits = (rows + 64 * TC_BK - 1) / (64 * TC_BK);
+    const long long max_splits = (rows + 64 * krows - 1) / (64 * krows);
     int splits = 1;
     double best_fill = 0.0;
     for (int waves = 2; waves <= 4; ++waves) {
@@ -628,13 +664,14 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
         if (fill > best_fill + 1e-9) { best_fill = fill; splits = s; }
     }
     long long rps = (rows + splits - 1) / splits;
-    rps = (rps + TC_BK - 1) / TC_BK * TC_BK;
+    rps = (rps + krows - 1) / krows * krows;
     if ((rows + rps - 1) / rps < splits) splits = (int)((rows + rps - 1) / rps);
 
     TcWgradArgs t;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw; t.wp = a.x.wp;
     t.cin = a.cin; t.cout = a.cout; t.bn = bn;
     t.rows = rows; t.rows_per_split = rps; t.dw = a.out;
+    t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.yb = a.w_bound;
     const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
     int stages = TC_SMEM_LIMIT / stage_bytes;
     if (stages > 6) stages = 6;
@@ -643,11 +680,9 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
 
     CUtensorMap mdh, mdl, mxh, mxl;
     int rc;
-    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if ((rc = make_map(&mdh, a.w_hi, rows, a.cout, TC_BK, sw))) return rc;
-    if ((rc = make_map(&mdl, a.w_lo, rows, a.cout, TC_BK, sw))) return rc;
-    if ((rc = make_map(&mxh, a.x_hi, rows, a.cin, TC_BK, sw))) return rc;
-    if ((rc = make_map(&mxl, a.x_lo, rows, a.cin, TC_BK, sw))) return rc;
+    const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map_pair(&mdh, &mdl, a.w_hi, a.w_lo, a.w_h2, rows, a.cout, krows, sw))) return rc;
+    if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, krows, sw))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));

@@ -70,33 +70,55 @@ __global__ void pack_input_kernel(const float *__restrict__ src, long long sn, l
 }
 
 // ------------------------------------------------------------------ BN statistics -> scale / shift
-__global__ void bn_finalize_kernel(const double *__restrict__ stats, double count, int c,
+// One block.  out_bound (optional): an upper bound of |scale*y + shift| (+ |residual|) over the tensor, from the
+// BATCH statistics of y whatever statistics define scale/shift:  scale*y + shift = scale*(y - mu_b) + (scale*mu_b +
+// shift) and |y - mu_b| <= sqrt(count * var_b) for every one of the `count` samples.  ReLU and max-pooling only
+// shrink it.  It defines the power-of-two scale of the fp16 split planes the apply pass writes.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const double *__restrict__ stats, double count, int c,
                                    const float *__restrict__ gamma, const float *__restrict__ beta,
                                    float *running_mean, float *running_var, float momentum, float eps,
-                                   int use_running, float *mean, float *invstd, float *scale, float *shift) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
-    float m, is;
-    if (use_running) {
-        m = running_mean[i];
-        is = 1.f / sqrtf(running_var[i] + eps);
-    } else {
-        double mu = stats[i] / count;
-        double var = stats[c + i] / count - mu * mu;
-        if (var < 0.0) var = 0.0;
-        m = (float)mu;
-        is = (float)(1.0 / sqrt(var + (double)eps));
-        if (running_mean) {
-            double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-            running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * m;
-            running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unb;
+                                   int use_running, float *mean, float *invstd, float *scale, float *shift,
+                                   const float *res_bound, float *out_bound) {
+    __shared__ float red[32];
+    float bmax = 0.f;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float m, is;
+        double mu = 0.0, var = 0.0;
+        if (stats) {
+            mu = stats[i] / count;
+            var = stats[c + i] / count - mu * mu;
+            if (var < 0.0) var = 0.0;
+        }
+        if (use_running) {
+            m = running_mean[i];
+            is = 1.f / sqrtf(running_var[i] + eps);
+        } else {
+            m = (float)mu;
+            is = (float)(1.0 / sqrt(var + (double)eps));
+            if (running_mean) {
+                double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * m;
+                running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unb;
+            }
+        }
+        float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+        const float sc = g * is, sf = b - m * g * is;
+        mean[i] = m;
+        invstd[i] = is;
+        scale[i] = sc;
+        shift[i] = sf;
+        if (out_bound) bmax = fmaxf(bmax, (float)(fabs((double)sc) * sqrt(count * var) + fabs((double)sc * mu + (double)sf)));
+    }
+    if (out_bound) {
+        bmax = warp_max(bmax);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bmax;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+            v = warp_max(v);
+            if (threadIdx.x == 0) *out_bound = v * 1.001f + (res_bound ? *res_bound : 0.f);
         }
     }
-    float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
-    mean[i] = m;
-    invstd[i] = is;
-    scale[i] = g * is;
-    shift[i] = b - m * g * is;
 }
 
 // ------------------------------------------------------------------ fused BN-apply / residual / ReLU / max-pool
@@ -105,9 +127,16 @@ struct BnPool {
     const float *yp, *scale, *shift, *resp;
     int res_mode;  // 0 none, 1 added before the activation, 2 added after it
     int relu, pk, sh, sw, c_off, cg;
-    float *out_hi, *out_lo;
+    float *out_hi, *out_lo;     // fp32 plane (may be NULL when only the fp16 planes are wanted), TF32 lo plane
+    __half *out_h2;             // packed fp16 hi|lo planes (optional) and the bound that defines their scale
+    const float *out_bound;
     uint8_t *idx;
 };
+__device__ __forceinline__ void bnpool_store(const BnPool &a, unsigned pix, int c, const float4 &v, float s16) {
+    const size_t o = (size_t)pix * a.out.c + a.c_off + c;
+    if (a.out_hi) st4_split(a.out_hi, a.out_lo, o, v);
+    if (a.out_h2) st4_h2(a.out_h2, pix, a.out.c, a.c_off + c, v, s16);
+}
 
 __device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, int w, int c, const float4 &sc,
                                                const float4 &sf) {
@@ -121,16 +150,15 @@ __device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, in
 
 __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
     const int c = (int)(threadIdx.x % a.cg) * 4;
+    const float s16 = a.out_h2 ? f16_scale_from_bound(*a.out_bound) : 1.f;
     DLIO_PIX_LOOP(pix, a.out.n * a.out.hp * a.out.wp, a.cg) {
         int xx = (int)(pix % (unsigned)a.out.wp);
         unsigned t = pix / (unsigned)a.out.wp;
         int yy = (int)(t % (unsigned)a.out.hp);
         int n = (int)(t / (unsigned)a.out.hp);
-        size_t o = (size_t)pix * a.out.c + a.c_off + c;
         int ho = yy - a.out.ph, wo = xx - a.out.pw;
         if (ho < 0 || ho >= a.out.h || wo < 0 || wo >= a.out.w) {
-            st4(a.out_hi + o, f4(0.f));
-            if (a.out_lo) st4(a.out_lo + o, f4(0.f));
+            bnpool_store(a, pix, c, f4(0.f), 1.f);
             continue;
         }
         float4 sc = f4(1.f), sf = f4(0.f);
@@ -163,7 +191,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
             if (a.idx)
                 *reinterpret_cast<uchar4 *>(a.idx + (((size_t)n * a.out.h + ho) * a.out.w + wo) * a.y.c + c) = bi;
         }
-        st4_split(a.out_hi, a.out_lo, o, best);
+        bnpool_store(a, pix, c, best, s16);
     }
 }
 
@@ -179,6 +207,7 @@ struct BnBwd {
     float *dres;
     int dres_c, dres_acc;
     double *sums;
+    int want_absmax;   // sums[2C] receives max |dz| (bit pattern of a non-negative double, atomicMax)
 };
 
 // Gradient of a 3x3 max-pool (pad 1, stride SH x SW) gathered at input position (h, w): the sum of dout over
@@ -238,6 +267,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
     }
     const float inv_hw = 1.f / (float)(a.y.h * a.y.w);
     float4 s1 = f4(0.f), s2 = f4(0.f);
+    float amax = 0.f;
     DLIO_PIX_LOOP(pix, a.y.n * a.y.h * a.y.w, a.cg) {
         int w = (int)(pix % (unsigned)a.y.w);
         unsigned t = pix / (unsigned)a.y.w;
@@ -270,7 +300,13 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
             float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
             s1 = add4(s1, g);
             s2 = fma4(g, yh, s2);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
         }
+    }
+    if (a.sums && a.want_absmax) {
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0)
+            atomicMax(reinterpret_cast<unsigned long long *>(a.sums + 2 * C), (unsigned long long)__double_as_longlong((double)amax));
     }
     if (a.sums) {
         atomicAdd(&red[c + 0], s1.x); atomicAdd(&red[c + 1], s1.y);
@@ -291,11 +327,34 @@ struct BnApply {
     int pre_relu, batch_stats, cg;
     float *dy_hi, *dy_lo, *dgamma, *dbeta;
     double *dbias;
+    __half *dy_h2;     // packed fp16 hi|lo planes of dy (optional); needs sums[2C] = max |dz|
+    float *dy_bound;   // written by block 0: the bound that defines their scale
 };
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
     __shared__ float red[MAX_C];
+    __shared__ float wred[32];
     const int C = a.cg * 4;
+    float s16 = 1.f;
+    if (a.dy_h2) {
+        // |dy| <= |scale| * (max|dz| + |mean dz| + sqrt(count) * |mean(dz * yhat)|)  (|yhat| <= sqrt(count));
+        // every block derives the same bound (C <= 1024 values), block 0 publishes it for dgrad / wgrad
+        const float mz = (float)a.sums[2 * C];
+        float b = 0.f;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            float t = mz;
+            if (a.batch_stats) t += (float)(fabs(a.sums[i]) / a.count + sqrt(a.count) * fabs(a.sums[C + i]) / a.count);
+            b = fmaxf(b, fabsf(a.scale ? a.scale[i] : 1.f) * t);
+        }
+        b = warp_max(b);
+        if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = b;
+        __syncthreads();
+        b = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) b = fmaxf(b, wred[i]);
+        b *= 1.001f;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.dy_bound = b;
+        s16 = f16_scale_from_bound(b);
+    }
     if (a.dbias) {
         for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
         __syncthreads();
@@ -330,8 +389,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
         int h = yy - a.dy.ph, w = xx - a.dy.pw;
         size_t o = (size_t)pix * C + c;
         if (h < 0 || h >= a.dy.h || w < 0 || w >= a.dy.w) {
-            st4(a.dy_hi + o, f4(0.f));
+            if (a.dy_hi) st4(a.dy_hi + o, f4(0.f));
             if (a.dy_lo) st4(a.dy_lo + o, f4(0.f));
+            if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, C, c);
             continue;
         }
         float4 y = ld4(a.yp + a.y.off(n, h, w) + c);
@@ -345,7 +405,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
             if (!(y.z > 0.f)) d.z = 0.f;
             if (!(y.w > 0.f)) d.w = 0.f;
         }
-        st4_split(a.dy_hi, a.dy_lo, o, d);
+        if (a.dy_hi) st4_split(a.dy_hi, a.dy_lo, o, d);
+        if (a.dy_h2) st4_h2(a.dy_h2, pix, C, c, d, s16);
         sb = add4(sb, d);
     }
     if (a.dbias) {
@@ -515,13 +576,14 @@ extern "C" int dlio_pack_input(const float *src, long long sn, long long st, lon
 extern "C" int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma,
                                 const float *beta, float *running_mean, float *running_var, float momentum,
                                 float eps, int use_running, float *mean, float *invstd, float *scale,
-                                float *shift, void *stream) {
+                                float *shift, const float *res_bound, float *out_bound, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(c > 0 && mean && invstd && scale && shift, "bn_finalize: bad argument");
     DLIO_CHECK_ARG(use_running ? (running_mean && running_var) : (stats && count > 0), "bn_finalize: missing statistics");
-    bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(
+    DLIO_CHECK_ARG(!out_bound || (stats && count > 0), "bn_finalize: the output bound needs the batch statistics");
+    bn_finalize_kernel<<<1, c >= 1024 ? 1024 : (c + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(
         stats, (double)count, c, gamma, beta, running_mean, running_var, momentum, eps, use_running, mean, invstd,
-        scale, shift);
+        scale, shift, res_bound, out_bound);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
@@ -533,9 +595,12 @@ static int check_cg(int c, const char *who) {
 
 extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                                     dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
-                                    float *out_hi, float *out_lo, uint8_t *pool_idx, void *stream) {
+                                    float *out_hi, float *out_lo, void *out_h2, const float *out_bound,
+                                    uint8_t *pool_idx, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(out) && y_ptr && out_hi, "bn_act_pool_fwd: bad argument");
+    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(out) && y_ptr && (out_hi || out_h2), "bn_act_pool_fwd: bad argument");
+    DLIO_CHECK_ARG(!out_h2 || (out_bound && (((uintptr_t)out_h2) & 15) == 0), "bn_act_pool_fwd: fp16 planes need their bound");
+    DLIO_CHECK_ARG(out_hi || !out_lo, "bn_act_pool_fwd: out_lo without out_hi");
     int rc = check_cg(y.c, "bn_act_pool_fwd");
     if (rc) return rc;
     DLIO_CHECK_ARG(p.c_off % 4 == 0 && p.c_off + y.c <= out.c && out.c % 4 == 0, "bn_act_pool_fwd: bad channel offset");
@@ -550,6 +615,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     a.res_mode = p.res_mode; a.relu = p.relu; a.pk = p.pool_k; a.sh = p.pool_sh; a.sw = p.pool_sw;
     a.c_off = p.c_off; a.cg = y.c / 4;
     a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx;
+    a.out_h2 = (__half *)out_h2; a.out_bound = out_bound;
     long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
     bn_act_pool_fwd_kernel<<<grid_for(total, block_for_cg(a.cg), 16), block_for_cg(a.cg), 0, (cudaStream_t)stream>>>(a);
     DLIO_LAUNCH_CHECK();
@@ -561,7 +627,7 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
                                            dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, int grad_src,
                                            dlio_tensor4 dout, const float *dout_ptr, int ld_dout,
                                            const uint8_t *pool_idx, float *dz, float *dres, int dres_c,
-                                           int dres_accumulate, double *sums, void *stream) {
+                                           int dres_accumulate, double *sums, int sums_absmax, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(y) && y_ptr && dout_ptr && dz, "bn_act_pool_bwd_reduce: bad argument");
     int rc = check_cg(y.c, "bn_act_pool_bwd_reduce");
@@ -578,6 +644,8 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
     a.grad_src = grad_src; a.ld_dout = ld_dout;
     a.pooled_h = dout.h; a.pooled_w = dout.w;
     a.idx = pool_idx; a.dz = dz; a.dres = dres; a.dres_c = dres_c; a.dres_acc = dres_accumulate; a.sums = sums;
+    a.want_absmax = sums_absmax;
+    DLIO_CHECK_ARG(!sums_absmax || (sums && y.c % 32 == 0), "bn_act_pool_bwd_reduce: sums_absmax needs sums and c %% 32 == 0");
     int block = block_for_cg(a.cg);
     long long total = (long long)y.n * y.h * y.w * a.cg;
     const int grid = grid_for(total, block, 8);
@@ -598,9 +666,13 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
 extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
                                  long long count, const float *scale, const float *mean, const float *invstd,
                                  int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
-                                 float *dgamma, float *dbeta, double *dbias_sums, void *stream) {
+                                 void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
+                                 void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && dz && dy_hi, "bn_bwd_apply: bad argument");
+    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && dz && (dy_hi || dy_h2), "bn_bwd_apply: bad argument");
+    DLIO_CHECK_ARG(!dy_h2 || (dy_bound && sums && (((uintptr_t)dy_h2) & 15) == 0), "bn_bwd_apply: fp16 planes need sums[2C] and dy_bound");
+    DLIO_CHECK_ARG(!dy_h2 || y.c % 32 == 0, "bn_bwd_apply: fp16 planes need c %% 32 == 0 (whole warps in the bound reduction)");
+    DLIO_CHECK_ARG(dy_hi || !dy_lo, "bn_bwd_apply: dy_lo without dy_hi");
     DLIO_CHECK_ARG(dy_t.n == y.n && dy_t.h == y.h && dy_t.w == y.w && dy_t.c == y.c, "bn_bwd_apply: dy geometry");
     int rc = check_cg(y.c, "bn_bwd_apply");
     if (rc) return rc;
@@ -609,6 +681,7 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
     a.yp = y_ptr; a.dz = dz; a.scale = scale; a.mean = mean; a.invstd = invstd; a.sums = sums;
     a.count = (double)count; a.pre_relu = pre_relu; a.batch_stats = batch_stats; a.cg = y.c / 4;
     a.dy_hi = dy_hi; a.dy_lo = dy_lo; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias_sums;
+    a.dy_h2 = (__half *)dy_h2; a.dy_bound = dy_bound;
     int block = block_for_cg(a.cg);
     long long total = (long long)a.dy.n * a.dy.hp * a.dy.wp * a.cg;
     bn_bwd_apply_kernel<<<grid_for(total, block, 8), block, 0, (cudaStream_t)stream>>>(a);

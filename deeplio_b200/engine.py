@@ -19,10 +19,19 @@ BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
 # tcgen05 (3xTF32) convolution path: stride-1 convolutions whose input has a multiple of 32 channels
 USE_TC = True
+# tcgen05 fp16 split path ("3xF16", twice the TF32 rate): stride-1 convolutions, input channels a multiple of 64;
+# operands are packed fp16 hi|lo planes scaled from device-resident bounds (include/deeplio_b200.h)
+USE_F16 = True
+# debugging aid (scripts/repeat_parity.py): when a dict, every conv_bn backward stores clones of its tensors here
+DEBUG_TRACE = None
 
 
 def tc_ok(cin, cout, stride):
     return USE_TC and tuple(stride) == (1, 1) and cin % 32 == 0 and cout % 16 == 0
+
+
+def f16_ok(cin, cout, stride):
+    return USE_TC and USE_F16 and tuple(stride) == (1, 1) and cin % 64 == 0 and cout % 16 == 0
 
 
 def stream():
@@ -41,16 +50,20 @@ def pool_out(n, s, ceil_mode):
 
 
 class Act:
-    """Padded NHWC fp32 activation: memory [n][h+2ph][w+2pw][c], zero pads."""
-    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "lo", "needs_grad")
+    """Padded NHWC activation: memory [n][h+2ph][w+2pw][c], zero pads.  Up to three representations:
+    ``t`` fp32 (what every non-tensor-core consumer reads), ``lo`` the low-order TF32 plane x - trunc_tf32(x) that
+    goes with ``t`` on the 3xTF32 path, ``h2`` the packed fp16 hi|lo planes [n][hp][wp][2][c] of the 3xF16 path.
+    ``bound`` (device float[1]) >= max |x|: defines the scale of ``h2`` and feeds the bound of a residual sum."""
+    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "lo", "h2", "bound", "needs_grad")
 
-    def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True, split=False, lo=None):
-        """``split``: also allocate the low-order TF32 plane ``lo`` = x - trunc_tf32(x).  ``t`` always holds the
-        full fp32 values (the tensor core reads their top 19 bits), so every other consumer just reads ``t``."""
+    def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True, split=False, lo=None,
+                 f32=True, f16=False):
         self.n, self.h, self.w, self.c, self.ph, self.pw = n, h, w, c, ph, pw
-        self.t = t if t is not None else torch.empty((n, h + 2 * ph, w + 2 * pw, c), device=device,
-                                                     dtype=torch.float32)
+        shape = (n, h + 2 * ph, w + 2 * pw, c)
+        self.t = t if t is not None else (torch.empty(shape, device=device, dtype=torch.float32) if f32 else None)
         self.lo = lo if lo is not None else (torch.empty_like(self.t) if split else None)
+        self.h2 = torch.empty(shape[:3] + (2, c), device=device, dtype=torch.float16) if f16 else None
+        self.bound = None
         self.needs_grad = needs_grad
 
     @property
@@ -123,11 +136,13 @@ def pack_input(run, view, c_pad, ph, pw):
 
 
 def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
-            res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0):
+            res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0,
+            out_f32=True):
     """conv(+bias)(+ReLU if pre_relu) -> BatchNorm (batch statistics when run.training) -> (+res)(ReLU)(+res)
     -> optional 3x3 max-pool, or -> global average into ``feat`` [N, feat_ld] at column feat_off.
 
-    Returns the output Act (None when ``feat`` is given)."""
+    ``out_f32=False``: the caller guarantees that the output is consumed only by fp16 tensor-core convolutions
+    (forward, dgrad and wgrad), so no fp32 copy of it is written.  Returns the output Act (None when ``feat``)."""
     p, st = run.params, stream()
     w = p[cname + ".weight"]
     b = p.get(cname + ".bias")
@@ -141,14 +156,18 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     ho, wo = (x.h + 2 * cph - kh) // sh + 1, (x.w + 2 * cpw - kw) // sw + 1
     cv = L.Conv(kh, kw, sh, sw, cph, cpw)
     n = x.n
-    fwd_tc = x.lo is not None and tc_ok(cin_pad, cout, stride) and x.ph >= cph and x.pw >= cpw
+    pads_ok = x.ph >= cph and x.pw >= cpw
+    fwd_f16 = x.h2 is not None and f16_ok(cin_pad, cout, stride) and pads_ok
+    fwd_tc = (not fwd_f16) and x.lo is not None and tc_ok(cin_pad, cout, stride) and pads_ok
     # first layer (8-channel input): stride-1 kh x 3 convolution over the space-to-depth views (csrc/conv_s2d.cu)
     s2d = (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7 and x.w % 4 == 0
            and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0 and not x.needs_grad)
+    assert fwd_f16 or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
     y = Act(n, ho, wo, cout, device=run.device)
-    stats = run.zeros(2 * cout, dtype=torch.float64) if run.training else None
+    # the batch statistics also bound the BN output (-> scale of the fp16 planes), so they are taken in eval mode too
+    stats = run.zeros(2 * cout, dtype=torch.float64)
     act = L.ACT_RELU if pre_relu else L.ACT_NONE
-    w_ohwi = w_lo = None
+    w_ohwi = w_lo = w_h2 = w_bound = None
     if s2d:
         R = 4 // sw
         x4_t4 = L.Tensor4(n, x.h, x.w // 4, 32, x.ph, 1)
@@ -157,20 +176,32 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         w4, w4_lo = run.empty(R * cout, kh, 3, 32), run.empty(R * cout, kh, 3, 32)
         L.weight_to_s2d(ptr(w), cout, cin, kh, kw, sw, ptr(w4), ptr(w4_lo), st)
         bias4 = b.repeat(R) if b is not None else None
-        stats4 = run.zeros(2 * R * cout, dtype=torch.float64) if run.training else None
+        stats4 = run.zeros(2 * R * cout, dtype=torch.float64)
         L.conv2d_fwd(x4_t4, ptr(x.t), ptr(x.lo), ptr(w4), ptr(w4_lo), ptr(bias4), cv4, act, y4_t4, ptr(y.t),
                      ptr(stats4), st)
-        if run.training:
-            L.fold_stats(ptr(stats4), R, cout, ptr(stats), st)
+        L.fold_stats(ptr(stats4), R, cout, ptr(stats), st)
+    elif fwd_f16:
+        w_bound = run.empty(1)
+        w_h2 = run.empty(cout, 2, kh * kw * cin_pad, dtype=torch.float16)
+        L.weight_pack_f16(ptr(w), cout, cin, kh, kw, cin_pad, 0, 1, ptr(w_bound), ptr(w_h2), st)
+        L.conv2d_fwd_f16(x.t4, ptr(x.h2), ptr(x.bound), ptr(w_h2), ptr(w_bound), ptr(b), cv, act, y.t4, ptr(y.t),
+                         ptr(stats), st)
     else:
         w_ohwi = run.empty(cout, kh, kw, cin_pad)
         w_lo = torch.empty_like(w_ohwi) if fwd_tc else None    # low-order TF32 plane of the weights
         L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(w_ohwi), ptr(w_lo), st)
-        L.conv2d_fwd(x.t4, ptr(x.t), ptr(x.lo), ptr(w_ohwi), ptr(w_lo), ptr(b), cv, act, y.t4, ptr(y.t), ptr(stats), st)
+        L.conv2d_fwd(x.t4, ptr(x.t), ptr(x.lo) if fwd_tc else None, ptr(w_ohwi), ptr(w_lo), ptr(b), cv, act, y.t4,
+                     ptr(y.t), ptr(stats), st)
     bnv = run.empty(4, cout)  # mean, invstd, scale, shift
     count = n * ho * wo
+    # the output of a Fire concat has two producers with separate statistics: no common bound, no fp16 planes
+    single = out is None and c_off == 0 and out_c is None
+    out_bound = run.empty(1) if (single and feat is None) else None
+    if res is not None and out_bound is not None and res.bound is None:
+        out_bound = None
     L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), BN_MOMENTUM, BN_EPS,
-                  0 if run.training else 1, ptr(bnv[0]), ptr(bnv[1]), ptr(bnv[2]), ptr(bnv[3]), st)
+                  0 if run.training else 1, ptr(bnv[0]), ptr(bnv[1]), ptr(bnv[2]), ptr(bnv[3]),
+                  ptr(res.bound) if (res is not None and out_bound is not None) else None, ptr(out_bound), st)
     if run.training:
         nbt = run.buffers.get(bname + ".num_batches_tracked")
         if nbt is not None:
@@ -187,16 +218,20 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         oh, ow = (pool_out(ho, pool[0], ceil), pool_out(wo, pool[1], ceil)) if pool else (ho, wo)
         if out is None:
             oc = out_c or cout
-            out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, split=USE_TC and oc % 32 == 0)
+            o16 = USE_TC and USE_F16 and out_bound is not None and oc % 64 == 0
+            assert out_f32 or o16, (cname, "out_f32=False needs an fp16-capable output")
+            out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, f32=out_f32, f16=o16,
+                      split=USE_TC and out_f32 and not o16 and oc % 32 == 0)
+            out.bound = out_bound
         assert out.h == oh and out.w == ow and out.n == n
         if pool and run.record:
             idx = run.empty(n, oh, ow, cout, dtype=torch.uint8)
         L.bn_act_pool_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), res.t4 if res is not None else dummy,
-                          ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(idx), st)
+                          ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(out.h2),
+                          ptr(out.bound) if out.h2 is not None else None, ptr(idx), st)
         result = out
     if not run.record:
         return result
-
     def bwd():
         st = stream()
         if feat is not None:
@@ -208,8 +243,18 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             dout = run.agrad.pop(id(out)) if c_off == 0 else run.agrad[id(out)]
             src, dout_t4, ld = (L.GRAD_POOL if pool else L.GRAD_DIRECT), out.t4_unpadded, 0
             bpb = bp
+        # which kernels consume dy: 3xF16 / 3xTF32 tensor-core kernels or the fp32 CUDA-core ones
+        if s2d:
+            wg, dg = "tf32", None
+        else:
+            wg = "f16" if (fwd_f16 and cout % 128 == 0) else ("tf32" if (fwd_tc and cout % 128 == 0) else "simt")
+            dg = None
+            if x.needs_grad:
+                dg = ("f16" if (f16_ok(cout, cin_pad, stride)) else ("tf32" if tc_ok(cout, cin_pad, stride) else "simt"))
+        assert wg != "simt" or x.t is not None, (cname, "wgrad on the CUDA cores needs the fp32 input plane")
+        modes = (wg, dg)
         dz = run.empty(n, ho, wo, cout)
-        sums = run.zeros(2 * cout, dtype=torch.float64)
+        sums = run.zeros(2 * cout + 1, dtype=torch.float64)
         dres, dres_c, dres_acc = None, 0, 0
         if res is not None and res.needs_grad:
             partial = res.c != cout
@@ -218,21 +263,25 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         L.bn_act_pool_bwd_reduce(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), ptr(bnv[0]), ptr(bnv[1]),
                                  res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
                                  bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
-                                 ptr(sums), st)
+                                 ptr(sums), 1 if "f16" in modes else 0, st)
         # backward on the tensor cores: dy is produced as padded split planes.  wgrad wants dy on x's padded grid,
         # dgrad wants pads >= (k - 1 - pad); x's pads satisfy both for the "same" stride-1 convolutions.
-        dgrad_tc = x.needs_grad and tc_ok(cout, cin_pad, stride)
-        wgrad_tc = fwd_tc and cout % 128 == 0
-        dpad = (x.ph, x.pw) if wgrad_tc else ((kh - 1 - cph, kw - 1 - cpw) if dgrad_tc else (0, 0))
+        on_x_grid = wg in ("f16", "tf32")
+        dpad = (x.ph, x.pw) if on_x_grid else ((kh - 1 - cph, kw - 1 - cpw) if dg in ("f16", "tf32") else (0, 0))
         if s2d:
             dpad = (x.ph, 4 // sw)    # x's padded grid expressed in output pixels
-        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, split=dgrad_tc or wgrad_tc or s2d)
-        dy = dya.t
+        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
+                  split="tf32" in modes, f16="f16" in modes)
+        dya.bound = run.empty(1) if dya.h2 is not None else None
         dgb = run.empty(2, cout)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
         L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
-                       1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dy), ptr(dya.lo), ptr(dgb[0]),
-                       ptr(dgb[1]), ptr(dbs), st)
+                       1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t), ptr(dya.lo), ptr(dya.h2),
+                       ptr(dya.bound), ptr(dgb[0]), ptr(dgb[1]), ptr(dbs), st)
+        if DEBUG_TRACE is not None:
+            DEBUG_TRACE[(id(run), cname)] = dict(dout=dout.clone(), dz=dz.clone(), sums=sums.clone(),
+                                                 dy=(dya.t if dya.t is not None else dya.h2).clone(), y=y.t.clone(),
+                                                 bnv=bnv.clone())
         del dz
         run.pgrad[bname + ".weight"] = dgb[0]
         run.pgrad[bname + ".bias"] = dgb[1]
@@ -243,20 +292,36 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dw = torch.empty_like(w)
         if s2d:
             dw4 = run.empty(R * cout, kh, 3, 32)
-            L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dy),
+            L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dya.t),
                                 ptr(dya.lo), cv4, ptr(dw4), st)
             L.weight_grad_from_s2d(ptr(dw4), cout, cin, kh, kw, sw, ptr(dw), st)
         else:
             dw_ohwi = run.empty(cout, kh, kw, cin_pad)
-            L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo), dya.t4, ptr(dy), ptr(dya.lo), cv, ptr(dw_ohwi), st)
+            if wg == "f16":
+                L.conv2d_bwd_weight_f16(x.t4, ptr(x.h2), ptr(x.bound), dya.t4, ptr(dya.h2), ptr(dya.bound), cv,
+                                        ptr(dw_ohwi), st)
+            else:
+                L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo) if wg == "tf32" else None, dya.t4, ptr(dya.t),
+                                    ptr(dya.lo) if wg == "tf32" else None, cv, ptr(dw_ohwi), st)
             L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
         run.pgrad[cname + ".weight"] = dw
-        if x.needs_grad:
+        if dg == "f16":
+            wb = w_bound if w_bound is not None else run.empty(1)
+            wt_h2 = run.empty(cin_pad, 2, kh * kw * cout, dtype=torch.float16)
+            L.weight_pack_f16(ptr(w), cout, cin, kh, kw, cin_pad, 1, 0 if w_bound is not None else 1, ptr(wb),
+                              ptr(wt_h2), st)
+            run.add_grad(x, lambda buf: L.conv2d_bwd_data_f16(dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2), ptr(wb),
+                                                              cv, x.t4_unpadded, ptr(buf), st))
+        elif dg is not None:
+            wo_, wl_ = w_ohwi, w_lo
+            if wo_ is None:
+                wo_ = run.empty(cout, kh, kw, cin_pad)
+                L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(wo_), None, st)
             wt_hi = wt_lo = None
-            if dgrad_tc:
-                wt_hi, wt_lo = torch.empty_like(w_ohwi), torch.empty_like(w_ohwi)
-                L.weight_flip_transpose(ptr(w_ohwi), cout, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
-            run.add_grad(x, lambda buf: L.conv2d_bwd_data(dya.t4, ptr(dy), ptr(dya.lo), ptr(w_ohwi), ptr(w_lo),
+            if dg == "tf32":
+                wt_hi, wt_lo = torch.empty_like(wo_), torch.empty_like(wo_)
+                L.weight_flip_transpose(ptr(wo_), cout, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
+            run.add_grad(x, lambda buf: L.conv2d_bwd_data(dya.t4, ptr(dya.t), ptr(dya.lo), ptr(wo_), ptr(wl_),
                                                           ptr(wt_hi), ptr(wt_lo), cv, x.t4_unpadded, ptr(buf), st))
 
     run.tape.append(bwd)
@@ -277,6 +342,7 @@ def se_layer(run, x, prefix, out_pad=(0, 0)):
     L.linear_fwd(ptr(hid), cr, ptr(w2), None, n, c, cr, L.ACT_SIGMOID, ptr(gate), c, st)
     out = Act(n, x.h, x.w, c, out_pad[0], out_pad[1], device=run.device, split=USE_TC and c % 32 == 0)
     L.channel_scale_fwd(x.t4, ptr(x.t), ptr(gate), out.t4, ptr(out.t), ptr(out.lo), st)
+    out.bound = x.bound       # gate <= 1
     if not run.record:
         return out
 
@@ -307,7 +373,9 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
     out = Act(x.n, oh, ow, x.c, out_pad[0], out_pad[1], device=run.device, split=USE_TC and x.c % 32 == 0)
     bp = L.BnPool(0, 0, 3, stride[0], stride[1], 0)
     idx = run.empty(x.n, oh, ow, x.c, dtype=torch.uint8) if run.record else None
-    L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(idx), st)
+    L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), ptr(out.lo), None, None,
+                      ptr(idx), st)
+    out.bound = x.bound
     if not run.record:
         return out
 
@@ -315,7 +383,7 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
         dout = run.agrad.pop(id(out))
         run.add_grad(x, lambda buf: L.bn_act_pool_bwd_reduce(
             x.t4, ptr(x.t), None, None, None, None, x.t4, None, bp, L.GRAD_POOL, out.t4_unpadded, ptr(dout), 0,
-            ptr(idx), ptr(buf), None, 0, 0, None, stream()))
+            ptr(idx), ptr(buf), None, 0, 0, None, 0, stream()))
 
     run.tape.append(bwd)
     run.keep.append((x, out))
@@ -333,7 +401,7 @@ def global_avg(run, x, feat, feat_ld, feat_off):
         dout = run.fgrad[id(feat)]
         run.add_grad(x, lambda buf: L.bn_act_pool_bwd_reduce(
             x.t4, ptr(x.t), None, None, None, None, x.t4, None, bp, L.GRAD_AVG, x.t4, ptr(dout), feat_ld, None,
-            ptr(buf), None, 0, 0, None, stream()))
+            ptr(buf), None, 0, 0, None, 0, stream()))
 
     run.tape.append(bwd)
     run.keep.append((x,))

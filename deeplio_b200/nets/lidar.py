@@ -57,9 +57,10 @@ class Simple1Encoder(_Encoder):
             cin = cout
 
     def program(self, run, x, feat, ld, off):
+        # every intermediate feeds only a stride-1 convolution with >= 128 output channels: fp16 planes suffice
         def blk(i, t, stride=(1, 1), pool=None, pad=(1, 1), **kw):
             return E.conv_bn(run, t, "conv%d" % i, "bn%d" % i, stride, pre_relu=True, relu=False, pool=pool,
-                             ceil=True, out_pad=pad, **kw)
+                             ceil=True, out_pad=pad, out_f32=not (E.USE_TC and E.USE_F16) or "feat" in kw, **kw)
         t = blk(1, x, (1, 2), pool=(1, 2), pad=(1, 2))
         t = blk(2, t, pool=(1, 2))
         t = blk(3, t)

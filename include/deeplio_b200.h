@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
- *   - all floating-point data is IEEE fp32; statistics accumulators are fp64;
+ *   - all floating-point data is IEEE fp32; statistics accumulators are fp64; the operands of the fp16
+ *     tensor-core kernels are "packed split planes" derived from fp32 tensors (see "fp16 operand split" below);
  *   - activations are "padded NHWC": memory [n][h + 2*ph][w + 2*pw][c] with ZERO pad rows / columns,
  *     described by dlio_tensor4 (the pads are those of the convolution that consumes the tensor);
  *   - convolution weights are OHWI: [cout][kh][kw][cin] (a channels_last nn.Conv2d weight, zero-copy);
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 1
+#define DLIO_ABI_VERSION 2
 
 typedef enum {
     DLIO_OK = 0,
@@ -58,6 +59,15 @@ typedef struct {
     int sh, sw; /* stride */
     int ph, pw; /* zero padding */
 } dlio_conv;
+
+/* ------------------------------------------------------------------ fp16 operand split ("3xF16")
+ * The tensor-core convolutions compute fp32-accurate products from fp16 operands: a tensor v[rows][C] (rows =
+ * padded pixels, or output channels for weights) is stored as ONE plane of halves, row r = [C hi | C lo],
+ *     hi = fp16(s*v),  lo = fp16((s*v - hi) * 2^11),  s = 2^(14 - ceil(log2(bound)))   (|v| <= bound)
+ * and the kernels accumulate hi*hi and (lo*hi + hi*lo) in separate fp32 accumulators, then undo s and 2^11.
+ * `bound` is ONE float in device memory per tensor, written by the kernel that produces the tensor's statistics
+ * (dlio_bn_finalize, dlio_bn_bwd_apply, dlio_weight_pack_f16) and read by the kernels that write or consume the
+ * planes -- the scale never visits the host.  A void* named *_h2 is such a plane; *_bound is its bound. */
 
 /* ------------------------------------------------------------------ library */
 int dlio_abi_version(void);
@@ -134,6 +144,25 @@ int dlio_fold_stats(const double *in, int r, int c, double *out, void *stream);
 int dlio_weight_flip_transpose(const float *w_ohwi, int cout, int cin, int kh, int kw,
                                float *wt_hi, float *wt_lo, void *stream);
 
+/* fp16 tensor-core path (tcgen05 kind::f16, three products per fp32 product).  Same semantics as the three
+ * calls above for stride-1 "same" convolutions with cin % 64 == 0 (wgrad also: cout % 128 == 0; dgrad: cout % 64
+ * == 0, cin % 16 == 0), operands given as packed split planes; there is no fallback: an inapplicable problem
+ * returns DLIO_ERR_INVALID.
+ *   dlio_weight_pack_f16: OIHW fp32 -> packed OHWI rows [cout][2][kh*kw*cin_pad] (transpose_flip == 0), or the
+ *   dgrad operand [cin_pad][2][kh*kw*cout], wt[ci][kh'][kw'][co] = w[co][ci][kh-1-kh'][kw-1-kw'] (transpose_flip
+ *   != 0).  compute_bound != 0: first reduces max |w| into *w_bound; otherwise *w_bound is read. */
+int dlio_weight_pack_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int cin_pad, int transpose_flip,
+                         int compute_bound, float *w_bound, void *w_h2, void *stream);
+int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, const void *w_h2,
+                        const float *w_bound, const float *bias, dlio_conv cv, int act, dlio_tensor4 y,
+                        float *y_ptr, double *stats, void *stream);
+int dlio_conv2d_bwd_data_f16(dlio_tensor4 dy, const void *dy_h2, const float *dy_bound, const void *wt_h2,
+                             const float *w_bound, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, void *stream);
+int dlio_conv2d_bwd_weight_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, dlio_tensor4 dy,
+                               const void *dy_h2, const float *dy_bound, dlio_conv cv, float *dw, void *stream);
+/* fp32 [rows][c] -> packed split plane, computing the bound (max |v|) first; test / staging helper */
+int dlio_pack_f16(const float *src, long long rows, int c, float *bound, void *dst_h2, void *stream);
+
 /* ------------------------------------------------------------------ batch-norm / activation / pooling
  * Replaces aten::batch_norm (train + eval), relu, max_pool2d_with_indices, adaptive_avg_pool2d and the
  * residual / bypass adds around them (lidar_feat_nets.py:306-342; base_net.py:55-71; pointseg_modules.py
@@ -143,10 +172,14 @@ int dlio_weight_flip_transpose(const float *w_ohwi, int cout, int cin, int kh, i
  *   mean, invstd = 1/sqrt(biased_var + eps), scale = gamma*invstd, shift = beta - mean*scale and updates
  *   running_mean / running_var (unbiased var, `momentum`).  With use_running != 0 (eval mode) scale/shift
  *   come from the running statistics and nothing is updated.  Outputs are [c] fp32 each.
+ *   out_bound (optional, needs stats): an upper bound of |scale*y + shift| over the tensor (+ *res_bound when
+ *   a residual will be added), from |y - mean_b| <= sqrt(count * var_b); it scales the fp16 planes that
+ *   dlio_bn_act_pool_fwd writes.
  */
 int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma, const float *beta,
                      float *running_mean, float *running_var, float momentum, float eps, int use_running,
-                     float *mean, float *invstd, float *scale, float *shift, void *stream);
+                     float *mean, float *invstd, float *scale, float *shift, const float *res_bound,
+                     float *out_bound, void *stream);
 
 typedef struct {
     int relu;       /* 1: apply ReLU after scale*y + shift (+ residual if res_mode == 1) */
@@ -159,11 +192,14 @@ typedef struct {
 
 /* out[n,ho,wo,c_off+c] = maxpool(act(scale[c]*y + shift[c] (+res)) (+res)); writes out's pads as zeros for
  * the channel range.  scale == shift == NULL means identity (plain max-pool / copy into a padded tensor).
- * out_lo (optional): low-order TF32 plane, v - trunc_tf32(v) (out_hi always receives the full fp32 value).  pool_idx (uint8 [n,ho,wo,c], required when pooling is
+ * out_lo (optional): low-order TF32 plane, v - trunc_tf32(v) (out_hi always receives the full fp32 value).
+ * out_h2 / out_bound (optional): packed fp16 split planes on out's padded grid, scaled from *out_bound; out_hi
+ * may then be NULL (no fp32 copy is written).  pool_idx (uint8 [n,ho,wo,c], required when pooling is
  * differentiated): window-relative arg-max, first maximum wins (torch tie-break). */
 int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                          dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
-                         float *out_hi, float *out_lo, uint8_t *pool_idx, void *stream);
+                         float *out_hi, float *out_lo, void *out_h2, const float *out_bound,
+                         uint8_t *pool_idx, void *stream);
 
 typedef enum { DLIO_GRAD_DIRECT = 0, DLIO_GRAD_POOL = 1, DLIO_GRAD_AVG = 2 } dlio_grad_src;
 
@@ -172,22 +208,26 @@ typedef enum { DLIO_GRAD_DIRECT = 0, DLIO_GRAD_POOL = 1, DLIO_GRAD_AVG = 2 } dli
  * when there is no BN).  grad_src: DIRECT / POOL  dout is an (unpadded or padded) NHWC gradient of the
  * op's output, read at channel c_off; AVG  dout is [n, ld_dout] read at c_off and spread as 1/(h*w).
  * dres (optional, unpadded [n,h,w,dres_c], written at channel c_off): gradient of the residual input;
- * overwritten, or added to when dres_accumulate != 0. */
+ * overwritten, or added to when dres_accumulate != 0.  sums_absmax != 0: sums has 2c+1 entries and sums[2c]
+ * receives max |dz| (what dlio_bn_bwd_apply needs to scale fp16 planes of dy). */
 int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                                 const float *mean, const float *invstd,
                                 dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, int grad_src,
                                 dlio_tensor4 dout, const float *dout_ptr, int ld_dout, const uint8_t *pool_idx,
                                 float *dz, float *dres, int dres_c, int dres_accumulate, double *sums,
-                                void *stream);
+                                int sums_absmax, void *stream);
 
 /* backward pass 2: dy = scale * (dz - mean(dz) - yhat * mean(dz*yhat)) (batch_stats != 0) or scale * dz
  * (eval-mode BN); if pre_relu (conv -> ReLU -> BN, lidar_feat_nets.py:308-309) dy *= (y > 0).  Writes dy
  * (geometry dy_t, zero pads, optional TF32 split), dgamma[c], dbeta[c] and accumulates
- * dbias_sums[c] += sum dy (fp64, caller zeroes; may be NULL). */
+ * dbias_sums[c] += sum dy (fp64, caller zeroes; may be NULL).  dy_h2 / dy_bound (optional; needs sums[2c] =
+ * max |dz|): dy as packed fp16 split planes, and the bound it was scaled from (OUTPUT, for dgrad / wgrad);
+ * dy_hi may then be NULL. */
 int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
                       long long count, const float *scale, const float *mean, const float *invstd,
                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
-                      float *dgamma, float *dbeta, double *dbias_sums, void *stream);
+                      void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
+                      void *stream);
 int dlio_f64_to_f32(const double *src, float *dst, int n, void *stream);
 
 /* global average pooling (adaptive_avg_pool2d((1,1)), lidar_feat_nets.py:84-85,131,175,340; SE squeeze,

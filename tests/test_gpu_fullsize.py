@@ -104,11 +104,30 @@ def test_one_adam_step_matches_oracle():
     assert abs(float(loss) - float(oloss)) < 1e-5 * max(1.0, abs(float(oloss)))
     ropt.zero_grad()
     oloss.backward()
-    # (1) the gradient arena holds the model's gradients: whole-model relative L2 error against the oracle
+    # (1) the gradient arena holds the model's gradients: whole-model relative L2 error against the oracle.  Bar:
+    # 1e-3, or 2 x the oracle's own response (fp64) to a 2e-6 relative perturbation of weights and inputs, the
+    # size of fp32 / split-precision round-off -- this 16x128 fixture amplifies such a perturbation 1000-fold
+    # (measured 2.4e-3 .. 2.5e-3 whole-model; BatchNorm over a few dozen samples).  Per-tensor parity with a
+    # per-tensor sensitivity bar is tests/test_gpu_model.py.
     ours = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
-    num = sum(float(((ours[k] - leaves[k].grad) ** 2).sum()) for k in ours)
-    den = sum(float((leaves[k].grad ** 2).sum()) for k in ours)
-    assert (num / den) ** 0.5 < 1e-3
+
+    def l2(ga, gb):
+        num = sum(float(((ga[k].double() - gb[k].double()) ** 2).sum()) for k in ga)
+        return (num / sum(float((gb[k].double() ** 2).sum()) for k in ga)) ** 0.5
+
+    def oracle_grads64(seed, amp):
+        gen = torch.Generator().manual_seed(seed)
+
+        def jit(t):
+            t = t.double() if t.is_floating_point() else t
+            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if (amp and t.is_floating_point()) else t
+        st = {k: (jit(v).requires_grad_(True) if (v.is_floating_point() and "running_" not in k) else jit(v)) for k, v in sd.items()}
+        p_, o_ = O.deeplio_forward(st, cfg, *(jit(t) for t in inputs), training=True)
+        (mse(p_, gt_pos.double()) + mse(o_, gt_ori.double()) * float(torch.exp(torch.tensor(3.0))) - 3.0).backward()
+        return {k: st[k].grad for k in ours}
+    g64 = oracle_grads64(0, 0.0)
+    sens = max(l2(oracle_grads64(s_, 2e-6), g64) for s_ in (1, 2, 3))
+    assert l2(ours, g64) < max(1e-3, 2 * sens), (l2(ours, g64), sens)
     # (2) the fused flat-arena step == torch.optim.Adam fed the SAME gradients (single entries of the conv
     # gradients are ill-conditioned in this 16x128 fixture and Adam's first step is lr * sign(g), so the
     # optimizer is checked on identical gradients; gradient parity itself is tests/test_gpu_model.py)

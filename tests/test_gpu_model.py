@@ -56,18 +56,24 @@ def test_model_matches_oracle_and_golden(name):
     # near-constant channel multiplies noise by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5
     # turns a 1e-6 input change into a 30 % change of its weight gradient).  The bar per tensor is therefore
     # max(GRAD_TOL, 4 x its measured sensitivity), where the sensitivity is the larger of (a) the fp32
-    # reference's own distance from fp64 and (b) the change of the fp64 gradient when every weight and input is
-    # perturbed by 2e-6 relative (the size of fp32 / 3xTF32 round-off).
+    # reference's own distance from fp64 and (b) the largest change of the fp64 gradient over several draws of a
+    # 2e-6 .. 4e-6 relative perturbation of every weight and input (the size of fp32 / split-precision round-off).
+    # Several draws, because the dominant effect is discrete: one ReLU input within ~1e-6 of zero flips its mask
+    # in some draws and not in others (scripts/repeat_parity.py shows the B200 path itself landing on either
+    # side from run to run, through the summation order of the fp64 statistics atomics), and with 64 samples
+    # per channel one flip moves that layer's gradients by 10-30 %.
     def f64(t):
         return t.double() if t.is_floating_point() else t
     sd64 = {k: f64(v) for k, v in sd.items()}
     in64 = tuple(t.double() for t in inputs)
     _, _, g64, _ = oracle_train_step(cfg, sd64, in64)
-    gen = torch.Generator().manual_seed(99)
+    gperts = []
+    for seed, amp in ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)):
+        gen = torch.Generator().manual_seed(seed)
 
-    def jitter(t):
-        return t * (1.0 + 2e-6 * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
-    _, _, gpert, _ = oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))
+        def jitter(t):
+            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
+        gperts.append(oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))[2])
     gmax = max(float(n) for n, _ in rec["grads"].values())
     params = dict(model.named_parameters())
     assert set(params) == set(ograds)
@@ -76,7 +82,7 @@ def test_model_matches_oracle_and_golden(name):
         g = p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])
         scale = g64[k].abs().max().item()
         e_ref = (ograds[k].double() - g64[k]).abs().max().item()
-        e_pert = (gpert[k] - g64[k]).abs().max().item()
+        e_pert = max((gp[k] - g64[k]).abs().max().item() for gp in gperts)
         e_ours = (g.double() - g64[k]).abs().max().item()
         sens = max(e_ref, e_pert)
         assert e_ours <= max(GRAD_TOL * scale, 4 * sens) + 1e-5 * gmax, (k, e_ours, e_ref, e_pert, scale)

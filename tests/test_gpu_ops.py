@@ -106,8 +106,101 @@ def split_padded(L, x, ph, pw):
     lo = torch.empty_like(hi)
     t_src, t_dst = L.Tensor4(n, h, w, c, 0, 0), L.Tensor4(n, h, w, c, ph, pw)
     L.bn_act_pool_fwd(t_src, src.data_ptr(), None, None, t_src, None, L.BnPool(0, 0, 1, 1, 1, 0), t_dst, hi.data_ptr(),
-                      lo.data_ptr(), None, _st())
+                      lo.data_ptr(), None, None, None, _st())
     return hi, lo
+
+
+def pack_f16(L, x, ph, pw):
+    """NCHW cpu -> (packed fp16 hi|lo planes [n, hp, wp, 2, c], bound[1]) through dlio_pack_f16."""
+    src = to_padded_nhwc(x, ph, pw)
+    n, hp, wp, c = src.shape
+    h2 = torch.empty(n, hp, wp, 2, c, dtype=torch.float16, device=DEV)
+    bound = torch.full((1,), float("nan"), device=DEV)
+    L.pack_f16(src.data_ptr(), n * hp * wp, c, bound.data_ptr(), h2.data_ptr(), _st())
+    return h2, bound, src
+
+
+F16_CASES = [
+    # n, cin, cout, h, w, (kh, kw), bias, act, extra tensor pad, magnitude of x, magnitude of dy
+    (2, 64, 128, 9, 33, (3, 5), True, 1, 0, 1.0, 1.0),
+    (1, 128, 128, 8, 17, (3, 3), False, 0, 0, 1.0, 1.0),
+    (1, 256, 192, 5, 9, (3, 3), True, 1, 0, 3e-6, 2e4),
+    (2, 128, 256, 6, 11, (3, 3), False, 0, 0, 7e3, 1e-7),
+    (3, 512, 512, 17, 65, (3, 3), True, 1, 0, 1.0, 1e-3),
+    (2, 768, 64, 6, 10, (1, 1), True, 0, 1, 1.0, 1.0),
+    (4, 64, 256, 8, 16, (3, 3), True, 0, 0, 40.0, 1.0),
+    (1, 64, 64, 20, 70, (3, 3), False, 0, 0, 1.0, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES)
+def test_conv_f16_split_fwd_dgrad_wgrad(case):
+    """tcgen05 3xF16 convolution (packed fp16 hi|lo operands with device-side power-of-two scales) against F.conv2d
+    in fp32, at operand magnitudes from 1e-7 to 2e4.  Tolerance 1e-5 of the largest output, as for 3xTF32: the
+    split keeps 22 bits per operand and the four-accumulator scheme bounds the truncating accumulation."""
+    L = _lib()
+    n, cin, cout, h, w, (kh, kw), bias, act, extra, xmag, dymag = case
+    g = torch.Generator().manual_seed(cin * 11 + cout)
+    x = torch.randn(n, cin, h, w, generator=g) * xmag
+    x[0, 0, 0, 0] = 0.0
+    x[0, 1 % cin, 0, 1] = xmag * 1e-9          # far below the fp16 normal range of the scaled tensor
+    wt = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = (torch.randn(cout, generator=g) * xmag) if bias else None
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    ref = F.conv2d(x.double(), wt.double(), b.double() if bias else None, 1, (ph, pw))
+    if act:
+        ref = F.relu(ref)
+    tph, tpw = ph + extra, pw + extra
+    x_h2, x_b, x_src = pack_f16(L, x, tph, tpw)
+    assert abs(x_b.item() - x.abs().max().item()) <= 1e-6 * x.abs().max().item()
+    # the packed planes reproduce the fp32 tensor to 2^-22 of each value (or 2^-36 / scale absolutely)
+    s = 2.0 ** (14 - torch.tensor(x_b.item()).frexp().exponent.item())
+    back = (x_h2[..., 0, :].double() + x_h2[..., 1, :].double() / 2048.0) / s
+    assert ((back - x_src.double()).abs() <= x_src.double().abs() * 2.0 ** -21 + 2.0 ** -35 / s).all()
+    wd = wt.to(DEV)
+    w_b = torch.empty(1, device=DEV)
+    w_h2 = torch.empty(cout, 2, kh * kw * cin, dtype=torch.float16, device=DEV)
+    L.weight_pack_f16(wd.data_ptr(), cout, cin, kh, kw, cin, 0, 1, w_b.data_ptr(), w_h2.data_ptr(), _st())
+    y = torch.full((n, h, w, cout), float("nan"), device=DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    xt4, yt4 = L.Tensor4(n, h, w, cin, tph, tpw), L.Tensor4(n, h, w, cout, 0, 0)
+    cv = L.Conv(kh, kw, 1, 1, ph, pw)
+    L.profile_enable(1)
+    L.conv2d_fwd_f16(xt4, x_h2.data_ptr(), x_b.data_ptr(), w_h2.data_ptr(), w_b.data_ptr(),
+                     b.to(DEV).data_ptr() if bias else None, cv, act, yt4, y.data_ptr(), stats.data_ptr(), _st())
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert "conv_fwd_tc" in prof and len(prof) == 1, prof
+    assert relerr(from_nhwc(y).double(), ref) < 1e-5
+    st_ = stats.cpu()
+    assert torch.allclose(st_[:cout], ref.sum((0, 2, 3)), rtol=5e-5, atol=1e-4 * xmag)
+    assert torch.allclose(st_[cout:], (ref ** 2).sum((0, 2, 3)), rtol=5e-5, atol=1e-4 * xmag * xmag)
+
+    # dgrad: convolution of the padded dy with the flipped / transposed weights
+    dy = torch.randn(n, cout, h, w, generator=g) * dymag
+    xr = x.double().requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    F.conv2d(xr, wr, None, 1, (ph, pw)).backward(dy.double())
+    dy_h2, dy_b, _ = pack_f16(L, dy, tph, tpw)
+    wt_h2 = torch.empty(cin, 2, kh * kw * cout, dtype=torch.float16, device=DEV)
+    L.weight_pack_f16(wd.data_ptr(), cout, cin, kh, kw, cin, 1, 0, w_b.data_ptr(), wt_h2.data_ptr(), _st())
+    dx = torch.full((n, h, w, cin), float("nan"), device=DEV)
+    dyt4 = L.Tensor4(n, h, w, cout, tph, tpw)
+    L.conv2d_bwd_data_f16(dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), wt_h2.data_ptr(), w_b.data_ptr(), cv,
+                          L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), _st())
+    assert relerr(from_nhwc(dx).double(), xr.grad) < 1e-5
+
+    # wgrad: x and dy on the same padded grid, both read pixel-major (MN-major fp16 operands, 128-byte swizzle)
+    if cout % 128 == 0:
+        dw_ohwi = torch.full((cout, kh, kw, cin), float("nan"), device=DEV)
+        L.conv2d_bwd_weight_f16(xt4, x_h2.data_ptr(), x_b.data_ptr(), dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), cv,
+                                dw_ohwi.data_ptr(), _st())
+        assert relerr(dw_ohwi.permute(0, 3, 1, 2).cpu().double(), wr.grad) < 1e-5
+    else:
+        with pytest.raises(L.DlioError):
+            L.conv2d_bwd_weight_f16(xt4, x_h2.data_ptr(), x_b.data_ptr(), dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), cv,
+                                    y.data_ptr(), _st())
 
 
 TC_CASES = [
@@ -269,6 +362,84 @@ def test_conv_bn_block_vs_torch(cfg):
     assert relerr(run.pgrad["bn.bias"].cpu(), leaves[4].grad) < tol
     if res_mode:
         assert relerr(from_nhwc(run.agrad[id(ra)]), leaves[5].grad) < tol
+
+
+@pytest.mark.parametrize("variant", ["simple1", "bn_relu", "eval"])
+def test_conv_bn_chain_on_fp16_planes(variant):
+    """Two chained engine.conv_bn blocks where the second convolution (forward, dgrad, wgrad) runs on the packed
+    fp16 planes the first block's BN pass wrote (no fp32 copy in the 'simple1' variant), against the same chain in
+    torch fp64 on the CPU.  Checks the device-side bounds: they must dominate the tensors they scale."""
+    from deeplio_b200 import engine as E
+    n, cin, c1, c2, h, w = 2, 32, 64, 128, 12, 36
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, cin, h, w, generator=g)
+    w1 = torch.randn(c1, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    w2 = torch.randn(c2, c1, 3, 3, generator=g) / (c1 * 9) ** 0.5
+    b1, b2 = torch.randn(c1, generator=g) * 0.1, torch.randn(c2, generator=g) * 0.1
+    g1, be1 = torch.rand(c1, generator=g) * 3 + 0.5, torch.randn(c1, generator=g)
+    g2, be2 = torch.rand(c2, generator=g) + 0.5, torch.randn(c2, generator=g) * 0.1
+    pre_relu = variant == "simple1"
+    training = variant != "eval"
+    rm1, rv1 = torch.randn(c1, generator=g) * 0.1, torch.rand(c1, generator=g) + 0.5
+    rm2, rv2 = torch.randn(c2, generator=g) * 0.1, torch.rand(c2, generator=g) + 0.5
+
+    def block(t, wt, b, gamma, beta, rm, rv, pool, res=None):
+        y = F.conv2d(t, wt, b, 1, 1)
+        if pre_relu:
+            y = F.relu(y)
+        y = F.batch_norm(y, rm.clone().double(), rv.clone().double(), gamma, beta, training, 0.1, 1e-5)
+        if res is not None:
+            y = y + res
+        if not pre_relu:
+            y = F.relu(y)
+        if pool:
+            y = F.max_pool2d(y, 3, pool, 1, ceil_mode=True)
+        return y
+    leaves = [t.double().clone().requires_grad_(True) for t in (x, w1, b1, g1, be1, w2, b2, g2, be2)]
+    mid = block(leaves[0], *leaves[1:5], rm1, rv1, (1, 2))
+    ref = block(mid, *leaves[5:9], rm2, rv2, None)
+    dout = torch.randn(ref.shape, generator=g)
+    if training:
+        ref.backward(dout.double())
+
+    params = {"c1.weight": w1, "c1.bias": b1, "n1.weight": g1, "n1.bias": be1,
+              "c2.weight": w2, "c2.bias": b2, "n2.weight": g2, "n2.bias": be2}
+    params = {k: v.to(DEV) for k, v in params.items()}
+    bufs = {"n1.running_mean": rm1.to(DEV), "n1.running_var": rv1.to(DEV),
+            "n2.running_mean": rm2.to(DEV), "n2.running_var": rv2.to(DEV)}
+    run = E.Run(params, bufs, torch.device(DEV), training, training)
+    xa = E.Act(n, h, w, cin, 1, 1, t=to_padded_nhwc(x, 1, 1))
+    L = _lib()
+    L.profile_enable(1)
+    m = E.conv_bn(run, xa, "c1", "n1", (1, 1), pre_relu=pre_relu, relu=not pre_relu, pool=(1, 2), ceil=True,
+                  out_pad=(1, 1), out_f32=variant != "simple1")
+    assert m.h2 is not None and (m.t is None) == (variant == "simple1")
+    out = E.conv_bn(run, m, "c2", "n2", (1, 1), pre_relu=pre_relu, relu=not pre_relu, out_pad=(0, 0))
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    assert prof["conv_fwd_tc"][1] == 1 and prof["conv_fwd_simt"][1] == 1, prof
+    # the bound dominates the tensor, and the planes reproduce it
+    s = 2.0 ** (14 - torch.tensor(m.bound.item()).frexp().exponent.item())
+    back = (m.h2[..., 0, :].double() + m.h2[..., 1, :].double() / 2048.0).cpu() / s
+    mid_nhwc = F.pad(mid.detach().permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))
+    assert mid.detach().abs().max().item() <= m.bound.item() <= 3000 * mid.detach().abs().max().item()
+    assert relerr(back, mid_nhwc) < 2e-5
+    assert relerr(from_nhwc(out.t).double(), ref.detach()) < 2e-5
+    if not training:
+        L.profile_enable(0)
+        return
+    run.agrad[id(out)] = to_padded_nhwc(dout, 0, 0)
+    run.backward()
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert prof["conv_wgrad_tc"][1] == 1 and prof["conv_dgrad_tc"][1] == 2, prof   # dgrad of block 1 runs on 3xTF32
+    tol = 5e-5
+    assert relerr(from_nhwc(run.agrad[id(xa)]).double(), leaves[0].grad) < tol
+    for name, leaf in zip(("c1.weight", "c1.bias", "n1.weight", "n1.bias", "c2.weight", "c2.bias", "n2.weight", "n2.bias"),
+                          leaves[1:]):
+        scale = leaf.grad.abs().max().item() if "bias" not in name[:2] else 1.0
+        assert (run.pgrad[name].cpu().double() - leaf.grad).abs().max().item() < tol * max(scale, leaves[5].grad.abs().max().item()), name
 
 
 def test_bn_eval_mode_uses_running_stats():
