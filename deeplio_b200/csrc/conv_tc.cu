@@ -29,8 +29,11 @@ namespace dlio {
 constexpr int TC_BM = 128;       // output rows (padded pixels) per CTA
 constexpr int TC_BK = 32;        // fp32 elements per K chunk = one 128-byte swizzle row (64 halves in f16 mode)
 constexpr int TC_BK16 = 64;
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_LIMIT = 200 * 1024;
+constexpr int TC_THREADS = 192;          // wgrad kernel: producer, MMA, 4 epilogue warps
+constexpr int TC_FWD_THREADS = 320;      // forward / dgrad kernel: producer, MMA, 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_SMEM_LIMIT = 221 * 1024;   // pipeline stages + epilogue scratch (227 KB per CTA minus alignment slack)
+constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 2 * 64 * 8;   // per-warp fp64 column sums
 
 struct TcArgs {
     Geo x;             // padded input geometry (pads are memory)
@@ -39,7 +42,9 @@ struct TcArgs {
     int cin, cout, bn;  // bn: output channels per CTA (multiple of 16, <= 256)
     int act;
     int stages;
-    int cluster;       // 1, or 2: CTA pairs along M share the weight tile through TMA multicast
+    int seg;           // K stages per main-accumulator segment
+    long long mtiles;  // 128-row tiles of the padded grid
+    int ntiles;        // cout / bn
     const float *bias;
     float *out;
     double *stats;
@@ -76,24 +81,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask`, and each of those
-// CTAs' mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                               uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
+// One lane of a converged warp (elect.sync): the tcgen05.mma / TMA / commit instructions take their operands from
+// uniform registers, and ptxas only keeps them there -- without wrapping every instruction in a per-lane
+// "elect, move to uniform registers, execute, loop" sequence of ~10 instructions -- when the warp is converged and
+// the issuing lane comes from elect.sync.  (Issuing from `if (lane == 0)` cost ~300 instructions per K stage and
+// made the single issuing thread, not the tensor pipe, the bound of the main loop: 190 clocks per MMA.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// MMA kind and A-collector usage are compile-time; `f16` selects kind::f16 (fp16 operands, K = 16 per
+// MMA kind and A-collector usage are compile-time; F16 selects kind::f16 (fp16 operands, K = 16 per
 // instruction) over kind::tf32 (K = 8) -- both consume 32 bytes of every operand row per instruction.
 #define DLIO_UMMA_ASM(KIND, COLL)                                                                         \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                      \
@@ -101,9 +99,9 @@ __device__ __forceinline__ void cluster_sync_all() {
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)                                             \
                  : "memory")
 // coll: 0 plain, 1 collector::a::fill, 2 collector::a::lastuse
-template <int COLL>
-__device__ __forceinline__ void umma(bool f16, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    if (f16) {
+template <bool F16, int COLL>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (F16) {
         if (COLL == 0) DLIO_UMMA_ASM("f16", "");
         else if (COLL == 1) DLIO_UMMA_ASM("f16", ".collector::a::fill");
         else DLIO_UMMA_ASM("f16", ".collector::a::lastuse");
@@ -147,13 +145,55 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool f16) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// v[j] = value of column j in this lane's row; returns the sum over the warp's 32 rows of column `lane`
+// (16 + 8 + 4 + 2 + 1 shuffles; v is destroyed)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float keep = up ? v[j + n] : v[j];
+            const float send = up ? v[j] : v[j + n];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+
+// Persistent kernel: grid = min(tiles, SMs) CTAs, tile t -> (M tile t / ntiles, N tile t % ntiles), so the CTAs
+// that run at the same time share their X rows in L2.  The four TMEM regions of bn columns are two MAIN
+// accumulators used in ping-pong and two CORRECTION accumulators (one per tile parity):
+//   * the MMA warp sends the hi*hi products of SEG consecutive K stages into one main accumulator, commits it
+//     (mfull) and switches to the other one; the lo*hi + hi*lo products of the whole tile go to corr[tile & 1];
+//   * the epilogue warps drain each committed main accumulator into REGISTERS (round-to-nearest fp32 adds) while
+//     the tensor pipe works on the next segment, so a TMEM accumulator never sees more than 4*SEG truncating MMA
+//     steps whatever K is, and at the end of a tile only the correction accumulator is left to read;
+//   * bias / ReLU / store / BN statistics of tile t overlap the main loop of tile t + 1.
+// Barriers: full/empty per smem stage; mfull/mempty per main accumulator; cfull/cempty per correction accumulator.
+template <bool F16>
+__global__ void __launch_bounds__(TC_FWD_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[2 * 8 + 1];
+    __shared__ uint64_t bars[2 * 8 + 8];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float red[2][256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -161,173 +201,256 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const uint32_t b_bytes = (uint32_t)a.bn * TC_BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const int S = a.stages;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+    const uint32_t mfull0 = smem_u32(&bars[16]), mempty0 = smem_u32(&bars[18]);
+    const uint32_t cfull0 = smem_u32(&bars[20]), cempty0 = smem_u32(&bars[22]);
 
-    const bool f16 = a.f16 != 0;
-    const int bk = f16 ? TC_BK16 : TC_BK;                   // elements per 128-byte K chunk
+    constexpr bool f16 = F16;
+    constexpr int bk = F16 ? TC_BK16 : TC_BK;               // elements per 128-byte K chunk
     const int cchunks = a.cin / bk;
-    const int iters = a.kh * a.kw * cchunks;
-    const long long q0 = (long long)blockIdx.x * TC_BM;
-    const int n0 = blockIdx.y * a.bn;
-    const int tmem_cols = 4 * a.bn <= 64 ? 64 : (4 * a.bn <= 128 ? 128 : (4 * a.bn <= 256 ? 256 : 512));
-    const int nmain = iters < 3 ? iters : 3;
-    uint32_t cta_rank = 0;
-    if (a.cluster == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int iters = a.kh * a.kw * cchunks;                // K stages per tile
+    const int SEG = a.seg;
+    const long long tiles = a.mtiles * a.ntiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, (uint32_t)a.cluster);   // freed when every CTA of the pair has consumed it
+            mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tfull, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(mfull0 + 8 * i, 1);
+            mbar_init(mempty0 + 8 * i, TC_EPI_WARPS);
+            mbar_init(cfull0 + 8 * i, 1);
+            mbar_init(cempty0 + 8 * i, TC_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 512; i += TC_THREADS) red[i >> 8][i & 255] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"((uint32_t)tmem_cols)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (a.cluster == 2) cluster_sync_all();   // peer barriers must exist before multicast traffic / remote arrives
-    else __syncthreads();
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    // TMEM columns: main accumulators at 0 and bn, correction accumulators at 2 bn and 3 bn
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (whole warp converged, one elected lane issues) =====
+        uint32_t s = 0, ph = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const long long q0 = (tile / a.ntiles) * TC_BM;
+            const int n0 = (int)(tile % a.ntiles) * a.bn;
+            int dy = 0, dx = 0, cc = 0, wcol = 0;            // tap (dy, dx), channel chunk, weight column tap*cin + cc*bk
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const int tap = it / cchunks, cc = it - tap * cchunks;
-                const int dy = tap / a.kw, dx = tap - dy * a.kw;
-                const long long row = q0 + (long long)(dy - a.ph) * a.x.wp + (dx - a.pw);
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t fb = full0 + 8 * s;
-                mbar_expect_tx(fb, stage_bytes);
-                tma_load_2d(sa, &tm_xhi, fb, cc * bk, (int)row);
-                tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * bk, (int)row);
-                if (a.cluster == 2) {   // each CTA fetches half of the weight tile for both
-                    const uint32_t half = b_bytes / 2;
-                    const int nh = n0 + (int)cta_rank * (a.bn / 2);
-                    tma_load_2d_mc(sa + 2 * a_bytes + cta_rank * half, &tm_whi, fb, tap * a.cin + cc * bk, nh, 3);
-                    tma_load_2d_mc(sa + 2 * a_bytes + b_bytes + cta_rank * half, &tm_wlo, fb, tap * a.cin + cc * bk, nh, 3);
-                } else {
-                    tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, tap * a.cin + cc * bk, n0);
-                    tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, tap * a.cin + cc * bk, n0);
+                if (elect_one()) {
+                    const int row = (int)(q0 + (long long)(dy - a.ph) * a.x.wp + (dx - a.pw));
+                    const uint32_t sa = smem_u32(smem) + s * stage_bytes;
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, stage_bytes);
+                    tma_load_2d(sa, &tm_xhi, fb, cc * bk, row);
+                    tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
+                    tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, wcol, n0);
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, wcol, n0);
                 }
+                __syncwarp();
+                wcol += bk;
+                if (++cc == cchunks) {
+                    cc = 0;
+                    if (++dx == a.kw) { dx = 0; ++dy; }
+                }
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(a.bn, f16);
+        // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+        const uint32_t idesc = make_idesc(a.bn, f16);
+        const uint32_t sa0 = smem_u32(smem);
+        const uint64_t dA_hi = make_kmajor_desc(sa0), dA_lo = make_kmajor_desc(sa0 + a_bytes);
+        const uint64_t dB_hi = make_kmajor_desc(sa0 + 2 * a_bytes), dB_lo = make_kmajor_desc(sa0 + 2 * a_bytes + b_bytes);
+        const uint32_t stage16 = stage_bytes >> 4;               // descriptor start addresses count 16-byte units
+        uint32_t s = 0, ph = 0, seg = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t p = tcount & 1u;
+            mbar_wait(cempty0 + 8 * p, ((tcount >> 1) & 1u) ^ 1u);     // epilogue has read corr[p] of tile - 2
+            const uint32_t t_corr = tmem_base + (2 + p) * a.bn;
+            uint32_t t_main = 0;
+            int si = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                if (si == 0) {
+                    mbar_wait(mempty0 + 8 * (seg & 1u), ((seg >> 1) & 1u) ^ 1u);  // epilogue has drained main[seg & 1]
+                    t_main = tmem_base + (seg & 1u) * a.bn;
+                }
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t d_ahi = make_kmajor_desc(sa), d_alo = make_kmajor_desc(sa + a_bytes);
-                const uint64_t d_bhi = make_kmajor_desc(sa + 2 * a_bytes), d_blo = make_kmajor_desc(sa + 2 * a_bytes + b_bytes);
+                const bool seg_end = si == SEG - 1 || it == iters - 1;
+                if (elect_one()) {
+                    const uint64_t so = (uint64_t)(s * stage16);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {                // 128-byte rows / 32 bytes per MMA K step
-                    const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
-                    umma<0>(f16, tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma<1>(f16, tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma<2>(f16, tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {                // 128-byte rows / 32 bytes per MMA K step
+                        const uint64_t ko = so + (uint64_t)(k * 2);
+                        umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                        umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                        umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
+                    if (seg_end) umma_commit(mfull0 + 8 * (seg & 1u));   // this segment's main accumulator is complete
+                    if (it == iters - 1) umma_commit(cfull0 + 8 * p);    // and so is the tile's correction accumulator
                 }
-                // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-                if (a.cluster == 2) umma_commit_mc(empty0 + 8 * s, 3);
-                else umma_commit(empty0 + 8 * s);
+                __syncwarp();
+                if (seg_end) { ++seg; si = 0; } else ++si;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tfull);                // accumulator complete
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;               // row of the tile == TMEM lane
-        const long long q = q0 + r;
-        bool valid = q < a.rows;
-        size_t obase = 0;
-        if (valid) {
-            int xx = (int)(q % a.x.wp);
-            long long t = q / a.x.wp;
-            int yy = (int)(t % a.x.hp);
-            int n = (int)(t / a.x.hp);
-            int h = yy - a.x.ph, w = xx - a.x.pw;
-            valid = h >= 0 && h < a.x.h && w >= 0 && w < a.x.w;
-            if (valid) obase = a.o.off(n, h, w);
-        }
-        float *tr = reinterpret_cast<float *>(smem) + (size_t)(warp - 2) * 32 * 33;   // pipeline smem is free now
+        // ===== epilogue: 8 warps; warp w reads TMEM lane quadrant w % 4 (a hardware rule) and one half of the
+        // tile's columns, so every scheduler has two epilogue warps to hide TMEM / shared-memory latency with
+        const int quad = warp & 3, ew = warp - 2, half = ew >> 2;
+        const int cw = a.bn >= 64 ? a.bn / 2 : a.bn;          // columns per warp
+        const bool active = half == 0 || a.bn >= 64;
+        const int cb = half * cw;                              // first column of this warp inside the tile
+        double *red = reinterpret_cast<double *>(smem + (size_t)S * stage_bytes) + (size_t)ew * 2 * 64;   // [2][64]
+        for (int i = lane; i < 2 * 64; i += 32) red[i] = 0.0;
         // f16: undo the two power-of-two operand scales; the correction accumulator carries another 2^-11
-        float inv_x = 1.f, inv_w = 1.f, corr = 1.f;
+        float inv = 1.f, corr = 1.f;
         if (f16) {
-            inv_x = 1.f / f16_scale_from_bound(*a.xb);
-            inv_w = 1.f / f16_scale_from_bound(*a.wb);
+            inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.wb));
             corr = 1.f / 2048.f;
         }
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int c0 = 0; c0 < a.bn; c0 += 32) {
-            uint32_t v[32], u[32];
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-            tmem_ld32(trow, v);
-            for (int m = 1; m < nmain; ++m) {
-                tmem_ld32(trow + m * a.bn, u);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        const int nseg = (iters + SEG - 1) / SEG;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        uint32_t seg = 0, tcount = 0;
+        int red_n0 = -1;
+        auto flush_stats = [&](int n0) {
+            __syncwarp();
+            for (int c = lane; c < cw; c += 32) {
+                atomicAdd(a.stats + n0 + cb + c, red[c]);
+                atomicAdd(a.stats + a.cout + n0 + cb + c, red[64 + c]);
+                red[c] = 0.0;
+                red[64 + c] = 0.0;
             }
-            tmem_ld32(trow + 3 * a.bn, u);
-            const int ncol = min(32, a.bn - c0);
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv_x * inv_w;
-                if (a.bias && j < ncol) x += a.bias[n0 + c0 + j];
-                if (a.act == DLIO_ACT_RELU) x = fmaxf(x, 0.f);
-                f[j] = valid ? x : 0.f;
-            }
+            __syncwarp();
+        };
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+            const long long q = (tile / a.ntiles) * TC_BM + quad * 32 + lane;   // row of the tile == TMEM lane
+            const int n0 = (int)(tile % a.ntiles) * a.bn;
+            bool valid = q < a.rows;
+            size_t obase = 0;
             if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    if (j < ncol) st4(a.out + obase + n0 + c0 + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+                int xx = (int)(q % a.x.wp);
+                long long t = q / a.x.wp;
+                int yy = (int)(t % a.x.hp);
+                int n = (int)(t / a.x.hp);
+                int h = yy - a.x.ph, w = xx - a.x.pw;
+                valid = h >= 0 && h < a.x.h && w >= 0 && w < a.x.w;
+                if (valid) obase = a.o.off(n, h, w) + n0 + cb;
             }
-            if (a.stats) {
-                // column sums over the warp's 32 rows through a padded shared-memory transpose
+            if (a.stats && active && red_n0 != n0) {
+                if (red_n0 >= 0) flush_stats(red_n0);
+                red_n0 = n0;
+            }
+            // --- drain the main-accumulator segments into registers as the MMA warp completes them
+            float acc[2][32];
+            for (int sg = 0; sg < nseg; ++sg, ++seg) {
+                const uint32_t b = seg & 1u;
+                mbar_wait(mfull0 + 8 * b, (seg >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (active) {
+                    const uint32_t t_main = tmem_base + lane_off + b * a.bn + cb;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = f[j];
-                __syncwarp();
-                float s1 = 0.f, s2 = 0.f;
+                    for (int c = 0; c < 2; ++c) {
+                        if (c * 32 < cw) {
+                            uint32_t v[32];
+                            tmem_ld32_nowait(t_main + c * 32, v);
+                            tmem_ld_wait();
+                            if (sg == 0) {
 #pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                    float x = tr[rr * 33 + lane];
-                    s1 += x;
-                    s2 = fmaf(x, x, s2);
+                                for (int j = 0; j < 32; ++j) acc[c][j] = __uint_as_float(v[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) acc[c][j] += __uint_as_float(v[j]);
+                            }
+                        }
+                    }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane < ncol) {
-                    atomicAdd(&red[0][c0 + lane], s1);
-                    atomicAdd(&red[1][c0 + lane], s2);
+                if (lane == 0) mbar_arrive(mempty0 + 8 * b);
+            }
+            // --- correction accumulator, then the tile's epilogue proper (overlaps the next tile's main loop)
+            const uint32_t p = tcount & 1u;
+            mbar_wait(cfull0 + 8 * p, (tcount >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float rinv = valid ? inv : 0.f;      // rows on pads contribute exact zeros to the statistics
+            if (active) {
+                const uint32_t t_corr = tmem_base + lane_off + (2 + p) * a.bn + cb;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c * 32 < cw) {
+                        uint32_t u[32];
+                        tmem_ld32_nowait(t_corr + c * 32, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c][j] = fmaf(__uint_as_float(u[j]), corr, acc[c][j]) * rinv;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cempty0 + 8 * p);
+            if (!active) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int c0 = c * 32;
+                if (c0 < cw) {
+                    const int ncol = min(32, cw - c0);
+                    if (a.bias) {
+                        const float bmask = valid ? 1.f : 0.f;
+                        const float *bp = a.bias + n0 + cb + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j < ncol) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + j));
+                                acc[c][j] = fmaf(b4.x, bmask, acc[c][j]);
+                                acc[c][j + 1] = fmaf(b4.y, bmask, acc[c][j + 1]);
+                                acc[c][j + 2] = fmaf(b4.z, bmask, acc[c][j + 2]);
+                                acc[c][j + 3] = fmaf(b4.w, bmask, acc[c][j + 3]);
+                            }
+                        }
+                    }
+                    if (a.act == DLIO_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c][j] = fmaxf(acc[c][j], 0.f);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < ncol)
+                                st4(a.out + obase + c0 + j, make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]));
+                    }
+                    if (a.stats) {
+                        // per-column sums over the warp's 32 rows: butterfly transpose-reduce, lane l ends with column l
+                        float sq[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sq[j] = acc[c][j] * acc[c][j];
+                        const float s1 = warp_colsum32(acc[c], lane), s2 = warp_colsum32(sq, lane);
+                        if (lane < ncol) {          // this lane owns column c0 + lane of the warp's private sums
+                            red[c0 + lane] += (double)s1;
+                            red[64 + c0 + lane] += (double)s2;
+                        }
+                    }
                 }
             }
         }
-        if (a.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-            for (int c = threadIdx.x - 64; c < a.bn; c += 128) {
-                atomicAdd(a.stats + n0 + c, (double)red[0][c]);
-                atomicAdd(a.stats + a.cout + n0 + c, (double)red[1][c]);
-            }
-        }
+        if (a.stats && active && red_n0 >= 0) flush_stats(red_n0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (a.cluster == 2) cluster_sync_all();   // no CTA may exit while its peer can still signal its barriers
-    else __syncthreads();
+    __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -415,46 +538,41 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.act = a.act;
     t.bias = a.bias; t.out = a.out; t.stats = a.stats; t.rows = rows;
     const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
-    int stages = TC_SMEM_LIMIT / stage_bytes;
+    int stages = (TC_SMEM_LIMIT - TC_EPI_SMEM) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages < 2) return 0;
     t.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    t.seg = 8;   // 32 truncating MMA steps per TMEM accumulator, whatever K is
+    const size_t smem = (size_t)stages * stage_bytes + TC_EPI_SMEM + 1024;
 
     CUtensorMap mxh, mxl, mwh, mwl;
     const long long K = (long long)a.kh * a.kw * a.cin;
     int rc;
     if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, TC_BM))) return rc;
-    const long long mtiles = (rows + TC_BM - 1) / TC_BM;
-    // CTA pairs that share the weight tile through TMA multicast are implemented and tested (set to 2), but
-    // measured 6 % SLOWER (fwd 8.32 -> 8.81 ms / step): ncu sampling shows the producer waiting on `empty`, i.e.
-    // the loop is bound by the tensor pipe reading its SS operands from shared memory (8 KB per 64-cycle MMA =
-    // the full 128 B/clk), not by L2 -> SM traffic, and pairing adds lock-step between the two CTAs.
-    constexpr bool kPairMulticast = false;
-    t.cluster = (kPairMulticast && mtiles >= 2 && bn % 16 == 0) ? 2 : 1;
-    if ((rc = make_map_pair(&mwh, &mwl, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn / t.cluster))) return rc;
+    if ((rc = make_map_pair(&mwh, &mwl, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn))) return rc;
+    t.mtiles = (rows + TC_BM - 1) / TC_BM;
+    t.ntiles = a.cout / bn;
+    // (CTA pairs sharing the weight tile through TMA multicast were tried in round 1 and measured 6 % slower:
+    // the main loop is bound by shared-memory bandwidth -- TMA fills plus the SS operand reads of the MMAs --
+    // not by L2 -> SM traffic.)
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        DLIO_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
-        attr_set = true;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        DLIO_CUDA(cudaGetDevice(&dev));
+        DLIO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        DLIO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+        DLIO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
     }
     ProfScope prof(prof_kind, st);
     if (a.o.ph > 0 || a.o.pw > 0) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
-    dim3 grid((unsigned)((mtiles + t.cluster - 1) / t.cluster * t.cluster), (unsigned)(a.cout / bn));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = t.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DLIO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mxh, mxl, mwh, mwl, t));
+    const long long tiles = t.mtiles * t.ntiles;
+    // one persistent CTA per SM; keep the grid a multiple of ntiles so that a CTA stays on one N tile (its BN
+    // statistics then accumulate in shared memory over all its tiles)
+    long long grid = tiles < n_sm ? tiles : n_sm;
+    if (grid > t.ntiles) grid -= grid % t.ntiles;
+    if (f16) conv_tc_kernel<true><<<(unsigned)grid, TC_FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, t);
+    else conv_tc_kernel<false><<<(unsigned)grid, TC_FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, t);
     DLIO_LAUNCH_CHECK();
     return 1;
 }
@@ -490,6 +608,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, bool f
     return d;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_constant__ CUtensorMap tm_dylo,
                 const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, TcWgradArgs a) {
@@ -513,10 +632,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     const long long k_begin = (long long)blockIdx.x * a.rows_per_split;
     long long k_end = k_begin + a.rows_per_split;
     if (k_end > a.rows) k_end = a.rows;
-    const bool f16 = a.f16 != 0;
-    const int krows = f16 ? 64 : 32;                        // pixel rows (K) per stage
-    const int bc = f16 ? 64 : 32;                           // channels per TMA box (128 bytes)
-    const uint32_t box_bytes = (uint32_t)krows * 128;
+    constexpr bool f16 = F16;
+    constexpr int krows = F16 ? 64 : 32;                    // pixel rows (K) per stage
+    constexpr int bc = F16 ? 64 : 32;                       // channels per TMA box (128 bytes)
+    constexpr uint32_t box_bytes = (uint32_t)krows * 128;
     const int iters = k_end > k_begin ? (int)((k_end - k_begin + krows - 1) / krows) : 0;
     const int tmem_cols = 4 * a.bn <= 64 ? 64 : (4 * a.bn <= 128 ? 128 : (4 * a.bn <= 256 ? 256 : 512));
     const int nmain = iters < 3 ? iters : 3;
@@ -542,49 +661,60 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const int na_boxes = TC_BM / bc, nb_boxes = a.bn / bc;
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const long long q = k_begin + (long long)it * krows;
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        // TMA producer: whole warp converged, one elected lane issues (see elect_one)
+        constexpr int na_boxes = TC_BM / bc;
+        const int nb_boxes = a.bn / bc;
+        uint32_t s = 0, ph = 0;
+        int q = (int)k_begin;
+        const int qs = (int)shift;
+        for (int it = 0; it < iters; ++it, q += krows) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem) + s * stage_bytes;
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, stage_bytes);
+#pragma unroll
                 for (int j = 0; j < na_boxes; ++j) {
-                    tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, (int)q);
-                    tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, (int)q);
+                    tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, q);
+                    tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, q);
                 }
                 for (int j = 0; j < nb_boxes; ++j) {
-                    tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, ci0 + bc * j, (int)(q + shift));
-                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, ci0 + bc * j, (int)(q + shift));
+                    tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, ci0 + bc * j, q + qs);
+                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, ci0 + bc * j, q + qs);
                 }
             }
+            __syncwarp();
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // both operands MN-major: bits 15 and 16 of the instruction descriptor
-            const uint32_t idesc = make_idesc(a.bn, f16) | (1u << 15) | (1u << 16);
-            const uint64_t kstep = (uint64_t)((f16 ? 2048 : 1024) >> 4);   // one MMA K step = two row groups
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t d_ahi = make_mnmajor_desc(sa, f16), d_alo = make_mnmajor_desc(sa + a_bytes, f16);
-                const uint64_t d_bhi = make_mnmajor_desc(sa + 2 * a_bytes, f16), d_blo = make_mnmajor_desc(sa + 2 * a_bytes + b_bytes, f16);
+        // MMA issuer; both operands MN-major: bits 15 and 16 of the instruction descriptor
+        const uint32_t idesc = make_idesc(a.bn, f16) | (1u << 15) | (1u << 16);
+        constexpr uint64_t kstep = (uint64_t)((F16 ? 2048 : 1024) >> 4);   // one MMA K step = two row groups
+        const uint32_t sa0 = smem_u32(smem);
+        const uint64_t dA_hi = make_mnmajor_desc(sa0, f16), dA_lo = make_mnmajor_desc(sa0 + a_bytes, f16);
+        const uint64_t dB_hi = make_mnmajor_desc(sa0 + 2 * a_bytes, f16), dB_lo = make_mnmajor_desc(sa0 + 2 * a_bytes + b_bytes, f16);
+        const uint32_t stage16 = stage_bytes >> 4;
+        const uint32_t t_corr = tmem_base + 3 * a.bn;
+        uint32_t s = 0, ph = 0, m = 0;                          // m: main accumulator of this stage (round-robin)
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint64_t so = (uint64_t)(s * stage16);
+                const uint32_t t_main = tmem_base + m * a.bn;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t ko = (uint64_t)k * kstep;
-                    umma<0>(f16, tmem_base + 3 * a.bn, d_alo + ko, d_bhi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma<1>(f16, tmem_base + 3 * a.bn, d_ahi + ko, d_blo + ko, idesc, 1u);
-                    umma<2>(f16, tmem_base + (it % 3) * a.bn, d_ahi + ko, d_bhi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                    const uint64_t ko = so + (uint64_t)k * kstep;
+                    umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                    umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                    umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
+                if (it == iters - 1) umma_commit(tfull);
             }
-            umma_commit(tfull);
+            __syncwarp();
+            if (++m == 3) m = 0;
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
     } else {
         const int quad = warp & 3;
@@ -685,13 +815,15 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, krows, sw))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+        DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+        DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
         attr_set = true;
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
     dim3 grid((unsigned)splits, (unsigned)(taps * (a.cin / bn)), (unsigned)(a.cout / TC_BM));
-    wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
+    if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
+    else wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     DLIO_LAUNCH_CHECK();
     return 1;
 }
