@@ -77,26 +77,33 @@ __global__ void act_bwd_kernel(const float *__restrict__ y, int ldy, const float
     dz[i] = dy[(size_t)m * lddy + n] * act_grad_from_out(y[(size_t)m * ldy + n], act);
 }
 
-// out[n] = sum_m dz[m, n]
+// out[n] = sum_m dz[m, n]   (8 independent loads in flight per thread: the loop is latency-bound otherwise)
 __global__ void colsum_kernel(const float *__restrict__ dz, int lddz, int M, int N, float *__restrict__ out) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    float s = 0.f;
-    for (int m = 0; m < M; ++m) s += dz[(size_t)m * lddz + n];
-    out[n] = s;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int m = 0;
+    for (; m + 8 <= M; m += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += dz[(size_t)(m + u) * lddz + n];
+    }
+    for (; m < M; ++m) s[0] += dz[(size_t)m * lddz + n];
+    out[n] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
-constexpr int DX_NC = 128;  // n rows per CTA
+constexpr int DX_NC = 128;  // n rows per CTA (at most; `nc` rows when the problem is too small to fill the GPU)
 
+// The n loop keeps 8 independent weight loads in flight per thread: with one load per iteration a 4-CTA launch
+// (the IMU LSTM's recurrent dgrad, 120 launches per step) took 38 us of pure load latency.
 __global__ void __launch_bounds__(128) linear_dx_kernel(const float *__restrict__ dz, int lddz,
-                                                        const float *__restrict__ w, int M, int N, int K,
+                                                        const float *__restrict__ w, int M, int N, int K, int nc,
                                                         float *__restrict__ dx, int lddx) {
     __shared__ float zs[LIN_MB][DX_NC];
     const int k = blockIdx.x * 128 + threadIdx.x;
-    const int nb = blockIdx.y * DX_NC;
+    const int nb = blockIdx.y * nc;
     const int m0 = blockIdx.z * LIN_MB;
-    for (int i = threadIdx.x; i < LIN_MB * DX_NC; i += 128) {
-        int m = i / DX_NC, n = i - m * DX_NC;
+    for (int i = threadIdx.x; i < LIN_MB * nc; i += 128) {
+        int m = i / nc, n = i - m * nc;
         zs[m][n] = (m0 + m < M && nb + n < N) ? dz[(size_t)(m0 + m) * lddz + nb + n] : 0.f;
     }
     __syncthreads();
@@ -104,9 +111,20 @@ __global__ void __launch_bounds__(128) linear_dx_kernel(const float *__restrict_
 #pragma unroll
     for (int m = 0; m < LIN_MB; ++m) acc[m] = 0.f;
     if (k < K) {
-        const int nend = min(DX_NC, N - nb);
-        for (int n = 0; n < nend; ++n) {
-            float wv = w[(size_t)(nb + n) * K + k];
+        const int nend = min(nc, N - nb);
+        const float *wp = w + (size_t)nb * K + k;
+        int n = 0;
+        for (; n + 8 <= nend; n += 8) {
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = wp[(size_t)(n + u) * K];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int m = 0; m < LIN_MB; ++m) acc[m] = fmaf(zs[m][n + u], wv[u], acc[m]);
+        }
+        for (; n < nend; ++n) {
+            float wv = wp[(size_t)n * K];
 #pragma unroll
             for (int m = 0; m < LIN_MB; ++m) acc[m] = fmaf(zs[m][n], wv, acc[m]);
         }
@@ -136,8 +154,19 @@ __global__ void __launch_bounds__(128) linear_dw_kernel(const float *__restrict_
         __syncthreads();
         if (k < K) {
             const int mend = min(64, M - mb);
-            for (int m = 0; m < mend; ++m) {
-                float xv = x[(size_t)(mb + m) * ldx + k];
+            const float *xp = x + (size_t)mb * ldx + k;
+            int m = 0;
+            for (; m + 8 <= mend; m += 8) {       // 8 independent loads in flight (latency-bound otherwise)
+                float xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xv[u] = xp[(size_t)(m + u) * ldx];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int r = 0; r < DW_NR; ++r) acc[r] = fmaf(zs[m + u][r], xv[u], acc[r]);
+            }
+            for (; m < mend; ++m) {
+                float xv = xp[(size_t)m * ldx];
 #pragma unroll
                 for (int r = 0; r < DW_NR; ++r) acc[r] = fmaf(zs[m][r], xv, acc[r]);
             }
@@ -159,8 +188,11 @@ int linear_fwd_launch(const float *x, int ldx, const float *w, const float *b, c
 }
 int linear_dx_launch(const float *dz, int lddz, const float *w, int M, int N, int K, float *dx, int lddx,
                      cudaStream_t st) {
-    dim3 grid(ceil_div(K, 128), ceil_div(N, DX_NC), ceil_div(M, LIN_MB));
-    linear_dx_kernel<<<grid, 128, 0, st>>>(dz, lddz, w, M, N, K, dx, lddx);
+    // fewer n rows per CTA when 128-row slabs would leave most SMs idle
+    int nc = DX_NC;
+    while (nc > 16 && (long long)ceil_div(K, 128) * ceil_div(N, nc) * ceil_div(M, LIN_MB) < 148) nc >>= 1;
+    dim3 grid(ceil_div(K, 128), ceil_div(N, nc), ceil_div(M, LIN_MB));
+    linear_dx_kernel<<<grid, 128, 0, st>>>(dz, lddz, w, M, N, K, nc, dx, lddx);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
