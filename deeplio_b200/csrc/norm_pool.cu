@@ -24,6 +24,21 @@ static inline int block_for_cg(int cg) {
     if (unit <= 256) return unit * (256 / unit);
     return cg * (256 / cg > 0 ? 256 / cg : 1);
 }
+// persistent grid of a row-structured kernel: exactly the number of blocks that are resident at once
+template <typename K>
+static int resident_grid(K kernel, int block) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return 148 * per_sm;
+}
+// column segments per row such that a persistent grid gets >= 8 work items per block (load balance), while a
+// segment keeps at least two pixels per w-lane
+static inline int row_segments(int rows, int width, int wlanes, int grid) {
+    int segs = (8 * grid + rows - 1) / rows;
+    const int max_segs = width / (2 * wlanes) > 0 ? width / (2 * wlanes) : 1;
+    if (segs > max_segs) segs = max_segs;
+    return segs < 1 ? 1 : segs;
+}
 static inline int grid_for(long long total, int block, int per_sm = 8) {
     long long g = (total + block - 1) / block;
     long long cap = 148LL * per_sm;
@@ -135,6 +150,7 @@ struct BnPool {
     const float *yp, *scale, *shift, *resp;
     int res_mode;  // 0 none, 1 added before the activation, 2 added after it
     int relu, pk, sh, sw, c_off, cg;
+    int segs;                   // row-structured kernels: column segments per row
     float *out_hi, *out_lo;     // fp32 plane (may be NULL when only the fp16 planes are wanted), TF32 lo plane
     __half *out_h2;             // packed fp16 hi|lo planes (optional) and the bound that defines their scale
     const float *out_bound;
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
 // tracking -- the generic kernel spent 70 % of its 600 instructions per output on 64-bit index arithmetic (two
 // divisions per pixel, nine bounds checks and address computations) and ran at 21 % of the HBM bandwidth.
 template <int SH, int SW, bool RELU>
-__global__ void __launch_bounds__(256) bn_pool3_fwd_kernel(BnPool a) {
+__global__ void __launch_bounds__(256, 5) bn_pool3_fwd_kernel(BnPool a) {
     const int cg = a.cg, C = cg * 4;
     const int c = (int)(threadIdx.x % cg) * 4;
     const int wl = (int)(threadIdx.x / cg), WL = (int)(blockDim.x / cg);
@@ -219,12 +235,17 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_kernel(BnPool a) {
         sc = ld4(a.scale + c);
         sf = ld4(a.shift + c);
     }
-    const int rows = a.out.n * a.out.hp;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    // work items: (output row, column segment); a persistent grid strides over them so that every SM stays busy
+    // whatever the number of rows
+    const int rows = a.out.n * a.out.hp, segs = a.segs, items = rows * segs;
+    const int seg_w = (a.out.wp + segs - 1) / segs;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int row = item / segs, seg = item - row * segs;
+        const int x_begin = seg * seg_w, x_end = min(a.out.wp, x_begin + seg_w);
         const int n = row / a.out.hp, ho = row - n * a.out.hp - a.out.ph;
         const unsigned pix0 = (unsigned)row * (unsigned)a.out.wp;          // padded output pixel index of column 0
         if (ho < 0 || ho >= a.out.h) {
-            for (int x = wl; x < a.out.wp; x += WL) bnpool_store(a, pix0 + x, c, f4(0.f), 1.f);
+            for (int x = x_begin + wl; x < x_end; x += WL) bnpool_store(a, pix0 + x, c, f4(0.f), 1.f);
             continue;
         }
         // the three input rows of this output row (block-uniform validity)
@@ -236,8 +257,9 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_kernel(BnPool a) {
             rv[dy] = h >= 0 && h < a.y.h;
             rp[dy] = a.yp + a.y.off(n, rv[dy] ? h : 0, 0) + c;
         }
+        const bool rows_ok = rv[0] && rv[1] && rv[2];
         uint8_t *irow = a.idx ? a.idx + ((size_t)(n * a.out.h + ho) * a.out.w) * C + c : nullptr;
-        for (int x = wl; x < a.out.wp; x += WL) {
+        for (int x = x_begin + wl; x < x_end; x += WL) {
             const int wo = x - a.out.pw;
             if (wo < 0 || wo >= a.out.w) {
                 bnpool_store(a, pix0 + x, c, f4(0.f), 1.f);
@@ -246,22 +268,41 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_kernel(BnPool a) {
             const int w0 = wo * SW - 1;
             float4 best = f4(-FLT_MAX);
             unsigned bi = 0;                                   // four packed window-relative arg-max bytes
+#define DLIO_POOL_TAKE(v, r)                                                          \
+    do {                                                                              \
+        if (v.x > best.x) { best.x = v.x; bi = (bi & 0xFFFFFF00u) | (r); }            \
+        if (v.y > best.y) { best.y = v.y; bi = (bi & 0xFFFF00FFu) | ((r) << 8); }     \
+        if (v.z > best.z) { best.z = v.z; bi = (bi & 0xFF00FFFFu) | ((r) << 16); }    \
+        if (v.w > best.w) { best.w = v.w; bi = (bi & 0x00FFFFFFu) | ((r) << 24); }    \
+    } while (0)
+            if (rows_ok && w0 >= 0 && w0 + 2 < a.y.w) {
+                // interior window: nine independent loads issued back to back (the kernel is bound by load latency)
+                float4 v[9];
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                if (!rv[dy]) continue;
+                for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int w = w0 + dx;
-                    if (w < 0 || w >= a.y.w) continue;
-                    float4 v = fma4(sc, ld4(rp[dy] + w * C), sf);
-                    if (RELU) v = relu4(v);
-                    const unsigned r = (unsigned)(dy * 3 + dx);
-                    if (v.x > best.x) { best.x = v.x; bi = (bi & 0xFFFFFF00u) | r; }
-                    if (v.y > best.y) { best.y = v.y; bi = (bi & 0xFFFF00FFu) | (r << 8); }
-                    if (v.z > best.z) { best.z = v.z; bi = (bi & 0xFF00FFFFu) | (r << 16); }
-                    if (v.w > best.w) { best.w = v.w; bi = (bi & 0x00FFFFFFu) | (r << 24); }
+                    for (int dx = 0; dx < 3; ++dx) v[dy * 3 + dx] = ld4(rp[dy] + (w0 + dx) * C);
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    float4 t = fma4(sc, v[r], sf);
+                    if (RELU) t = relu4(t);
+                    DLIO_POOL_TAKE(t, (unsigned)r);
+                }
+            } else {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (!rv[dy]) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int w = w0 + dx;
+                        if (w < 0 || w >= a.y.w) continue;
+                        float4 t = fma4(sc, ld4(rp[dy] + w * C), sf);
+                        if (RELU) t = relu4(t);
+                        DLIO_POOL_TAKE(t, (unsigned)(dy * 3 + dx));
+                    }
                 }
             }
+#undef DLIO_POOL_TAKE
             if (irow) *reinterpret_cast<unsigned *>(irow + (size_t)wo * C) = bi;
             bnpool_store(a, pix0 + x, c, best, s16);
         }
@@ -281,6 +322,7 @@ struct BnBwd {
     int dres_c, dres_acc;
     double *sums;
     int want_absmax;   // sums[2C] receives max |dz| (bit pattern of a non-negative double, atomicMax)
+    int segs;          // row-structured kernel: column segments per row
 };
 
 // Gradient of a 3x3 max-pool (pad 1, stride SH x SW) gathered at input position (h, w): the sum of dout over
@@ -395,7 +437,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
 // walks whole input rows, so the candidate pooling-window rows, their arg-max / gradient row pointers and the
 // window-relative row offsets are computed once per row instead of per element (see bn_pool3_fwd_kernel).
 template <int SH, int SW>
-__global__ void __launch_bounds__(256) bn_pool3_bwd_reduce_kernel(BnBwd a) {
+__global__ void __launch_bounds__(256, 4) bn_pool3_bwd_reduce_kernel(BnBwd a) {
     __shared__ float red[2 * MAX_C];
     constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;
     const int cg = a.cg, C = cg * 4;
@@ -414,9 +456,12 @@ __global__ void __launch_bounds__(256) bn_pool3_bwd_reduce_kernel(BnBwd a) {
     }
     float4 s1 = f4(0.f), s2 = f4(0.f);
     float amax = 0.f;
-    const int rows = a.y.n * a.y.h;
+    const int rows = a.y.n * a.y.h, segs = a.segs, items = rows * segs;
+    const int seg_w = (a.y.w + segs - 1) / segs;
     const int dstride = a.dout.c;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int row = item / segs, seg = item - row * segs;
+        const int w_begin = seg * seg_w, w_end = min(a.y.w, w_begin + seg_w);
         const int n = row / a.y.h, h = row - n * a.y.h;
         const int ho0 = SH == 1 ? h - 1 : h >> 1;
         const uint8_t *ip[NR];
@@ -434,7 +479,7 @@ __global__ void __launch_bounds__(256) bn_pool3_bwd_reduce_kernel(BnBwd a) {
         }
         const float *yrow = a.yp + a.y.off(n, h, 0) + c;
         float *dzrow = a.dz + ((size_t)row * a.y.w) * C + c;
-        for (int w = wl; w < a.y.w; w += WL) {
+        for (int w = w_begin + wl; w < w_end; w += WL) {
             const int wo0 = SW == 1 ? w - 1 : w >> 1;
             float4 g = f4(0.f);
 #pragma unroll
@@ -789,11 +834,12 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     if (a.pk == 3 && a.res_mode == 0 && (a.sh == 1 || a.sh == 2) && (a.sw == 1 || a.sw == 2) &&
         (long long)a.out.n * a.out.hp * a.out.wp < (1LL << 31)) {
         const int rows = a.out.n * a.out.hp;
-        const int grid = rows < 148 * 8 ? rows : 148 * 8;
 #define DLIO_POOL3(SH_, SW_)                                                              \
     do {                                                                                  \
-        if (a.relu) bn_pool3_fwd_kernel<SH_, SW_, true><<<grid, block, 0, st>>>(a);       \
-        else bn_pool3_fwd_kernel<SH_, SW_, false><<<grid, block, 0, st>>>(a);             \
+        auto kern = a.relu ? bn_pool3_fwd_kernel<SH_, SW_, true> : bn_pool3_fwd_kernel<SH_, SW_, false>; \
+        const int grid = resident_grid(kern, block);                                      \
+        a.segs = row_segments(rows, a.out.wp, block / a.cg, grid);                        \
+        kern<<<grid, block, 0, st>>>(a);                                                  \
     } while (0)
         if (a.sh == 1 && a.sw == 2) DLIO_POOL3(1, 2);
         else if (a.sh == 2 && a.sw == 2) DLIO_POOL3(2, 2);
@@ -839,11 +885,16 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
                       (long long)y.n * y.h * y.w < (1LL << 31);
     if (fast) {
         const int rows = y.n * y.h;
-        const int g2 = rows < 148 * 8 ? rows : 148 * 8;
-        if (a.sh == 1 && a.sw == 2) bn_pool3_bwd_reduce_kernel<1, 2><<<g2, block, 0, st>>>(a);
-        else if (a.sh == 2 && a.sw == 2) bn_pool3_bwd_reduce_kernel<2, 2><<<g2, block, 0, st>>>(a);
-        else if (a.sh == 1 && a.sw == 1) bn_pool3_bwd_reduce_kernel<1, 1><<<g2, block, 0, st>>>(a);
-        else if (a.sh == 2 && a.sw == 1) bn_pool3_bwd_reduce_kernel<2, 1><<<g2, block, 0, st>>>(a);
+#define DLIO_RED3(SH_, SW_)                                                               \
+    do {                                                                                  \
+        const int g2 = resident_grid(bn_pool3_bwd_reduce_kernel<SH_, SW_>, block);        \
+        a.segs = row_segments(rows, y.w, block / a.cg, g2);                               \
+        bn_pool3_bwd_reduce_kernel<SH_, SW_><<<g2, block, 0, st>>>(a);                    \
+    } while (0)
+        if (a.sh == 1 && a.sw == 2) DLIO_RED3(1, 2);
+        else if (a.sh == 2 && a.sw == 2) DLIO_RED3(2, 2);
+        else if (a.sh == 1 && a.sw == 1) DLIO_RED3(1, 1);
+        else if (a.sh == 2 && a.sw == 1) DLIO_RED3(2, 1);
         else {
             set_error("bn_act_pool_bwd_reduce: unsupported pool stride %dx%d", a.sh, a.sw);
             return DLIO_ERR_INVALID;
