@@ -31,8 +31,10 @@ LR, WD = 1e-3, 1e-4                   # reference defaults (deeplio/train.py:39,
 # ----------------------------------------------------------------------------- workload description
 def conv_flops_simple1(n_images):
     """Algorithmic conv FLOPs of ONE Simple-1 encoder over n_images 64x2048 images, split by
-    the kernel class that runs each layer: {class: flops}.  conv1 (Cin = 6) runs on the CUDA-core kernels and
-    needs no dgrad (the input has no gradient); conv2..conv7 (stride 1, Cin % 32 == 0) run on tcgen05."""
+    the kernel class that runs each layer: {class: flops}.  Every layer runs on tcgen05: conv2..conv7 (stride 1,
+    Cin % 64 == 0) as 3xF16, conv1 (Cin = 6, 5x7 stride (1,2)) as 3xTF32 through the space-to-depth view
+    (csrc/conv_s2d.cu; its 2.3x extra MACs are NOT counted -- these are algorithmic FLOPs).  conv1 needs no dgrad
+    (the input has no gradient)."""
     from deeplio_b200.engine import pool_out
     spec = [(6, 64, 5, 7, (1, 2), (1, 2)), (64, 128, 3, 5, (1, 1), (1, 2)), (128, 128, 3, 3, (1, 1), None),
             (128, 256, 3, 3, (1, 1), (2, 2)), (256, 256, 3, 3, (1, 1), None), (256, 512, 3, 3, (1, 1), (2, 2)),
@@ -43,9 +45,9 @@ def conv_flops_simple1(n_images):
     for i, (ci, co, kh, kw, (sh, sw), pool) in enumerate(spec):
         ho, wo = (h + 2 * ((kh - 1) // 2) - kh) // sh + 1, (w + 2 * ((kw - 1) // 2) - kw) // sw + 1
         f = 2.0 * co * ho * wo * ci * kh * kw * n_images
-        tc = (sh, sw) == (1, 1) and ci % 32 == 0
+        tc = ((sh, sw) == (1, 1) and ci % 32 == 0) or i == 0
         out["conv_fwd_tc" if tc else "conv_fwd_simt"] += f
-        out["conv_wgrad_tc" if (tc and co % 128 == 0) else "conv_wgrad_simt"] += f
+        out["conv_wgrad_tc" if (tc and (co % 128 == 0 or i == 0)) else "conv_wgrad_simt"] += f
         if i > 0:
             out["conv_dgrad_tc" if ((sh, sw) == (1, 1) and co % 32 == 0 and ci % 16 == 0) else "conv_dgrad_simt"] += f
         h, w = ho, wo
@@ -263,12 +265,20 @@ def run_b200(args):
         dom = max((k for k in classes if k in flops), key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
         tc = dom.endswith("_tc")
-        # the tcgen05 kernels issue 3 TF32 MMAs per algorithmic FLOP pair; TF32 runs at half the bf16 rate, so the
-        # tensor-pipe ceiling for fp32-equivalent FLOPs is bf16_peak / 6 (shown as frac_of_3xtf32_ceiling)
+        # the tcgen05 kernels issue 3 fp16 MMAs per fp32-accurate product (hi*hi, lo*hi, hi*lo), and fp16 runs at the
+        # bf16 rate, so the tensor-pipe ceiling for fp32-equivalent algorithmic FLOPs is bf16_peak / 3
+        # (frac_of_3xf16_ceiling); `frac` is against the measured bf16 peak itself, as the contract asks.
+        # traffic: dram bytes per launch of this class from the committed ncu pass (profiles/r01_traffic.json)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": c["tflops"], "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": c["tflops"] / bf16_peak, "traffic": None, "peak_source": peak_src,
-                    "frac_of_3xtf32_ceiling": (c["tflops"] / (bf16_peak / 6.0)) if tc else None,
-                    "math": "3xTF32 tcgen05 (fp32-equivalent algorithmic FLOPs)" if tc else "fp32 FMA (CUDA cores)",
+                    "frac": c["tflops"] / bf16_peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac_of_3xf16_ceiling": (c["tflops"] / (bf16_peak / 3.0)) if tc else None,
+                    "math": ("3xF16 tcgen05: three kind::f16 MMAs per fp32-accurate product, fp32 accumulation "
+                             "(fp32-equivalent algorithmic FLOPs)") if tc else "fp32 FMA (CUDA cores)",
                     "launch_ms": c["ms_per_step"] / c["launches_per_step"], "classes": classes}
 
     cpu_baseline = None

@@ -22,6 +22,10 @@ USE_TC = True
 # tcgen05 fp16 split path ("3xF16", twice the TF32 rate): stride-1 convolutions, input channels a multiple of 64;
 # operands are packed fp16 hi|lo planes scaled from device-resident bounds (include/deeplio_b200.h)
 USE_F16 = True
+# optim.FlatAdam marks its parameters with ``_dlio_grad_inplace``: their .grad is a zeroed slice of one gradient
+# arena before each backward, so the backward kernels may write parameter gradients straight into it (overwrite
+# == accumulate into zeros) and hand autograd None -- one AccumulateGrad add kernel less per parameter tensor
+# (116 launches per step).  One backward per zero_grad(), as in the reference's train loop.
 # debugging aid (scripts/repeat_parity.py): when a dict, every conv_bn backward stores clones of its tensors here
 DEBUG_TRACE = None
 
@@ -87,8 +91,9 @@ class Run:
         self.tape = []
         self.agrad = {}           # id(Act) -> unpadded NHWC gradient tensor
         self.fgrad = {}           # id(feature buffer) -> gradient tensor [N, ld]
-        self.pgrad = {}           # parameter name -> gradient tensor
+        self.pgrad = {}           # parameter name -> gradient tensor (absent: written in place into param.grad)
         self.keep = []            # keeps Acts alive so that id() stays unique
+        self.param_objs = {}      # name -> nn.Parameter (in-place parameter gradients)
 
     # -- helpers
     def empty(self, *shape, dtype=torch.float32):
@@ -96,6 +101,17 @@ class Run:
 
     def zeros(self, *shape, dtype=torch.float32):
         return torch.zeros(shape, device=self.device, dtype=dtype)
+
+    def param_grad(self, name, like):
+        """Tensor the backward kernels write the gradient of parameter ``name`` into: the parameter's own .grad
+        (FlatAdam parameters; nothing is returned to autograd for it) or a fresh tensor registered in ``pgrad``."""
+        p = self.param_objs.get(name)
+        if (p is not None and getattr(p, "_dlio_grad_inplace", False) and p.grad is not None and p.grad.is_contiguous()
+                and p.grad.shape == like.shape and p.grad.dtype == torch.float32):
+            return p.grad
+        g = torch.empty_like(like)
+        self.pgrad[name] = g
+        return g
 
     def grad_slot(self, act, zeroed=False):
         """Returns (buffer, existed).  A fresh buffer is uninitialised unless ``zeroed``."""
@@ -273,23 +289,19 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
                   split="tf32" in modes, f16="f16" in modes)
         dya.bound = run.empty(1) if dya.h2 is not None else None
-        dgb = run.empty(2, cout)
+        dgamma, dbeta = run.param_grad(bname + ".weight", gamma), run.param_grad(bname + ".bias", beta)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
         L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
                        1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t), ptr(dya.lo), ptr(dya.h2),
-                       ptr(dya.bound), ptr(dgb[0]), ptr(dgb[1]), ptr(dbs), st)
+                       ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
         if DEBUG_TRACE is not None:
             DEBUG_TRACE[(id(run), cname)] = dict(dout=dout.clone(), dz=dz.clone(), sums=sums.clone(),
                                                  dy=(dya.t if dya.t is not None else dya.h2).clone(), y=y.t.clone(),
                                                  bnv=bnv.clone())
         del dz
-        run.pgrad[bname + ".weight"] = dgb[0]
-        run.pgrad[bname + ".bias"] = dgb[1]
         if b is not None:
-            db = run.empty(cout)
-            L.f64_to_f32(ptr(dbs), ptr(db), cout, st)
-            run.pgrad[cname + ".bias"] = db
-        dw = torch.empty_like(w)
+            L.f64_to_f32(ptr(dbs), ptr(run.param_grad(cname + ".bias", b)), cout, st)
+        dw = run.param_grad(cname + ".weight", w)
         if s2d:
             dw4 = run.empty(R * cout, kh, 3, 32)
             L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dya.t),
@@ -304,7 +316,6 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                 L.conv2d_bwd_weight(x.t4, ptr(x.t), ptr(x.lo) if wg == "tf32" else None, dya.t4, ptr(dya.t),
                                     ptr(dya.lo) if wg == "tf32" else None, cv, ptr(dw_ohwi), st)
             L.weight_grad_to_oihw(ptr(dw_ohwi), cout, cin, kh, kw, cin_pad, ptr(dw), st)
-        run.pgrad[cname + ".weight"] = dw
         if dg == "f16":
             wb = w_bound if w_bound is not None else run.empty(1)
             wt_h2 = run.empty(cin_pad, 2, kh * kw * cout, dtype=torch.float16)
@@ -351,14 +362,12 @@ def se_layer(run, x, prefix, out_pad=(0, 0)):
         dout = run.agrad.pop(id(out))
         dgate = run.empty(n, c)
         L.spatial_dot(out.t4_unpadded, ptr(dout), x.t4, ptr(x.t), ptr(dgate), st)
-        dhid, dw2, scr = run.empty(n, cr), torch.empty_like(w2), run.empty(n, c)
+        dhid, dw2, scr = run.empty(n, cr), run.param_grad(prefix + "fc.2.weight", w2), run.empty(n, c)
         L.linear_bwd(ptr(hid), cr, ptr(w2), ptr(gate), c, ptr(dgate), c, n, c, cr, L.ACT_SIGMOID, ptr(dhid), cr,
                      ptr(dw2), None, ptr(scr), st)
-        dm, dw1, scr2 = run.empty(n, c), torch.empty_like(w1), run.empty(n, cr)
+        dm, dw1, scr2 = run.empty(n, c), run.param_grad(prefix + "fc.0.weight", w1), run.empty(n, cr)
         L.linear_bwd(ptr(m), c, ptr(w1), ptr(hid), cr, ptr(dhid), cr, n, cr, c, L.ACT_RELU, ptr(dm), c, ptr(dw1),
                      None, ptr(scr2), st)
-        run.pgrad[prefix + "fc.0.weight"] = dw1
-        run.pgrad[prefix + "fc.2.weight"] = dw2
         run.add_grad(x, lambda buf: L.channel_scale_bwd(ptr(dout), ptr(gate), ptr(dm), n, x.h * x.w, c, ptr(buf), st))
 
     run.tape.append(bwd)

@@ -222,6 +222,7 @@ class _EncoderPair(torch.autograd.Function):
             pd = dict(zip(names[e], groups[e]))
             bufs = dict(enc[e].named_buffers())
             run = E.Run(pd, bufs, dev, net.training, record)
+            run.param_objs = dict(enc[e].named_parameters())
             x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)   # row pads of 4 pixels: space-to-depth first layer
             enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)
             runs.append(run)

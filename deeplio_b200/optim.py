@@ -38,6 +38,11 @@ class FlatAdam:
                 p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
         self.offsets = offsets
         self.step_count = 0
+        # zero_grad() below leaves every .grad a zeroed arena slice, so the encoders' backward kernels may write
+        # their parameter gradients straight into the arena instead of going through AccumulateGrad (engine.py);
+        # this assumes ONE backward per zero_grad(), which is how the reference trains (trainer.py:268-272)
+        for p in self.params:
+            p._dlio_grad_inplace = True
 
     def zero_grad(self):
         """One memset for every gradient; the views stay installed so autograd accumulates in place."""
