@@ -588,7 +588,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
 // MN-major FP16 operands (f16 mode) use the plain 128-byte swizzle (layout type 2 <-> TMA SWIZZLE_128B): an atom
 // is 64 channels x 8 pixel rows (1024 bytes).  A stage holds 64 pixel rows; each TMA box is [64 rows x 64
 // channels] = 8192 bytes (LBO), 8-row groups 1024 bytes apart (SBO); one K = 16 MMA step spans two row groups.
-// grid = (K splits, taps * Cin/BN, Cout/128); partial tiles are combined with fp32 atomic adds into dw.
+// grid = (taps * Cin/BN, K splits, Cout/128); partial tiles are combined with fp32 atomic adds into dw.
 struct TcWgradArgs {
     int kh, kw, ph, pw, wp;
     int cin, cout, bn, stages;
@@ -624,12 +624,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     const int S = a.stages;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
 
+    // blockIdx.x = (tap, ci block) is the fastest-varying index, blockIdx.y the K split: the CTAs that are resident
+    // together work on the SAME pixel range for different taps, so dy (identical for every tap) and x (shifted by a
+    // few rows) are served by L2 -- with the split index fastest, every tap streamed both tensors from DRAM again
+    // (ncu: 1.7 GB read for 0.42 GB of operands in Simple-1 conv2, 50 % DRAM utilisation)
     const int nblk = a.cin / a.bn;
-    const int tap = blockIdx.y / nblk, ci0 = (blockIdx.y - tap * nblk) * a.bn;
+    const int tap = blockIdx.x / nblk, ci0 = (blockIdx.x - tap * nblk) * a.bn;
     const int co0 = blockIdx.z * TC_BM;
     const int dy_ = tap / a.kw, dx_ = tap - dy_ * a.kw;
     const long long shift = (long long)(dy_ - a.ph) * a.wp + (dx_ - a.pw);
-    const long long k_begin = (long long)blockIdx.x * a.rows_per_split;
+    const long long k_begin = (long long)blockIdx.y * a.rows_per_split;
     long long k_end = k_begin + a.rows_per_split;
     if (k_end > a.rows) k_end = a.rows;
     constexpr bool f16 = F16;
@@ -821,7 +825,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
-    dim3 grid((unsigned)splits, (unsigned)(taps * (a.cin / bn)), (unsigned)(a.cout / TC_BM));
+    dim3 grid((unsigned)(taps * (a.cin / bn)), (unsigned)splits, (unsigned)(a.cout / TC_BM));
     if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     else wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     DLIO_LAUNCH_CHECK();
