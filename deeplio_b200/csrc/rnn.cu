@@ -170,6 +170,356 @@ __global__ void __launch_bounds__(256) rnn_step_bwd_kernel(BwdArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ whole-sequence kernels (short hidden size)
+// For the IMU nets (H = 128, T = 15 .. 50) one launch runs ALL T steps of a layer.  A CLUSTER OF TWO CTAs serves one
+// (direction, chunk of RB batch rows): each CTA keeps the W_hh rows of half of the hidden units in shared memory
+// for the whole sequence (4 * 64 * 128 floats = 128 KB at H = 128), h_{t-1} in shared memory and c_{t-1} in
+// registers of the lane that owns (unit, batch row).  Every warp owns hidden units warp, warp + 16, ...; the G*RB
+// partial dot products of a unit are reduced with ONE 31-shuffle transpose-reduce (lane l ends with gate l / RB of
+// batch row l % RB) and three more shuffles bring the gates of a batch row together.  The two CTAs exchange their
+// halves of h_t through the layer output in global memory (which has to be written anyway): cluster barrier with
+// release / acquire, then an L1-bypassing reload of h_t.  60 step launches per IMU window become 4.
+constexpr int SEQ_WARPS = 16;
+constexpr int SEQ_CLUSTER = 2;
+
+__device__ __forceinline__ float warp_colsum32_rnn(float (&v)[32], int lane) {
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float keep = up ? v[j + n] : v[j];
+            const float send = up ? v[j] : v[j + n];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// all threads of both CTAs; orders the global-memory writes before it against the reads after it
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared-memory address of `p` in the peer CTA `rank` of the cluster, and a store through it (DSMEM)
+__device__ __forceinline__ uint32_t peer_smem(const void *p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_peer(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct SeqDir {
+    const float *w_hh, *b_hh, *gx;
+    const float *h0, *c0;          // [B, H] or nullptr (zeros)
+    float *gates, *cst, *hprev_save, *cprev_save;
+    float *y;                      // layer output [B, T, DH], this direction's columns start at y
+    float *hn, *cn;                // [B, H]
+};
+struct SeqArgs {
+    SeqDir d[2];
+    int B, T, H, DH;
+};
+constexpr int SEQ_ITEMS = 2;       // (batch row, unit) pairs per thread in the point-wise phase: RB * H / 2 <= 1024
+constexpr int SEQ_ROWT = 128;      // row threads of the recurrent product (x 4 k groups = 512 threads)
+constexpr int SEQ_MAXR = 3;        // W_hh rows per row thread: G * H / 2 <= 384
+
+// Step structure: (A) the recurrent pre-activations as a register-blocked product: thread (k group, row thread)
+// owns up to three W_hh rows x all RB batch rows for a quarter of the k range -- per k two 128-bit loads of h
+// (batch-contiguous, broadcast) and one conflict-free load per row feed 8 FMAs per row, no shuffles; the four
+// partial sums meet in shared memory.  (B) one thread per (batch row, unit) applies the cell non-linearity -- its
+// input-projection values gx were prefetched before (A), so their L2 latency is hidden -- keeps c_t in a register,
+// writes the saved tensors, and stores h_t into the NEXT h buffer of BOTH CTAs (the peer's through distributed
+// shared memory); one cluster barrier per step.  (A first version with one warp per hidden unit and a shuffle
+// transpose-reduce per unit spent 77 % of its 2200 instructions per warp and step outside the FMAs.)
+template <int KIND>
+__global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS * 32) rnn_seq_fwd_kernel(SeqArgs a) {
+    extern __shared__ float sm[];
+    constexpr int G = KIND == 0 ? 4 : 3;
+    const uint32_t rank = cluster_rank();
+    const SeqDir &s = a.d[blockIdx.x / SEQ_CLUSTER];
+    const bool reverse = blockIdx.x / SEQ_CLUSTER == 1;
+    const int H = a.H, T = a.T, HU = H / SEQ_CLUSTER, j0 = (int)rank * HU;
+    const int R = G * HU, RP = R + 1;          // own W_hh rows (g, u); padded row count of the transposed copy
+    const int b0 = blockIdx.y * RB;
+    const int nb = min(RB, a.B - b0);
+    float *ws = sm;                            // [H][RP]: ws[k][g * HU + u] = W_hh[g * H + j0 + u][k]
+    float *hs = ws + (((size_t)H * RP + 3) & ~(size_t)3);   // [2][H][RB], 16-byte aligned
+    float *part = hs + 2 * H * RB;             // [4 k groups][RB][R]
+    float *bhh = part + 4 * RB * R;            // [R]
+    // W_hh slice -> shared memory, 8 independent loads in flight per thread (one load per iteration made this
+    // prologue ~60 us of pure L2 latency per launch)
+    for (int i0 = threadIdx.x; i0 < R * H; i0 += 8 * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * blockDim.x;
+            const int k = i % H, r = i / H, g = r / HU, u = r - g * HU;      // coalesced along k
+            v[q] = i < R * H ? __ldg(s.w_hh + ((size_t)g * H + j0 + u) * H + k) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * blockDim.x;
+            if (i < R * H) ws[(size_t)(i % H) * RP + i / H] = v[q];
+        }
+    }
+    for (int i = threadIdx.x; i < R; i += blockDim.x) bhh[i] = __ldg(s.b_hh + (size_t)(i / HU) * H + j0 + i % HU);
+    for (int i = threadIdx.x; i < RB * H; i += blockDim.x) {
+        int b = i / H, k = i - b * H;
+        hs[k * RB + b] = (b < nb && s.h0) ? s.h0[(size_t)(b0 + b) * H + k] : 0.f;
+    }
+    // point-wise role: items it = threadIdx.x + q * blockDim.x  <->  (batch row it / HU, unit it % HU)
+    float creg[SEQ_ITEMS];
+#pragma unroll
+    for (int q = 0; q < SEQ_ITEMS; ++q) {
+        const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
+        creg[q] = (KIND == 0 && it < RB * HU && bl < nb && s.c0) ? s.c0[(size_t)(b0 + bl) * H + j0 + u] : 0.f;
+    }
+    const uint32_t peer_hs = peer_smem(hs, rank ^ 1u);
+    const int kg = threadIdx.x / SEQ_ROWT, rp = threadIdx.x % SEQ_ROWT;
+    const int kper = (H + 3) / 4, k_begin = kg * kper, k_end = min(H, k_begin + kper);
+    bool rowok[SEQ_MAXR];
+#pragma unroll
+    for (int m = 0; m < SEQ_MAXR; ++m) rowok[m] = rp + m * SEQ_ROWT < R;
+    cluster_barrier();                         // both CTAs are set up before any remote store
+    int cur = 0;
+    for (int step = 0; step < T; ++step) {
+        const int t = reverse ? T - 1 - step : step;
+        const float *hc = hs + cur * H * RB;
+        // prefetch the input projections of this step for the point-wise role
+        float gxr[SEQ_ITEMS][G];
+#pragma unroll
+        for (int q = 0; q < SEQ_ITEMS; ++q) {
+            const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
+            if (it < RB * HU && bl < nb) {
+                const float *gx = s.gx + ((size_t)(b0 + bl) * T + t) * G * H + j0 + u;
+#pragma unroll
+                for (int g = 0; g < G; ++g) gxr[q][g] = __ldg(gx + (size_t)g * H);
+            }
+        }
+        // (A) recurrent pre-activations, partial over this thread's k range
+        {
+            float acc[SEQ_MAXR][RB];
+#pragma unroll
+            for (int m = 0; m < SEQ_MAXR; ++m)
+#pragma unroll
+                for (int b = 0; b < RB; ++b) acc[m][b] = 0.f;
+            const float *wr = ws + (size_t)k_begin * RP + rp;
+            const float *hp4 = hc + k_begin * RB;
+#pragma unroll 4
+            for (int k = k_begin; k < k_end; ++k, wr += RP, hp4 += RB) {
+                const float4 h0 = *reinterpret_cast<const float4 *>(hp4);
+                const float4 h1 = *reinterpret_cast<const float4 *>(hp4 + 4);
+                const float hv[RB] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int m = 0; m < SEQ_MAXR; ++m) {
+                    const float w = rowok[m] ? wr[m * SEQ_ROWT] : 0.f;      // select, not a branch
+#pragma unroll
+                    for (int b = 0; b < RB; ++b) acc[m][b] = fmaf(w, hv[b], acc[m][b]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < SEQ_MAXR; ++m) {
+                const int r = rp + m * SEQ_ROWT;
+                if (r < R) {
+#pragma unroll
+                    for (int b = 0; b < RB; ++b) part[(kg * RB + b) * R + r] = acc[m][b];
+                }
+            }
+        }
+        __syncthreads();
+        // (B) cell update, one (batch row, unit) per thread
+        float *hnext = hs + (cur ^ 1) * H * RB;
+#pragma unroll
+        for (int q = 0; q < SEQ_ITEMS; ++q) {
+            const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
+            if (it >= RB * HU || bl >= nb) continue;
+            const int b = b0 + bl, j = j0 + u;
+            const size_t row = (size_t)b * T + t;
+            const float hp = hc[j * RB + bl];
+            float pre[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int r = g * HU + u;
+                pre[g] = ((part[(0 * RB + bl) * R + r] + part[(1 * RB + bl) * R + r]) +
+                          (part[(2 * RB + bl) * R + r] + part[(3 * RB + bl) * R + r])) + bhh[r];
+            }
+            float h;
+            if (KIND == 0) {
+                const float gi = sigmoidf_(gxr[q][0] + pre[0]), gf = sigmoidf_(gxr[q][1] + pre[1]);
+                const float gg = tanhf(gxr[q][2] + pre[2]), go = sigmoidf_(gxr[q][3] + pre[3]);
+                const float cp = creg[q];
+                const float c = gf * cp + gi * gg;
+                h = go * tanhf(c);
+                creg[q] = c;
+                float *gt = s.gates + row * 4 * H;
+                gt[j] = gi; gt[H + j] = gf; gt[2 * H + j] = gg; gt[3 * H + j] = go;
+                s.cst[row * H + j] = c;
+                s.cprev_save[row * H + j] = cp;
+                if (step == T - 1 && s.cn) s.cn[(size_t)b * H + j] = c;
+            } else {
+                const float ghn = pre[2];
+                const float r = sigmoidf_(gxr[q][0] + pre[0]), z = sigmoidf_(gxr[q][1] + pre[1]);
+                const float n = tanhf(gxr[q][2] + r * ghn);
+                h = (1.f - z) * n + z * hp;
+                float *gt = s.gates + row * 4 * H;
+                gt[j] = r; gt[H + j] = z; gt[2 * H + j] = n; gt[3 * H + j] = ghn;
+            }
+            s.hprev_save[row * H + j] = hp;
+            s.y[((size_t)b * T + t) * a.DH + j] = h;
+            if (step == T - 1 && s.hn) s.hn[(size_t)b * H + j] = h;
+            hnext[j * RB + bl] = h;
+            st_peer(peer_hs + (uint32_t)(((cur ^ 1) * H * RB + j * RB + bl) * sizeof(float)), h);
+        }
+        cluster_barrier();      // h_t complete in both CTAs; everybody is done reading h_{t-1} and the partial sums
+        cur ^= 1;
+    }
+}
+
+// Backward through time in one launch (same clusters).  Per step: (1) point-wise gate gradients of the CTA's own
+// units from (dh, dc) -- written to global memory for the weight-gradient GEMMs that follow the time loop and kept
+// in shared memory (the saved gates of the NEXT step are prefetched meanwhile); (2) the recurrent product over
+// the CTA's own W_hh rows, dh_{t-1}[b][k] += sum_r dg[b][r] W_hh[r][k] for ALL k: the half that belongs to the
+// peer's units is stored straight into the peer's shared memory (double-buffered), one cluster barrier per step.
+struct SeqBwdDir {
+    const float *w_hh;
+    const float *gates, *cst, *hprev_save, *cprev_save;
+    const float *dout;             // gradient of the layer output, this direction's columns ([B, T, DH]) or nullptr
+    float *dh_rec, *dc_rec;        // [B, H]: in: gradient of (h_n, c_n); out: gradient of (h_0, c_0)
+    float *dgx, *dgh;              // [B*T, G*H]
+};
+struct SeqBwdArgs {
+    SeqBwdDir d[2];
+    int B, T, H, DH;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS * 32) rnn_seq_bwd_kernel(SeqBwdArgs a) {
+    extern __shared__ float sm[];
+    constexpr int G = KIND == 0 ? 4 : 3;
+    const uint32_t rank = cluster_rank();
+    const SeqBwdDir &s = a.d[blockIdx.x / SEQ_CLUSTER];
+    const bool reverse = blockIdx.x / SEQ_CLUSTER == 1;
+    const int H = a.H, T = a.T, HU = H / SEQ_CLUSTER, j0 = (int)rank * HU, GU = G * HU;
+    const int b0 = blockIdx.y * RB;
+    const int nb = min(RB, a.B - b0);
+    const int ngroups = blockDim.x / H;
+    float *ws = sm;                          // [G * HU][H]
+    float *dg = ws + (size_t)GU * H;         // [G * HU][RB] recurrent gate gradients of this step (own units), batch-contiguous
+    float *dh = dg + RB * GU;                // [RB][HU]
+    float *dc = dh + RB * HU;                // [RB][HU]
+    float *part = dc + RB * HU;              // [ngroups][RB][H] partial products of the row groups
+    float *xin = part + ngroups * RB * H;    // [2][RB][HU] contributions received from the peer (by step parity)
+    for (int i0 = threadIdx.x; i0 < GU * H; i0 += 8 * blockDim.x) {      // 8 independent loads in flight
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * blockDim.x;
+            const int k = i % H, ru = i / H, g = ru / HU, u = ru - g * HU;
+            v[q] = i < GU * H ? __ldg(s.w_hh + ((size_t)g * H + j0 + u) * H + k) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * blockDim.x;
+            if (i < GU * H) ws[i] = v[q];
+        }
+    }
+    for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
+        int b = i / HU, u = i - b * HU;
+        dh[i] = b < nb ? s.dh_rec[(size_t)(b0 + b) * H + j0 + u] : 0.f;
+        dc[i] = (KIND == 0 && b < nb) ? s.dc_rec[(size_t)(b0 + b) * H + j0 + u] : 0.f;
+    }
+    const uint32_t peer_xin = peer_smem(xin, rank ^ 1u);
+    cluster_barrier();
+    const int kq = threadIdx.x % H, rg = threadIdx.x / H;
+    for (int step = T - 1; step >= 0; --step) {
+        const int t = reverse ? T - 1 - step : step;
+        for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
+            const int bl = i / HU, u = i - bl * HU, j = j0 + u;
+            float *dgr = dg + u * RB + bl;       // + g * HU * RB
+            if (bl >= nb) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) dgr[g * HU * RB] = 0.f;
+                continue;
+            }
+            const int b = b0 + bl;
+            const size_t row = (size_t)b * T + t;
+            const float dhv = dh[i] + (s.dout ? __ldg(s.dout + ((size_t)b * T + t) * a.DH + j) : 0.f);
+            if (KIND == 0) {
+                const float *gt = s.gates + row * 4 * H;
+                const float gi = __ldg(gt + j), gf = __ldg(gt + H + j), gg = __ldg(gt + 2 * H + j), go = __ldg(gt + 3 * H + j);
+                const float tc = tanhf(__ldg(s.cst + row * H + j));
+                const float cp = __ldg(s.cprev_save + row * H + j);
+                const float dcv = dhv * go * (1.f - tc * tc) + dc[i];
+                const float d0 = dcv * gg * gi * (1.f - gi), d1 = dcv * cp * gf * (1.f - gf);
+                const float d2 = dcv * gi * (1.f - gg * gg), d3 = dhv * tc * go * (1.f - go);
+                float *o = s.dgx + row * 4 * H;
+                o[j] = d0; o[H + j] = d1; o[2 * H + j] = d2; o[3 * H + j] = d3;
+                dgr[0] = d0; dgr[HU * RB] = d1; dgr[2 * HU * RB] = d2; dgr[3 * HU * RB] = d3;
+                dc[i] = dcv * gf;
+                dh[i] = 0.f;
+            } else {
+                const float *gt = s.gates + row * 4 * H;
+                const float r = __ldg(gt + j), z = __ldg(gt + H + j), n = __ldg(gt + 2 * H + j), ghn = __ldg(gt + 3 * H + j);
+                const float hp = __ldg(s.hprev_save + row * H + j);
+                const float dn_pre = dhv * (1.f - z) * (1.f - n * n);
+                const float dr_pre = dn_pre * ghn * r * (1.f - r);
+                const float dz_pre = dhv * (hp - n) * z * (1.f - z);
+                float *ox = s.dgx + row * 3 * H, *oh = s.dgh + row * 3 * H;
+                ox[j] = dr_pre; ox[H + j] = dz_pre; ox[2 * H + j] = dn_pre;
+                oh[j] = dr_pre; oh[H + j] = dz_pre; oh[2 * H + j] = dn_pre * r;
+                dgr[0] = dr_pre; dgr[HU * RB] = dz_pre; dgr[2 * HU * RB] = dn_pre * r;
+                dh[i] = dhv * z;
+            }
+        }
+        __syncthreads();
+        // partial dh_{t-1}[b][k] over this CTA's rows; row group rg handles rows rg, rg + ngroups, ...
+        if (rg < ngroups) {
+            float acc[RB];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) acc[b] = 0.f;
+#pragma unroll 4
+            for (int r = rg; r < GU; r += ngroups) {
+                const float wv = ws[(size_t)r * H + kq];
+                const float4 g0 = *reinterpret_cast<const float4 *>(dg + r * RB);       // broadcast loads
+                const float4 g1 = *reinterpret_cast<const float4 *>(dg + r * RB + 4);
+                acc[0] = fmaf(g0.x, wv, acc[0]); acc[1] = fmaf(g0.y, wv, acc[1]);
+                acc[2] = fmaf(g0.z, wv, acc[2]); acc[3] = fmaf(g0.w, wv, acc[3]);
+                acc[4] = fmaf(g1.x, wv, acc[4]); acc[5] = fmaf(g1.y, wv, acc[5]);
+                acc[6] = fmaf(g1.z, wv, acc[6]); acc[7] = fmaf(g1.w, wv, acc[7]);
+            }
+#pragma unroll
+            for (int b = 0; b < RB; ++b) part[(rg * RB + b) * H + kq] = acc[b];
+        }
+        __syncthreads();
+        const int par = step & 1;
+        for (int i = threadIdx.x; i < RB * H; i += blockDim.x) {
+            const int bl = i / H, k = i - bl * H;
+            float v = 0.f;
+            for (int q = 0; q < ngroups; ++q) v += part[(q * RB + bl) * H + k];
+            const int owner = k / HU, u = k - owner * HU;
+            if (owner == (int)rank) dh[bl * HU + u] += v;
+            else st_peer(peer_xin + (uint32_t)((par * RB * HU + bl * HU + u) * sizeof(float)), v);
+        }
+        cluster_barrier();
+        for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) dh[i] += xin[par * RB * HU + i];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
+        int b = i / HU, u = i - b * HU;
+        if (b < nb) {
+            s.dh_rec[(size_t)(b0 + b) * H + j0 + u] = dh[i];
+            if (KIND == 0) s.dc_rec[(size_t)(b0 + b) * H + j0 + u] = dc[i];
+        }
+    }
+}
+
 __global__ void mul_inplace_kernel(float *x, const float *__restrict__ m, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -196,6 +546,22 @@ struct RnnLayout {
     float *yout(float *r, int l) const { return r + l * per_layer + D * per_dir; }
     int in_size(int l) const { return l == 0 ? I : D * H; }
 };
+
+// whole-sequence kernels: the W_hh rows of half the hidden units must fit in one CTA's shared memory (H <= 152 for
+// an LSTM, 176 for a GRU), and a single step is not worth a cluster launch
+static size_t seq_fwd_smem(int kind, int H) {
+    const size_t G = kind == 0 ? 4 : 3, R = G * (H / 2);
+    return ((((size_t)H * (R + 1) + 3) & ~(size_t)3) + 2 * (size_t)RB * H + 4 * RB * R + R) * sizeof(float);
+}
+static size_t seq_bwd_smem(int kind, int H) {
+    const size_t G = kind == 0 ? 4 : 3, HU = H / 2, threads = SEQ_WARPS * 32;
+    return (G * HU * H + RB * G * HU + 2 * RB * HU + (threads / H) * RB * H + 2 * RB * HU) * sizeof(float);
+}
+static bool use_seq_kernels(int kind, int H, int T) {
+    return H % 2 == 0 && H >= 16 && H <= SEQ_WARPS * 32 && (size_t)RB * (H / 2) <= (size_t)SEQ_ITEMS * SEQ_WARPS * 32 && T >= 2 &&
+           (kind == 0 ? 4 : 3) * (H / 2) <= SEQ_ROWT * SEQ_MAXR &&
+           seq_bwd_smem(kind, H) <= 200 * 1024 && seq_fwd_smem(kind, H) <= 200 * 1024;
+}
 
 static int check_rnn(int kind, int L, int D, int B, int T, int I, int H) {
     DLIO_CHECK_ARG((kind == 0 || kind == 1) && L >= 1 && (D == 1 || D == 2) && B > 0 && T > 0 && I > 0 && H > 0,
@@ -243,6 +609,31 @@ extern "C" int dlio_rnn_fwd(int kind, int L, int D, int B, int T, int I, int H, 
                                         lay.gx(reserve, l, d), G * H, st)))
                 return rc;
         }
+        if (use_seq_kernels(kind, H, T)) {
+            // one launch for all T steps (short hidden size: the IMU nets)
+            SeqArgs a;
+            a.B = B; a.T = T; a.H = H; a.DH = (int)DH;
+            for (int d = 0; d < D; ++d) {
+                const float *const *w = weights + 4 * (l * D + d);
+                const size_t slot = (size_t)(l * D + d) * B * H;
+                SeqDir &q = a.d[d];
+                q.w_hh = w[1]; q.b_hh = w[3]; q.gx = lay.gx(reserve, l, d);
+                q.h0 = h0 ? h0 + slot : nullptr;
+                q.c0 = c0 ? c0 + slot : nullptr;
+                q.gates = lay.gates(reserve, l, d); q.cst = lay.cst(reserve, l, d);
+                q.hprev_save = lay.hps(reserve, l, d); q.cprev_save = lay.cps(reserve, l, d);
+                q.y = yl + (size_t)d * H;
+                q.hn = hn + slot;
+                q.cn = kind == 0 ? cn + slot : nullptr;
+            }
+            dim3 grid(D * SEQ_CLUSTER, ceil_div(B, RB));
+            const size_t sm = seq_fwd_smem(kind, H);
+            DLIO_CUDA(cudaFuncSetAttribute(rnn_seq_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DLIO_CUDA(cudaFuncSetAttribute(rnn_seq_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (kind == 0) rnn_seq_fwd_kernel<0><<<grid, SEQ_WARPS * 32, sm, st>>>(a);
+            else rnn_seq_fwd_kernel<1><<<grid, SEQ_WARPS * 32, sm, st>>>(a);
+            DLIO_LAUNCH_CHECK();
+        } else
         for (int s = 0; s < T; ++s) {
             StepArgs a;
             a.B = B; a.T = T; a.H = H;
@@ -318,6 +709,29 @@ extern "C" int dlio_rnn_bwd(int kind, int L, int D, int B, int T, int I, int H, 
     for (int l = L - 1; l >= 0; --l) {
         const int Il = lay.in_size(l);
         const float *xin = l == 0 ? x : lay.yout(reserve, l - 1);
+        if (use_seq_kernels(kind, H, T)) {
+            SeqBwdArgs a;
+            a.B = B; a.T = T; a.H = H; a.DH = (int)DH;
+            for (int d = 0; d < D; ++d) {
+                const float *const *w = weights + 4 * (l * D + d);
+                const size_t slot = (size_t)(l * D + d) * B * H;
+                SeqBwdDir &q = a.d[d];
+                q.w_hh = w[1];
+                q.gates = lay.gates(reserve, l, d); q.cst = lay.cst(reserve, l, d);
+                q.hprev_save = lay.hps(reserve, l, d); q.cprev_save = lay.cps(reserve, l, d);
+                q.dout = dy ? dy + (size_t)d * H : nullptr;
+                q.dh_rec = dh0 + slot; q.dc_rec = kind == 0 ? dc0 + slot : nullptr;
+                q.dgx = dg[d][0]; q.dgh = dg[d][1];
+            }
+            const int threads = SEQ_WARPS * 32;
+            const size_t sm = seq_bwd_smem(kind, H);
+            DLIO_CUDA(cudaFuncSetAttribute(rnn_seq_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DLIO_CUDA(cudaFuncSetAttribute(rnn_seq_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            dim3 grid(D * SEQ_CLUSTER, ceil_div(B, RB));
+            if (kind == 0) rnn_seq_bwd_kernel<0><<<grid, threads, sm, st>>>(a);
+            else rnn_seq_bwd_kernel<1><<<grid, threads, sm, st>>>(a);
+            DLIO_LAUNCH_CHECK();
+        } else
         for (int s = T - 1; s >= 0; --s) {
             BwdArgs a;
             a.B = B; a.T = T; a.H = H;
