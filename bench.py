@@ -10,6 +10,7 @@ Prints ONE JSON line on rank 0.  ``--impl reference`` times the CPU restatement 
 reference is pure Python / PyTorch and does not travel to the GPU box) on the host cores.
 """
 import argparse
+import itertools
 import json
 import os
 import statistics
@@ -154,6 +155,7 @@ def run_b200(args):
     from deeplio_b200 import _lib, functional as Fn, nets, parallel
     from deeplio_b200.config import build_config_container
     from deeplio_b200.optim import FlatAdam
+    from deeplio_b200.pipeline import DevicePrefetcher, LaggedScalar
     from deeplio_b200.workloads import workload_config
 
     rank, local_rank, world = parallel.init_from_env()
@@ -162,7 +164,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.device_check(local_rank)
-    cfg, B, S, T = workload_config(WORKLOAD, H, W)
+    workload = args.workload or WORKLOAD
+    cfg, B, S, T = workload_config(workload, H, W)
     B = args.batch or B                       # per-GPU batch (weak scaling)
     build_config_container(cfg, argparse.Namespace(device=str(dev), batch_size=B))
     torch.manual_seed(1234)
@@ -204,11 +207,11 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """``fn(steps)`` enqueues ``steps`` train steps; device time between two events on the launching stream"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn(steps)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -223,16 +226,27 @@ def run_b200(args):
     sampler.start()
     _lib.profile_enable(1)
     n0 = _lib.launch_count()
-    ms_total = timed(lambda: train_step(resident), args.steps)
+    def resident_steps(steps):
+        for _ in range(steps):
+            train_step(resident)
+    ms_total = timed(resident_steps, args.steps)
     launches = _lib.launch_count() - n0
     prof = _lib.profile_read()
     _lib.profile_enable(0)
 
-    def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return float(train_step(d).item())           # device -> host read of the loss every step
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    # end to end through the public API: every step's inputs come from pinned host memory (copied on a copy stream
+    # one step ahead, deeplio_b200.pipeline.DevicePrefetcher) and every step's loss is read back on the host (one
+    # step late, LaggedScalar); all copies and reads happen inside the timed region
+    losses = []
+
+    def e2e_steps(steps):
+        lag = LaggedScalar()
+        for d in DevicePrefetcher(itertools.repeat(host, steps), dev):
+            losses.append(lag.push(train_step(d)))
+        losses.append(lag.flush())
+    e2e_steps(2)
+    ms_e2e = timed(e2e_steps, args.steps)
+    assert all(v is None or v == v for v in losses), "non-finite loss in the end-to-end run"
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
@@ -242,7 +256,9 @@ def run_b200(args):
     e2e = pairs_per_step * args.steps / (ms_e2e / 1e3)
 
     # roofline of the dominant kernel class (largest share of the step among the profiled conv classes)
-    flops = {k: 2 * v for k, v in conv_flops_simple1(B * S).items()}    # two encoders
+    # per-class FLOP accounting exists for the headline workload's encoder (Simple-1); other workloads (secondary
+    # runs, --workload) report class times only
+    flops = {k: 2 * v for k, v in conv_flops_simple1(B * S).items()} if "simple1" in workload else {}    # two encoders
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -261,7 +277,7 @@ def run_b200(args):
             classes[name]["gflop_per_step"] = flops[name] / 1e9
             classes[name]["tflops"] = flops[name] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None
     roofline = None
-    if classes:
+    if classes and flops:
         dom = max((k for k in classes if k in flops), key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
         tc = dom.endswith("_tc")
@@ -282,7 +298,7 @@ def run_b200(args):
                     "launch_ms": c["ms_per_step"] / c["launches_per_step"], "classes": classes}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and workload == WORKLOAD:
         fps, sec, cores = cpu_train_steps(3, 1)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "batch 1 x S=2 (2 frame pairs) per step, 3 timed steps after 1 warm-up, %.2f s/step" % sec}
@@ -291,13 +307,15 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "pairs_per_sample": S,
+                "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "pairs_per_sample": S,
                            "image": "64x2048x6 x2 (xyz, normals)", "imu_window": T, "parallelism": "dp%d" % world,
                            "params_M": n_params / 1e6, "optimizer": "adam lr 1e-3 wd 1e-4 (fused, flat arena)",
                            "l2": "working set per step (%.1f GB peak, activations) exceeds the 126 MB L2; no explicit flush" % peak_gb},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline}
+        if roofline is None:
+            line["classes"] = classes
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -311,6 +329,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's, 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="", help="secondary runs: another BASELINE.json workload "
+                    "(deeplio_b200.workloads.WORKLOADS); the default is the headline workload")
     args = ap.parse_args()
     # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry the one JSON line only
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
