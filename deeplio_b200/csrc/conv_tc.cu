@@ -592,6 +592,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
 struct TcWgradArgs {
     int kh, kw, ph, pw, wp;
     int cin, cout, bn, stages;
+    int swap;          // operands swapped (narrow Cin): A = x tiles of FOUR taps (M = 4 x 32 ci), B = dy (N = 128 co)
     long long rows, rows_per_split;
     float *dw;
     int f16;
@@ -628,8 +629,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     // together work on the SAME pixel range for different taps, so dy (identical for every tap) and x (shifted by a
     // few rows) are served by L2 -- with the split index fastest, every tap streamed both tensors from DRAM again
     // (ncu: 1.7 GB read for 0.42 GB of operands in Simple-1 conv2, 50 % DRAM utilisation)
+    //
+    // swap mode (Cin == 32: the first layer through its space-to-depth view).  With dy as the A operand, a 128 x 32
+    // tile costs one MMA per 32 bytes of K that reads the whole 4 KB dy slice from shared memory for 32 columns of
+    // output: ~60 clocks per MMA against a 16-clock floor, shared-memory bound.  Swapped, the M = 128 rows of A are the
+    // 32 input channels of FOUR taps (four x boxes at four row shifts -- a tap is nothing but a row shift) and dy is
+    // the B operand with N = 128 output channels: a quarter of the MMAs for the same shared-memory bytes each.
+    // Then blockIdx.x = group of four taps, blockIdx.z = 128-channel block of Cout, the tile is dw^T.
     const int nblk = a.cin / a.bn;
-    const int tap = blockIdx.x / nblk, ci0 = (blockIdx.x - tap * nblk) * a.bn;
+    const bool swap = a.swap != 0;
+    const int taps_all = a.kh * a.kw;
+    const int tap = swap ? blockIdx.x * 4 : blockIdx.x / nblk;
+    const int ci0 = swap ? 0 : (blockIdx.x - tap * nblk) * a.bn;
     const int co0 = blockIdx.z * TC_BM;
     const int dy_ = tap / a.kw, dx_ = tap - dy_ * a.kw;
     const long long shift = (long long)(dy_ - a.ph) * a.wp + (dx_ - a.pw);
@@ -677,14 +688,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
                 const uint32_t sa = smem_u32(smem) + s * stage_bytes;
                 const uint32_t fb = full0 + 8 * s;
                 mbar_expect_tx(fb, stage_bytes);
+                if (swap) {
+                    // A: x boxes of taps tap .. tap + 3 (the host passes the x maps first); a tap past the last one
+                    // reads rows far outside the tensor, which TMA fills with zeros
 #pragma unroll
-                for (int j = 0; j < na_boxes; ++j) {
-                    tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, q);
-                    tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, q);
-                }
-                for (int j = 0; j < nb_boxes; ++j) {
-                    tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, ci0 + bc * j, q + qs);
-                    tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, ci0 + bc * j, q + qs);
+                    for (int j = 0; j < na_boxes; ++j) {
+                        const int tj = tap + j, dyj = tj / a.kw, dxj = tj - dyj * a.kw;
+                        const int rj = tj < taps_all ? q + (dyj - a.ph) * a.wp + (dxj - a.pw) : -(1 << 30);
+                        tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, 0, rj);
+                        tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, 0, rj);
+                    }
+                    for (int j = 0; j < nb_boxes; ++j) {
+                        tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, co0 + bc * j, q);
+                        tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, co0 + bc * j, q);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < na_boxes; ++j) {
+                        tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, q);
+                        tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, q);
+                    }
+                    for (int j = 0; j < nb_boxes; ++j) {
+                        tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, ci0 + bc * j, q + qs);
+                        tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, ci0 + bc * j, q + qs);
+                    }
                 }
             }
             __syncwarp();
@@ -724,7 +751,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
         const int quad = warp & 3;
         const int co = co0 + quad * 32 + lane;
         const int taps = a.kh * a.kw;
-        float *orow = a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
+        // swap: TMEM lane = (tap quad, ci lane), column = output channel
+        float *orow = swap ? a.dw + ((size_t)co0 * taps + (tap + quad)) * a.cin + lane
+                           : a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
+        const bool row_ok = !swap || tap + quad < taps;
         float inv = 1.f, corr = 1.f;
         if (f16) {
             inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.yb));
@@ -743,6 +773,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
             }
             tmem_ld32(trow + 3 * a.bn, u);
             const int ncol = min(32, a.bn - c0);
+            if (swap) {
+                if (row_ok) {
+                    const size_t cstride = (size_t)taps * a.cin;      // next output channel
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        atomicAdd(orow + (size_t)(c0 + j) * cstride,
+                                  fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv);
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 if (j < ncol)
@@ -776,13 +816,15 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     for (int c : {128, 64, 32})
         if (a.cin % c == 0 && c % bc == 0) { bn = c; break; }
     if (!bn) return 0;
+    const bool swap = !f16 && a.cin == 32;       // see the kernel: four taps' x tiles as A, dy as B
+    if (swap) bn = TC_BM;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
     if (rows >= (1LL << 31) - 4096) return 0;
     if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out |
           (uintptr_t)a.x_h2 | (uintptr_t)a.w_h2) & 15) != 0) return 0;
 
     const int taps = a.kh * a.kw;
-    const int tiles = taps * (a.cin / bn) * (a.cout / TC_BM);
+    const int tiles = swap ? ((taps + 3) / 4) * (a.cout / TC_BM) : taps * (a.cin / bn) * (a.cout / TC_BM);
     // K splits: one CTA per SM (192 KB of smem), so the grid should fill whole waves of 148 CTAs -- a grid of
     // 450 CTAs (3.04 waves) ran at 76 % of a 444-CTA one.  Pick the split count whose total is closest below a
     // multiple of 148 among 2..4 waves, keeping at least 64 K chunks per CTA.
@@ -803,7 +845,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
 
     TcWgradArgs t;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw; t.wp = a.x.wp;
-    t.cin = a.cin; t.cout = a.cout; t.bn = bn;
+    t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.swap = swap ? 1 : 0;
     t.rows = rows; t.rows_per_split = rps; t.dw = a.out;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.yb = a.w_bound;
     const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
@@ -825,8 +867,9 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
-    dim3 grid((unsigned)(taps * (a.cin / bn)), (unsigned)splits, (unsigned)(a.cout / TC_BM));
+    dim3 grid((unsigned)(swap ? (taps + 3) / 4 : taps * (a.cin / bn)), (unsigned)splits, (unsigned)(a.cout / TC_BM));
     if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
+    else if (swap) wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mdh, mdl, t);   // x as A, dy as B
     else wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     DLIO_LAUNCH_CHECK();
     return 1;

@@ -218,6 +218,10 @@ TC_CASES = [
     (2, 80, 384, 6, 10, (3, 3), True, 0, 0),
     (2, 48, 192, 7, 9, (3, 3), True, 0, 0),
     (4, 64, 256, 8, 16, (3, 3), True, 0, 0),
+    # Cin = 32 with Cout % 128 == 0 (the first layer's space-to-depth view): wgrad with swapped operands, four taps
+    # per CTA -- 15 taps leave one dummy tap in the last group, 9 taps three
+    (2, 32, 128, 9, 21, (5, 3), True, 0, 0),
+    (3, 32, 256, 6, 14, (3, 3), False, 0, 1),
 ]
 
 
