@@ -22,7 +22,7 @@ class Conv(C.Structure):
 
 
 class BnPool(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("relu", "res_mode", "pool_k", "pool_sh", "pool_sw", "c_off")]
+    _fields_ = [(k, C.c_int) for k in ("relu", "res_mode", "pool_k", "pool_sh", "pool_sw", "c_off", "out_group")]
 
 
 class DlioError(RuntimeError):
@@ -55,6 +55,8 @@ _PROTOS = {
     "dlio_weight_flip_transpose": (I, [P, I, I, I, I, P, P, P]),
     "dlio_weight_pack_f16": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "dlio_pack_f16": (I, [P, LL, I, P, P, P]),
+    "dlio_weight_pack_pair_f16": (I, [P, I, I, I, I, I, I, P, P, P]),
+    "dlio_weight_grad_from_pair": (I, [P, I, I, I, I, P, P]),
     "dlio_conv2d_fwd_f16": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
     "dlio_conv2d_bwd_data_f16": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, P]),
     "dlio_conv2d_bwd_weight_f16": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
@@ -87,7 +89,7 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 if _lib.dlio_abi_version() != ABI_VERSION:
     raise ImportError("deeplio_b200: ABI version mismatch (library %d, binding %d)" % (_lib.dlio_abi_version(), ABI_VERSION))
 

@@ -122,22 +122,29 @@ __device__ __forceinline__ void f16_split(float v, __half &hi, __half &lo) {   /
     hi = __float2half_rn(v);
     lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
-// stores 4 consecutive channels (c % 4 == 0) of packed row `row` (C channels per half-row)
-__device__ __forceinline__ void st4_h2(__half *base, size_t row, int C, int c, const float4 &v, float s) {
+// stores 4 consecutive channels (c % 4 == 0) of packed row `row` (C channels per half-row).
+// group == 2 ("pixel-pair layout"): a packed row holds TWO consecutive pixels, [p0 C hi | p1 C hi | p0 C lo | p1 C lo]
+// -- the layout of a tensor whose consumer is a stride-2 convolution run on the tensor cores through the
+// pixel-pair view [n, h, w/2, 2C] (conv_s2d.cu); `row` is still the pixel index (the padded width must be even).
+__device__ __forceinline__ __half *h2_addr(__half *base, size_t row, int C, int c, int group) {
+    return group == 2 ? base + (row >> 1) * (size_t)(4 * C) + (row & 1) * (size_t)C + c
+                      : base + row * (size_t)(2 * C) + c;
+}
+__device__ __forceinline__ void st4_h2(__half *base, size_t row, int C, int c, const float4 &v, float s, int group = 1) {
     __align__(8) __half h[4];
     __align__(8) __half l[4];
     f16_split(v.x * s, h[0], l[0]);
     f16_split(v.y * s, h[1], l[1]);
     f16_split(v.z * s, h[2], l[2]);
     f16_split(v.w * s, h[3], l[3]);
-    __half *p = base + row * (size_t)(2 * C) + c;
+    __half *p = h2_addr(base, row, C, c, group);
     *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(h);
-    *reinterpret_cast<uint2 *>(p + C) = *reinterpret_cast<const uint2 *>(l);
+    *reinterpret_cast<uint2 *>(p + (group == 2 ? 2 * C : C)) = *reinterpret_cast<const uint2 *>(l);
 }
-__device__ __forceinline__ void st4_h2_zero(__half *base, size_t row, int C, int c) {
-    __half *p = base + row * (size_t)(2 * C) + c;
+__device__ __forceinline__ void st4_h2_zero(__half *base, size_t row, int C, int c, int group = 1) {
+    __half *p = h2_addr(base, row, C, c, group);
     *reinterpret_cast<uint2 *>(p) = make_uint2(0u, 0u);
-    *reinterpret_cast<uint2 *>(p + C) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2 *>(p + (group == 2 ? 2 * C : C)) = make_uint2(0u, 0u);
 }
 // atomic max of non-negative floats (their bit patterns order like unsigned integers)
 __device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {

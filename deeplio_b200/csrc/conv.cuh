@@ -20,6 +20,7 @@ struct ConvArgs {
     double *stats;
     Geo o;               // geometry of `out` for dgrad (dx)
     long long p_chunk;   // wgrad: pixels per z-slice
+    int hdec = 1;        // conv_tc_fwd: 2 = store / count only the even rows of the (stride-1) result
 };
 
 // conv_tc.cu: return 1 if the tcgen05 kernel took the problem, 0 if it does not apply, < 0 on error

@@ -111,8 +111,16 @@ extern "C" int dlio_pack_f16(const float *src, long long rows, int c, float *bou
 extern "C" int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, const void *w_h2,
                                    const float *w_bound, const float *bias, dlio_conv cv, int act, dlio_tensor4 y,
                                    float *y_ptr, double *stats, void *stream) {
-    int rc = same_conv_check(x, y, cv, "conv2d_fwd_f16");
-    if (rc) return rc;
+    // cv.sh == 2 (cv.sw == 1): computed as a stride-1 convolution, even rows stored (include/deeplio_b200.h)
+    const int hdec = cv.sh == 2 ? 2 : 1;
+    int rc;
+    if (hdec == 2) {
+        DLIO_CHECK_ARG(valid_t4(x) && valid_t4(y) && x.n == y.n && cv.sw == 1 && cv.kh == 2 * cv.ph + 1 &&
+                           cv.kw == 2 * cv.pw + 1 && x.w == y.w && y.h == (x.h - 1) / 2 + 1,
+                       "conv2d_fwd_f16: bad geometry for an H-stride-2 convolution");
+    } else if ((rc = same_conv_check(x, y, cv, "conv2d_fwd_f16"))) {
+        return rc;
+    }
     DLIO_CHECK_ARG(x_h2 && x_bound && w_h2 && w_bound && y_ptr, "conv2d_fwd_f16: null pointer");
     ConvArgs a;
     a.x = Geo(x); a.y = Geo(y); a.o = Geo(y);
@@ -120,7 +128,7 @@ extern "C" int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float
     a.cin = x.c; a.cout = y.c; a.act = act;
     a.x_hi = a.x_lo = a.w_hi = a.w_lo = nullptr;
     a.x_h2 = (const __half *)x_h2; a.w_h2 = (const __half *)w_h2; a.x_bound = x_bound; a.w_bound = w_bound;
-    a.bias = bias; a.out = y_ptr; a.stats = stats; a.p_chunk = 0;
+    a.bias = bias; a.out = y_ptr; a.stats = stats; a.p_chunk = 0; a.hdec = hdec;
     rc = conv_tc_fwd(a, DLIO_PROF_CONV_FWD_TC, (cudaStream_t)stream);
     if (rc < 0) return rc;
     DLIO_CHECK_ARG(rc == 1, "conv2d_fwd_f16: shape not supported (cin %d %% 64, cout %d %% 16, input pads %d,%d >= %d,%d)",
@@ -164,7 +172,7 @@ extern "C" int dlio_conv2d_bwd_weight_f16(dlio_tensor4 x, const void *x_h2, cons
     a.bias = nullptr; a.out = dw; a.stats = nullptr; a.p_chunk = 0;
     rc = conv_tc_wgrad(a, (cudaStream_t)stream);
     if (rc < 0) return rc;
-    DLIO_CHECK_ARG(rc == 1, "conv2d_bwd_weight_f16: shape not supported (cin %d %% 64, cout %d %% 128, shared padded grid)",
+    DLIO_CHECK_ARG(rc == 1, "conv2d_bwd_weight_f16: shape not supported (cin %d %% 64, cout %d %% 64, shared padded grid)",
                    x.c, dy.c);
     return DLIO_OK;
 }

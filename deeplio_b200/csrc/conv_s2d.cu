@@ -69,9 +69,109 @@ __global__ void fold_stats_kernel(const double *__restrict__ in, int R, int c, d
     out[i] = s;
 }
 
+// ---------------------------------------------------------------- pixel-pair view of W-stride-2 convolutions
+// value of the pair-view weight w2[co][dy][t][p * cin + c] (zero where the source column falls outside the kernel)
+__device__ __forceinline__ float pair_weight(const float *__restrict__ w, int cin, int kh, int kw, int kw2, int co,
+                                             int dy, int t, int pc) {
+    const int p = pc >= cin ? 1 : 0, c = pc - p * cin;
+    const int dx = 2 * (t - (kw2 - 1) / 2) + p + (kw - 1) / 2;
+    return (dx >= 0 && dx < kw) ? w[(((size_t)co * cin + c) * kh + dy) * kw + dx] : 0.f;
+}
+
+// packed fp16 split rows of w2 (forward / wgrad layout, or flipped + transposed for dgrad): see weight_pack_f16_kernel
+__global__ void __launch_bounds__(256) weight_pack_pair_f16_kernel(const float *__restrict__ w, int cout, int cin,
+                                                                   int kh, int kw, int kw2, int flip,
+                                                                   const float *bound, __half *__restrict__ out) {
+    const int taps = kh * kw2, c2 = 2 * cin;
+    const long long total = (long long)cout * taps * c2;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float s = f16_scale_from_bound(*bound);
+    int row, col, co, pc, tap;
+    long long K;
+    if (!flip) {
+        pc = (int)(i % c2);
+        long long t = i / c2;
+        tap = (int)(t % taps);
+        co = (int)(t / taps);
+        row = co; col = tap * c2 + pc; K = (long long)taps * c2;
+    } else {
+        co = (int)(i % cout);
+        long long t = i / cout;
+        const int tapf = (int)(t % taps);
+        pc = (int)(t / taps);
+        tap = taps - 1 - tapf;
+        row = pc; col = tapf * cout + co; K = (long long)taps * cout;
+    }
+    const float v = pair_weight(w, cin, kh, kw, kw2, co, tap / kw2, tap % kw2, pc);
+    __half h, l;
+    f16_split(v * s, h, l);
+    out[(size_t)row * 2 * K + col] = h;
+    out[(size_t)row * 2 * K + K + col] = l;
+}
+
+// dw[co][c][dy][dx] (OIHW) = dw2[co][dy][t][p * cin + c] for the one (t, p) that maps to dx
+__global__ void weight_grad_from_pair_kernel(const float *__restrict__ dw2, int cout, int cin, int kh, int kw, int kw2,
+                                             float *__restrict__ dw) {
+    const long long total = (long long)cout * cin * kh * kw;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dx = (int)(i % kw);
+    long long t1 = i / kw;
+    const int dy = (int)(t1 % kh);
+    t1 /= kh;
+    const int c = (int)(t1 % cin);
+    const int co = (int)(t1 / cin);
+    const int off = dx - (kw - 1) / 2;           // = 2 t' + p
+    const int tq = (off + 8) / 2 - 4;            // floor(off / 2)
+    const int p = off - 2 * tq, t = tq + (kw2 - 1) / 2;
+    dw[i] = dw2[((((size_t)co * kh + dy) * kw2 + t) * 2 + p) * cin + c];
+}
+
+__global__ void __launch_bounds__(256) absmax_plain_kernel(const float *__restrict__ x, long long n, float *bound) {
+    float m = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomic_max_nonneg(bound, m);
+}
+
 }  // namespace dlio
 
 using namespace dlio;
+
+extern "C" int dlio_weight_pack_pair_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int transpose_flip,
+                                         int compute_bound, float *w_bound, void *w_h2, void *stream) {
+    DLIO_CHECK_ARG(w_oihw && w_bound && w_h2 && cout > 0 && cin > 0 && kh > 0 && (kw == 1 || kw == 3 || kw == 5),
+                   "weight_pack_pair_f16: bad argument (kw must be 1, 3 or 5)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, st);
+    const long long n = (long long)cout * cin * kh * kw;
+    if (compute_bound) {
+        DLIO_CUDA(cudaMemsetAsync(w_bound, 0, sizeof(float), st));
+        int grid = ceil_div(n, 256 * 8);
+        absmax_plain_kernel<<<grid > 592 ? 592 : grid, 256, 0, st>>>(w_oihw, n, w_bound);
+        DLIO_LAUNCH_CHECK();
+    }
+    const int kw2 = kw > 1 ? 3 : 1;
+    const long long total = (long long)cout * kh * kw2 * 2 * cin;
+    weight_pack_pair_f16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w_oihw, cout, cin, kh, kw, kw2, transpose_flip,
+                                                                     w_bound, (__half *)w_h2);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_weight_grad_from_pair(const float *dw2, int cout, int cin, int kh, int kw, float *dw_oihw,
+                                          void *stream) {
+    DLIO_CHECK_ARG(dw2 && dw_oihw && cout > 0 && cin > 0 && kh > 0 && (kw == 1 || kw == 3 || kw == 5),
+                   "weight_grad_from_pair: bad argument (kw must be 1, 3 or 5)");
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
+    const long long total = (long long)cout * cin * kh * kw;
+    weight_grad_from_pair_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(dw2, cout, cin, kh, kw,
+                                                                                        kw > 1 ? 3 : 1, dw_oihw);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
 
 extern "C" int dlio_weight_to_s2d(const float *w_oihw, int cout, int cin, int kh, int kw, int sw, float *w4_hi,
                                   float *w4_lo, void *stream) {

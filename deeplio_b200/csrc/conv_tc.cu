@@ -50,6 +50,7 @@ struct TcArgs {
     double *stats;
     long long rows;    // R = n * hp * wp
     int f16;           // 0: 3xTF32 on fp32 planes; 1: 3xF16 on packed half planes (K chunk = 64 halves)
+    int hdec;          // 2: H-stride-2 convolution computed over the whole grid, only even rows are stored / counted
     const float *xb, *wb;   // f16: device bounds of the two operands (-> power-of-two scales)
 };
 
@@ -346,6 +347,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 int n = (int)(t / a.x.hp);
                 int h = yy - a.x.ph, w = xx - a.x.pw;
                 valid = h >= 0 && h < a.x.h && w >= 0 && w < a.x.w;
+                if (a.hdec == 2) {
+                    valid = valid && !(h & 1);
+                    h >>= 1;
+                }
                 if (valid) obase = a.o.off(n, h, w) + n0 + cb;
             }
             if (a.stats && active && red_n0 != n0) {
@@ -521,6 +526,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     const bool f16 = a.x_h2 != nullptr;
     if (f16 ? !(a.w_h2 && a.x_bound && a.w_bound) : !(a.x_lo && a.w_lo)) return 0;
     if (a.sh != 1 || a.sw != 1) return 0;
+    if (a.hdec != 1 && a.hdec != 2) return 0;
     if (a.cin % (f16 ? TC_BK16 : TC_BK) != 0 || a.cout % 16 != 0) return 0;
     if (a.x.ph < a.ph || a.x.pw < a.pw) return 0;
     if (a.kh != 2 * a.ph + 1 || a.kw != 2 * a.pw + 1) return 0;   // "same" convolution: output extent == input extent
@@ -533,6 +539,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
 
     TcArgs t;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.wb = a.w_bound;
+    t.hdec = a.hdec;
     t.x = a.x; t.o = a.o;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw;
     t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.act = a.act;
@@ -750,6 +757,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     } else {
         const int quad = warp & 3;
         const int co = co0 + quad * 32 + lane;
+        const bool co_ok = co < a.cout;      // Cout % 128 == 64: the upper half of the last tile is TMA zero fill
         const int taps = a.kh * a.kw;
         // swap: TMEM lane = (tap quad, ci lane), column = output channel
         float *orow = swap ? a.dw + ((size_t)co0 * taps + (tap + quad)) * a.cin + lane
@@ -785,7 +793,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                if (j < ncol)
+                if (j < ncol && co_ok)
                     atomicAdd(reinterpret_cast<float4 *>(orow + c0 + j),
                               make_float4(fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv,
                                           fmaf(__uint_as_float(u[j + 1]), corr, __uint_as_float(v[j + 1])) * inv,
@@ -808,7 +816,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     if (a.sh != 1 || a.sw != 1) return 0;
     if (a.kh != 2 * a.ph + 1 || a.kw != 2 * a.pw + 1) return 0;
     const int krows = f16 ? 64 : 32, bc = f16 ? 64 : 32;
-    if (a.cout % TC_BM != 0 || a.cin % bc != 0) return 0;
+    if (a.cout % bc != 0 || a.cin % bc != 0) return 0;
     // x and dy must share one padded grid, with pads covering the kernel reach
     if (a.x.n != a.y.n || a.x.h != a.y.h || a.x.w != a.y.w || a.x.ph != a.y.ph || a.x.pw != a.y.pw) return 0;
     if (a.x.ph < a.ph || a.x.pw < a.pw) return 0;
@@ -816,7 +824,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     for (int c : {128, 64, 32})
         if (a.cin % c == 0 && c % bc == 0) { bn = c; break; }
     if (!bn) return 0;
-    const bool swap = !f16 && a.cin == 32;       // see the kernel: four taps' x tiles as A, dy as B
+    const bool swap = !f16 && a.cin == 32 && a.cout % TC_BM == 0;   // see the kernel: four taps' x tiles as A, dy as B
     if (swap) bn = TC_BM;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
     if (rows >= (1LL << 31) - 4096) return 0;
@@ -824,7 +832,8 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
           (uintptr_t)a.x_h2 | (uintptr_t)a.w_h2) & 15) != 0) return 0;
 
     const int taps = a.kh * a.kw;
-    const int tiles = swap ? ((taps + 3) / 4) * (a.cout / TC_BM) : taps * (a.cin / bn) * (a.cout / TC_BM);
+    const int mblocks = (a.cout + TC_BM - 1) / TC_BM;
+    const int tiles = swap ? ((taps + 3) / 4) * mblocks : taps * (a.cin / bn) * mblocks;
     // K splits: one CTA per SM (192 KB of smem), so the grid should fill whole waves of 148 CTAs -- a grid of
     // 450 CTAs (3.04 waves) ran at 76 % of a 444-CTA one.  Pick the split count whose total is closest below a
     // multiple of 148 among 2..4 waves, keeping at least 64 K chunks per CTA.
@@ -867,7 +876,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
-    dim3 grid((unsigned)(swap ? (taps + 3) / 4 : taps * (a.cin / bn)), (unsigned)splits, (unsigned)(a.cout / TC_BM));
+    dim3 grid((unsigned)(swap ? (taps + 3) / 4 : taps * (a.cin / bn)), (unsigned)splits, (unsigned)mblocks);
     if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     else if (swap) wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mdh, mdl, t);   // x as A, dy as B
     else wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);

@@ -154,12 +154,13 @@ struct BnPool {
     float *out_hi, *out_lo;     // fp32 plane (may be NULL when only the fp16 planes are wanted), TF32 lo plane
     __half *out_h2;             // packed fp16 hi|lo planes (optional) and the bound that defines their scale
     const float *out_bound;
+    int group;                  // layout of out_h2: 1 plain, 2 pixel pairs (common.cuh, st4_h2)
     uint8_t *idx;
 };
 __device__ __forceinline__ void bnpool_store(const BnPool &a, unsigned pix, int c, const float4 &v, float s16) {
     const size_t o = (size_t)pix * a.out.c + a.c_off + c;
     if (a.out_hi) st4_split(a.out_hi, a.out_lo, o, v);
-    if (a.out_h2) st4_h2(a.out_h2, pix, a.out.c, a.c_off + c, v, s16);
+    if (a.out_h2) st4_h2(a.out_h2, pix, a.out.c, a.c_off + c, v, s16, a.group);
 }
 
 __device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, int w, int c, const float4 &sc,
@@ -537,6 +538,8 @@ struct BnApply {
     const double *sums;
     double count;
     int pre_relu, batch_stats, cg;
+    int hs;            // dy row step: y row i lies on dy row hs * i, the other dy rows are zero (H-strided convolution
+                       // whose backward runs as a stride-1 convolution over the input grid)
     float *dy_hi, *dy_lo, *dgamma, *dbeta;
     double *dbias;
     __half *dy_h2;     // packed fp16 hi|lo planes of dy (optional); needs sums[2C] = max |dz|
@@ -600,12 +603,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
         int n = (int)(t / (unsigned)a.dy.hp);
         int h = yy - a.dy.ph, w = xx - a.dy.pw;
         size_t o = (size_t)pix * C + c;
-        if (h < 0 || h >= a.dy.h || w < 0 || w >= a.dy.w) {
+        if (h < 0 || h >= a.dy.h || w < 0 || w >= a.dy.w || (a.hs == 2 && (h & 1))) {
             if (a.dy_hi) st4(a.dy_hi + o, f4(0.f));
             if (a.dy_lo) st4(a.dy_lo + o, f4(0.f));
             if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, C, c);
             continue;
         }
+        if (a.hs == 2) h >>= 1;
         float4 y = ld4(a.yp + a.y.off(n, h, w) + c);
         float4 dz = ld4(a.dz + (((size_t)n * a.y.h + h) * a.y.w + w) * C + c);
         float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
@@ -828,6 +832,8 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     a.c_off = p.c_off; a.cg = y.c / 4;
     a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx;
     a.out_h2 = (__half *)out_h2; a.out_bound = out_bound;
+    a.group = p.out_group == 2 ? 2 : 1;
+    DLIO_CHECK_ARG(a.group == 1 || (out_h2 && a.out.wp % 2 == 0), "bn_act_pool_fwd: the pixel-pair layout needs fp16 planes and an even padded width");
     long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
     const int block = block_for_cg(a.cg);
     cudaStream_t st = (cudaStream_t)stream;
@@ -925,7 +931,11 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
     DLIO_CHECK_ARG(!dy_h2 || (dy_bound && sums && (((uintptr_t)dy_h2) & 15) == 0), "bn_bwd_apply: fp16 planes need sums[2C] and dy_bound");
     DLIO_CHECK_ARG(!dy_h2 || y.c % 32 == 0, "bn_bwd_apply: fp16 planes need c %% 32 == 0 (whole warps in the bound reduction)");
     DLIO_CHECK_ARG(dy_hi || !dy_lo, "bn_bwd_apply: dy_lo without dy_hi");
-    DLIO_CHECK_ARG(dy_t.n == y.n && dy_t.h == y.h && dy_t.w == y.w && dy_t.c == y.c, "bn_bwd_apply: dy geometry");
+    // dy_t.h == y.h: dy on y's own grid.  dy_t.h == input height of an H-stride-2 convolution: y row i goes to dy row
+    // 2 i and the odd rows are zero (the backward of that convolution runs as a stride-1 one over the input grid)
+    const int hs = dy_t.h == y.h ? 1 : 2;
+    DLIO_CHECK_ARG(dy_t.n == y.n && (hs == 1 || (dy_t.h - 1) / 2 + 1 == y.h) && dy_t.w == y.w && dy_t.c == y.c,
+                   "bn_bwd_apply: dy geometry");
     int rc = check_cg(y.c, "bn_bwd_apply");
     if (rc) return rc;
     BnApply a;
@@ -933,7 +943,7 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
     a.yp = y_ptr; a.dz = dz; a.scale = scale; a.mean = mean; a.invstd = invstd; a.sums = sums;
     a.count = (double)count; a.pre_relu = pre_relu; a.batch_stats = batch_stats; a.cg = y.c / 4;
     a.dy_hi = dy_hi; a.dy_lo = dy_lo; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias_sums;
-    a.dy_h2 = (__half *)dy_h2; a.dy_bound = dy_bound;
+    a.dy_h2 = (__half *)dy_h2; a.dy_bound = dy_bound; a.hs = hs;
     int block = block_for_cg(a.cg);
     long long total = (long long)a.dy.n * a.dy.hp * a.dy.wp * a.cg;
     bn_bwd_apply_kernel<<<grid_for(total, block, 8), block, 0, (cudaStream_t)stream>>>(a);

@@ -38,6 +38,16 @@ def f16_ok(cin, cout, stride):
     return USE_TC and USE_F16 and tuple(stride) == (1, 1) and cin % 64 == 0 and cout % 16 == 0
 
 
+def pair_ok(x, cin, cout, kh, kw, stride):
+    """W-stride-2 convolution on the tensor cores through the pixel-pair view (csrc/conv_s2d.cu): the input's fp16
+    planes must be in the pixel-pair layout (producer called with ``out_group=2``); H stride 2 is computed over the
+    whole grid and decimated by the epilogue."""
+    sh, sw = stride
+    return (USE_TC and USE_F16 and sw == 2 and sh in (1, 2) and kw in (1, 3, 5) and x.h2 is not None and x.group == 2
+            and x.c == cin and cin % 32 == 0 and cout % 64 == 0 and x.w % 2 == 0 and x.pw % 2 == 0
+            and x.pw // 2 >= (1 if kw > 1 else 0) and x.ph >= (kh - 1) // 2 and (sh == 1 or x.h > 1))
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -58,7 +68,7 @@ class Act:
     ``t`` fp32 (what every non-tensor-core consumer reads), ``lo`` the low-order TF32 plane x - trunc_tf32(x) that
     goes with ``t`` on the 3xTF32 path, ``h2`` the packed fp16 hi|lo planes [n][hp][wp][2][c] of the 3xF16 path.
     ``bound`` (device float[1]) >= max |x|: defines the scale of ``h2`` and feeds the bound of a residual sum."""
-    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "lo", "h2", "bound", "needs_grad")
+    __slots__ = ("n", "h", "w", "c", "ph", "pw", "t", "lo", "h2", "bound", "needs_grad", "group")
 
     def __init__(self, n, h, w, c, ph=0, pw=0, device=None, t=None, needs_grad=True, split=False, lo=None,
                  f32=True, f16=False):
@@ -69,6 +79,7 @@ class Act:
         self.h2 = torch.empty(shape[:3] + (2, c), device=device, dtype=torch.float16) if f16 else None
         self.bound = None
         self.needs_grad = needs_grad
+        self.group = 1            # layout of h2: 1 plain, 2 pixel pairs (input of a W-stride-2 tensor-core convolution)
 
     @property
     def t4(self):
@@ -153,12 +164,14 @@ def pack_input(run, view, c_pad, ph, pw):
 
 def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
             res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0,
-            out_f32=True):
+            out_f32=True, out_group=1):
     """conv(+bias)(+ReLU if pre_relu) -> BatchNorm (batch statistics when run.training) -> (+res)(ReLU)(+res)
     -> optional 3x3 max-pool, or -> global average into ``feat`` [N, feat_ld] at column feat_off.
 
     ``out_f32=False``: the caller guarantees that the output is consumed only by fp16 tensor-core convolutions
-    (forward, dgrad and wgrad), so no fp32 copy of it is written.  Returns the output Act (None when ``feat``)."""
+    (forward, dgrad and wgrad), so no fp32 copy of it is written.  ``out_group=2``: the output feeds W-stride-2
+    convolutions only; its fp16 planes are written in the pixel-pair layout (needs an even padded width, else
+    ignored).  Returns the output Act (None when ``feat``)."""
     p, st = run.params, stream()
     w = p[cname + ".weight"]
     b = p.get(cname + ".bias")
@@ -173,12 +186,13 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     cv = L.Conv(kh, kw, sh, sw, cph, cpw)
     n = x.n
     pads_ok = x.ph >= cph and x.pw >= cpw
-    fwd_f16 = x.h2 is not None and f16_ok(cin_pad, cout, stride) and pads_ok
+    pair = pair_ok(x, cin, cout, kh, kw, stride)
+    fwd_f16 = x.h2 is not None and x.group == 1 and f16_ok(cin_pad, cout, stride) and pads_ok
     fwd_tc = (not fwd_f16) and x.lo is not None and tc_ok(cin_pad, cout, stride) and pads_ok
     # first layer (8-channel input): stride-1 kh x 3 convolution over the space-to-depth views (csrc/conv_s2d.cu)
     s2d = (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7 and x.w % 4 == 0
            and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0 and not x.needs_grad)
-    assert fwd_f16 or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
+    assert fwd_f16 or pair or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
     y = Act(n, ho, wo, cout, device=run.device)
     # the batch statistics also bound the BN output (-> scale of the fp16 planes), so they are taken in eval mode too
     stats = run.zeros(2 * cout, dtype=torch.float64)
@@ -196,6 +210,16 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         L.conv2d_fwd(x4_t4, ptr(x.t), ptr(x.lo), ptr(w4), ptr(w4_lo), ptr(bias4), cv4, act, y4_t4, ptr(y.t),
                      ptr(stats4), st)
         L.fold_stats(ptr(stats4), R, cout, ptr(stats), st)
+    elif pair:
+        # [n, h, w/2, 2 cin] view of the same memory, stride-1 kh x kw2 convolution, even rows kept when sh == 2
+        kw2 = 3 if kw > 1 else 1
+        x2_t4 = L.Tensor4(n, x.h, x.w // 2, 2 * cin, x.ph, x.pw // 2)
+        cv2 = L.Conv(kh, kw2, 1, 1, cph, (kw2 - 1) // 2)
+        w_bound = run.empty(1)
+        w_h2 = run.empty(cout, 2, kh * kw2 * 2 * cin, dtype=torch.float16)
+        L.weight_pack_pair_f16(ptr(w), cout, cin, kh, kw, 0, 1, ptr(w_bound), ptr(w_h2), st)
+        L.conv2d_fwd_f16(x2_t4, ptr(x.h2), ptr(x.bound), ptr(w_h2), ptr(w_bound), ptr(b),
+                         L.Conv(kh, kw2, sh, 1, cph, (kw2 - 1) // 2), act, y.t4, ptr(y.t), ptr(stats), st)
     elif fwd_f16:
         w_bound = run.empty(1)
         w_h2 = run.empty(cout, 2, kh * kw * cin_pad, dtype=torch.float16)
@@ -223,7 +247,7 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         if nbt is not None:
             nbt.add_(1)
     bp = L.BnPool(1 if relu else 0, res_mode if res is not None else 0, 3 if pool else 1,
-                  pool[0] if pool else 1, pool[1] if pool else 1, c_off)
+                  pool[0] if pool else 1, pool[1] if pool else 1, c_off, 1)
     idx = None
     dummy = y.t4
     if feat is not None:
@@ -239,6 +263,8 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, f32=out_f32, f16=o16,
                       split=USE_TC and out_f32 and not o16 and oc % 32 == 0)
             out.bound = out_bound
+            if out_group == 2 and o16 and (ow + 2 * out_pad[1]) % 2 == 0:
+                out.group = bp.out_group = 2
         assert out.h == oh and out.w == ow and out.n == n
         if pool and run.record:
             idx = run.empty(n, oh, ow, cout, dtype=torch.uint8)
@@ -262,8 +288,10 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         # which kernels consume dy: 3xF16 / 3xTF32 tensor-core kernels or the fp32 CUDA-core ones
         if s2d:
             wg, dg = "tf32", None
+        elif pair:
+            wg, dg = "f16", ("f16" if x.needs_grad else None)
         else:
-            wg = "f16" if (fwd_f16 and cout % 128 == 0) else ("tf32" if (fwd_tc and cout % 128 == 0) else "simt")
+            wg = "f16" if (fwd_f16 and cout % 64 == 0) else ("tf32" if (fwd_tc and cout % 32 == 0) else "simt")
             dg = None
             if x.needs_grad:
                 dg = ("f16" if (f16_ok(cout, cin_pad, stride)) else ("tf32" if tc_ok(cout, cin_pad, stride) else "simt"))
@@ -286,8 +314,12 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dpad = (x.ph, x.pw) if on_x_grid else ((kh - 1 - cph, kw - 1 - cpw) if dg in ("f16", "tf32") else (0, 0))
         if s2d:
             dpad = (x.ph, 4 // sw)    # x's padded grid expressed in output pixels
-        dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
-                  split="tf32" in modes, f16="f16" in modes)
+        if pair:
+            # dy on the padded grid of the pixel-pair view; with sh == 2 its rows are spread over the even input rows
+            dya = Act(n, x.h, wo, cout, x.ph, x.pw // 2, device=run.device, f32=False, f16=True)
+        else:
+            dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
+                      split="tf32" in modes, f16="f16" in modes)
         dya.bound = run.empty(1) if dya.h2 is not None else None
         dgamma, dbeta = run.param_grad(bname + ".weight", gamma), run.param_grad(bname + ".bias", beta)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
@@ -302,6 +334,19 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         if b is not None:
             L.f64_to_f32(ptr(dbs), ptr(run.param_grad(cname + ".bias", b)), cout, st)
         dw = run.param_grad(cname + ".weight", w)
+        if pair:
+            cv2s1 = L.Conv(kh, kw2, 1, 1, cph, (kw2 - 1) // 2)
+            dw2 = run.empty(cout, kh, kw2, 2 * cin)
+            L.conv2d_bwd_weight_f16(x2_t4, ptr(x.h2), ptr(x.bound), dya.t4, ptr(dya.h2), ptr(dya.bound), cv2s1,
+                                    ptr(dw2), st)
+            L.weight_grad_from_pair(ptr(dw2), cout, cin, kh, kw, ptr(dw), st)
+            if dg == "f16":
+                wt_h2 = run.empty(2 * cin, 2, kh * kw2 * cout, dtype=torch.float16)
+                L.weight_pack_pair_f16(ptr(w), cout, cin, kh, kw, 1, 0, ptr(w_bound), ptr(wt_h2), st)
+                run.add_grad(x, lambda buf: L.conv2d_bwd_data_f16(
+                    dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2), ptr(w_bound), cv2s1,
+                    L.Tensor4(n, x.h, x.w // 2, 2 * cin, 0, 0), ptr(buf), st))
+            return
         if s2d:
             dw4 = run.empty(R * cout, kh, 3, 32)
             L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dya.t),

@@ -92,9 +92,13 @@ class FlowNetEncoder(_Encoder):
             if last:
                 E.conv_bn(run, t, name + ".0", name + ".1", stride, feat=feat, feat_ld=ld, feat_off=off)
             else:
-                nk = self.SPEC[i + 1][2]
+                nk, nstride = self.SPEC[i + 1][2], self.SPEC[i + 1][3]
                 nkh, nkw = (nk, nk) if isinstance(nk, int) else nk
-                t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, (nkw - 1) // 2))
+                if nstride[1] == 2:
+                    # the next layer is W-strided: pixel-pair layout, even row pads (engine.pair_ok)
+                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, 2), out_group=2)
+                else:
+                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, (nkw - 1) // 2))
 
 
 class ResNetEncoder(_Encoder):
@@ -129,8 +133,10 @@ class ResNetEncoder(_Encoder):
                 nn.init.constant_(m.bias, 0)
 
     def program(self, run, x, feat, ld, off):
-        t = E.conv_bn(run, x, "conv1", "bn1", (1, 1), pool=(1, 2), ceil=False, out_pad=(1, 1))
-        for lname, nblk, _, stride in self.LAYERS:
+        # the first block of every layer is W-strided (conv1 and the 1x1 downsample): its input is produced in the
+        # pixel-pair layout with even row pads (engine.pair_ok)
+        t = E.conv_bn(run, x, "conv1", "bn1", (1, 1), pool=(1, 2), ceil=False, out_pad=(1, 2), out_group=2)
+        for li, (lname, nblk, _, stride) in enumerate(self.LAYERS):
             for b in range(nblk):
                 q = "%s.%d." % (lname, b)
                 s = stride if b == 0 else (1, 1)
@@ -138,7 +144,9 @@ class ResNetEncoder(_Encoder):
                 idn = t
                 if b == 0:
                     idn = E.conv_bn(run, t, q + "downsample.0", q + "downsample.1", s, relu=False)
-                t = E.conv_bn(run, o, q + "conv2", q + "bn2", (1, 1), relu=True, res=idn, res_mode=1, out_pad=(1, 1))
+                to_strided = b == nblk - 1 and li + 1 < len(self.LAYERS)
+                t = E.conv_bn(run, o, q + "conv2", q + "bn2", (1, 1), relu=True, res=idn, res_mode=1,
+                              out_pad=(1, 2) if to_strided else (1, 1), out_group=2 if to_strided else 1)
         E.global_avg(run, t, feat, ld, off)
 
 

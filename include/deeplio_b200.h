@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 2
+#define DLIO_ABI_VERSION 3
 
 typedef enum {
     DLIO_OK = 0,
@@ -145,14 +145,26 @@ int dlio_weight_flip_transpose(const float *w_ohwi, int cout, int cin, int kh, i
                                float *wt_hi, float *wt_lo, void *stream);
 
 /* fp16 tensor-core path (tcgen05 kind::f16, three products per fp32 product).  Same semantics as the three
- * calls above for stride-1 "same" convolutions with cin % 64 == 0 (wgrad also: cout % 128 == 0; dgrad: cout % 64
+ * calls above for stride-1 "same" convolutions with cin % 64 == 0 (wgrad also: cout % 64 == 0; dgrad: cout % 64
  * == 0, cin % 16 == 0), operands given as packed split planes; there is no fallback: an inapplicable problem
- * returns DLIO_ERR_INVALID.
+ * returns DLIO_ERR_INVALID.  dlio_conv2d_fwd_f16 also takes cv.sh == 2 (cv.sw == 1): the convolution is computed
+ * over the whole input grid and only the even rows are stored and counted in the statistics (y.h = (x.h + 2 ph -
+ * kh) / 2 + 1) -- with the pixel-pair view below this is how the reference's stride-(1,2) and (2,2) convolutions
+ * (FlowNet lidar_feat_nets.py:248-257, ResNet first blocks resnet.py:40-48) reach the tensor cores.
  *   dlio_weight_pack_f16: OIHW fp32 -> packed OHWI rows [cout][2][kh*kw*cin_pad] (transpose_flip == 0), or the
  *   dgrad operand [cin_pad][2][kh*kw*cout], wt[ci][kh'][kw'][co] = w[co][ci][kh-1-kh'][kw-1-kw'] (transpose_flip
  *   != 0).  compute_bound != 0: first reduces max |w| into *w_bound; otherwise *w_bound is read. */
 int dlio_weight_pack_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int cin_pad, int transpose_flip,
                          int compute_bound, float *w_bound, void *w_h2, void *stream);
+/* Pixel-pair view of a W-stride-2 convolution (kw in {1,3,5}, pad (kw-1)/2): on the SAME memory, x [n,h,w,c] with
+ * even w and even row pads is x2 [n,h,w/2,2c] (fp16 planes in the pixel-pair layout, dlio_bnpool.out_group == 2) and
+ * the layer is a stride-1 convolution with kernel kh x kw2 (kw2 = 3, or 1 for kw == 1) and weights
+ *     w2[co][dy][t][p*c + ci] = w[co][ci][dy][2 (t - (kw2-1)/2) + p + (kw-1)/2]   (zero where that column is outside)
+ * dlio_weight_pack_pair_f16 packs w2 as dlio_weight_pack_f16 packs w (rows [cout][2][kh*kw2*2cin], or the dgrad
+ * operand [2cin][2][kh*kw2*cout]); dlio_weight_grad_from_pair folds dw2 [cout][kh][kw2][2cin] back to OIHW. */
+int dlio_weight_pack_pair_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int transpose_flip,
+                              int compute_bound, float *w_bound, void *w_h2, void *stream);
+int dlio_weight_grad_from_pair(const float *dw2, int cout, int cin, int kh, int kw, float *dw_oihw, void *stream);
 int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, const void *w_h2,
                         const float *w_bound, const float *bias, dlio_conv cv, int act, dlio_tensor4 y,
                         float *y_ptr, double *stats, void *stream);
@@ -188,6 +200,9 @@ typedef struct {
     int pool_k;     /* 1 = no pooling, 3 = 3x3 max pool (pad 1; the output extent carries ceil_mode) */
     int pool_sh, pool_sw;
     int c_off;      /* channel offset inside the output (and residual) tensor (Fire concat) */
+    int out_group;  /* layout of out_h2: 0 / 1 plain rows [C hi | C lo] per pixel; 2 pixel pairs
+                       [p0 C hi | p1 C hi | p0 C lo | p1 C lo] -- the operand layout of a W-stride-2 convolution run
+                       through the pixel-pair view [n, h, w/2, 2C] (dlio_weight_pack_pair_f16); needs an even padded width */
 } dlio_bnpool;
 
 /* out[n,ho,wo,c_off+c] = maxpool(act(scale[c]*y + shift[c] (+res)) (+res)); writes out's pads as zeros for
@@ -222,7 +237,9 @@ int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float 
  * (geometry dy_t, zero pads, optional TF32 split), dgamma[c], dbeta[c] and accumulates
  * dbias_sums[c] += sum dy (fp64, caller zeroes; may be NULL).  dy_h2 / dy_bound (optional; needs sums[2c] =
  * max |dz|): dy as packed fp16 split planes, and the bound it was scaled from (OUTPUT, for dgrad / wgrad);
- * dy_hi may then be NULL. */
+ * dy_hi may then be NULL.  dy_t.h == y.h: dy on y's own grid.  dy_t.h == the input height of an H-stride-2
+ * convolution ((dy_t.h - 1) / 2 + 1 == y.h): y row i is written to dy row 2 i and the odd rows are zero, which is
+ * the dy operand of that convolution's backward run as a stride-1 convolution over its input grid. */
 int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
                       long long count, const float *scale, const float *mean, const float *invstd,
                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
