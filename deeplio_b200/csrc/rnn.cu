@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) rnn_step_bwd_kernel(BwdArgs a) {
 // halves of h_t through the layer output in global memory (which has to be written anyway): cluster barrier with
 // release / acquire, then an L1-bypassing reload of h_t.  60 step launches per IMU window become 4.
 constexpr int SEQ_WARPS = 16;
-constexpr int SEQ_CLUSTER = 2;
+constexpr int SEQ_CLUSTER = 4;     // CTAs per (direction, batch chunk): each owns H / 4 hidden units
 
 __device__ __forceinline__ float warp_colsum32_rnn(float (&v)[32], int lane) {
 #pragma unroll
@@ -281,7 +281,10 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
         const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
         creg[q] = (KIND == 0 && it < RB * HU && bl < nb && s.c0) ? s.c0[(size_t)(b0 + bl) * H + j0 + u] : 0.f;
     }
-    const uint32_t peer_hs = peer_smem(hs, rank ^ 1u);
+    uint32_t peer_hs[SEQ_CLUSTER - 1];         // the other CTAs' h buffers
+#pragma unroll
+    for (int p = 0; p < SEQ_CLUSTER - 1; ++p) peer_hs[p] = peer_smem(hs, (rank + 1u + p) % SEQ_CLUSTER);
+    const int nrow = (R + SEQ_ROWT - 1) / SEQ_ROWT;         // W_hh rows per row thread actually in use (uniform)
     const int kg = threadIdx.x / SEQ_ROWT, rp = threadIdx.x % SEQ_ROWT;
     const int kper = (H + 3) / 4, k_begin = kg * kper, k_end = min(H, k_begin + kper);
     bool rowok[SEQ_MAXR];
@@ -319,9 +322,11 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                 const float hv[RB] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
                 for (int m = 0; m < SEQ_MAXR; ++m) {
-                    const float w = rowok[m] ? wr[m * SEQ_ROWT] : 0.f;      // select, not a branch
+                    if (m < nrow) {                                         // uniform over the CTA
+                        const float w = rowok[m] ? wr[m * SEQ_ROWT] : 0.f;  // select, not a branch
 #pragma unroll
-                    for (int b = 0; b < RB; ++b) acc[m][b] = fmaf(w, hv[b], acc[m][b]);
+                        for (int b = 0; b < RB; ++b) acc[m][b] = fmaf(w, hv[b], acc[m][b]);
+                    }
                 }
             }
 #pragma unroll
@@ -375,7 +380,9 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
             s.y[((size_t)b * T + t) * a.DH + j] = h;
             if (step == T - 1 && s.hn) s.hn[(size_t)b * H + j] = h;
             hnext[j * RB + bl] = h;
-            st_peer(peer_hs + (uint32_t)(((cur ^ 1) * H * RB + j * RB + bl) * sizeof(float)), h);
+#pragma unroll
+            for (int p = 0; p < SEQ_CLUSTER - 1; ++p)
+                st_peer(peer_hs[p] + (uint32_t)(((cur ^ 1) * H * RB + j * RB + bl) * sizeof(float)), h);
         }
         cluster_barrier();      // h_t complete in both CTAs; everybody is done reading h_{t-1} and the partial sums
         cur ^= 1;
@@ -415,7 +422,7 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
     float *dh = dg + RB * GU;                // [RB][HU]
     float *dc = dh + RB * HU;                // [RB][HU]
     float *part = dc + RB * HU;              // [ngroups][RB][H] partial products of the row groups
-    float *xin = part + ngroups * RB * H;    // [2][RB][HU] contributions received from the peer (by step parity)
+    float *xin = part + ngroups * RB * H;    // [2][SEQ_CLUSTER - 1][RB][HU] contributions received from the peers (by step parity)
     for (int i0 = threadIdx.x; i0 < GU * H; i0 += 8 * blockDim.x) {      // 8 independent loads in flight
         float v[8];
 #pragma unroll
@@ -435,7 +442,12 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
         dh[i] = b < nb ? s.dh_rec[(size_t)(b0 + b) * H + j0 + u] : 0.f;
         dc[i] = (KIND == 0 && b < nb) ? s.dc_rec[(size_t)(b0 + b) * H + j0 + u] : 0.f;
     }
-    const uint32_t peer_xin = peer_smem(xin, rank ^ 1u);
+    // CTA `owner` receives the contribution of sender `rank` in slot (rank - owner - 1) mod CLUSTER of its xin
+    uint32_t peer_xin[SEQ_CLUSTER];
+#pragma unroll
+    for (int o = 0; o < SEQ_CLUSTER; ++o)
+        peer_xin[o] = peer_smem(xin, (uint32_t)o) +
+                      (uint32_t)((((int)rank - o - 1 + SEQ_CLUSTER) % SEQ_CLUSTER) * RB * HU * sizeof(float));
     cluster_barrier();
     const int kq = threadIdx.x % H, rg = threadIdx.x / H;
     for (int step = T - 1; step >= 0; --step) {
@@ -505,10 +517,15 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
             for (int q = 0; q < ngroups; ++q) v += part[(q * RB + bl) * H + k];
             const int owner = k / HU, u = k - owner * HU;
             if (owner == (int)rank) dh[bl * HU + u] += v;
-            else st_peer(peer_xin + (uint32_t)((par * RB * HU + bl * HU + u) * sizeof(float)), v);
+            else st_peer(peer_xin[owner] + (uint32_t)((par * (SEQ_CLUSTER - 1) * RB * HU + bl * HU + u) * sizeof(float)), v);
         }
         cluster_barrier();
-        for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) dh[i] += xin[par * RB * HU + i];
+        for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
+            float v = 0.f;
+#pragma unroll
+            for (int p = 0; p < SEQ_CLUSTER - 1; ++p) v += xin[(par * (SEQ_CLUSTER - 1) + p) * RB * HU + i];
+            dh[i] += v;
+        }
         __syncthreads();
     }
     for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
@@ -550,16 +567,17 @@ struct RnnLayout {
 // whole-sequence kernels: the W_hh rows of half the hidden units must fit in one CTA's shared memory (H <= 152 for
 // an LSTM, 176 for a GRU), and a single step is not worth a cluster launch
 static size_t seq_fwd_smem(int kind, int H) {
-    const size_t G = kind == 0 ? 4 : 3, R = G * (H / 2);
+    const size_t G = kind == 0 ? 4 : 3, R = G * (H / SEQ_CLUSTER);
     return ((((size_t)H * (R + 1) + 3) & ~(size_t)3) + 2 * (size_t)RB * H + 4 * RB * R + R) * sizeof(float);
 }
 static size_t seq_bwd_smem(int kind, int H) {
-    const size_t G = kind == 0 ? 4 : 3, HU = H / 2, threads = SEQ_WARPS * 32;
-    return (G * HU * H + RB * G * HU + 2 * RB * HU + (threads / H) * RB * H + 2 * RB * HU) * sizeof(float);
+    const size_t G = kind == 0 ? 4 : 3, HU = H / SEQ_CLUSTER, threads = SEQ_WARPS * 32;
+    return (G * HU * H + RB * G * HU + 2 * RB * HU + (threads / H) * RB * H + 2 * (SEQ_CLUSTER - 1) * RB * HU) * sizeof(float);
 }
 static bool use_seq_kernels(int kind, int H, int T) {
-    return H % 2 == 0 && H >= 16 && H <= SEQ_WARPS * 32 && (size_t)RB * (H / 2) <= (size_t)SEQ_ITEMS * SEQ_WARPS * 32 && T >= 2 &&
-           (kind == 0 ? 4 : 3) * (H / 2) <= SEQ_ROWT * SEQ_MAXR &&
+    return H % SEQ_CLUSTER == 0 && H >= 16 && H <= SEQ_WARPS * 32 &&
+           (size_t)RB * (H / SEQ_CLUSTER) <= (size_t)SEQ_ITEMS * SEQ_WARPS * 32 && T >= 2 &&
+           (kind == 0 ? 4 : 3) * (H / SEQ_CLUSTER) <= SEQ_ROWT * SEQ_MAXR &&
            seq_bwd_smem(kind, H) <= 200 * 1024 && seq_fwd_smem(kind, H) <= 200 * 1024;
 }
 

@@ -48,6 +48,18 @@ def pair_ok(x, cin, cout, kh, kw, stride):
             and x.pw // 2 >= (1 if kw > 1 else 0) and x.ph >= (kh - 1) // 2 and (sh == 1 or x.h > 1))
 
 
+def consumer_reads_f16_only(cin, cout, k, stride, w_out):
+    """True when a convolution (cin -> cout, kernel k, stride) that is the ONLY consumer of a tensor of width ``w_out``
+    runs its forward, dgrad and wgrad on the fp16 tensor-core kernels, so that the producer may skip the fp32 copy
+    (``conv_bn(out_f32=False)``) -- the stride-1 path or the pixel-pair view of a W-stride-2 layer."""
+    kh, kw = (k, k) if isinstance(k, int) else k
+    if not (USE_TC and USE_F16) or cout % 64 != 0:
+        return False
+    if tuple(stride) == (1, 1):
+        return cin % 64 == 0
+    return stride[1] == 2 and stride[0] in (1, 2) and kw in (1, 3, 5) and cin % 32 == 0 and w_out % 2 == 0
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 

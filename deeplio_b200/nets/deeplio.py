@@ -27,6 +27,9 @@ class DeepLIO(BaseNet):
         self.drop = None
         self.fc_pos = None
         self.fc_ori = None
+        # optional callable, invoked during backward when the gradients of everything downstream of the feature nets
+        # (fusion, odometry net, heads) are complete (deeplio_b200.parallel.OverlappedGradReducer)
+        self.on_head_grads_ready = None
 
     def initialize(self):
         last = next(n for n in (self.odom_feat_net, self.fusion_net, self.imu_feat_net, self.lidar_feat_net)
@@ -44,6 +47,9 @@ class DeepLIO(BaseNet):
             last = lidar = self.lidar_feat_net(lidar_imgs)
         if self.imu_feat_net is not None:
             last = imu = self.imu_feat_net(imu_meas)
+        feat = lidar if lidar is not None else imu
+        if self.on_head_grads_ready is not None and feat is not None and feat.requires_grad:
+            feat.register_hook(self._head_grads_hook)
         if self.fusion_net is not None:
             last = self.fusion_net([lidar, imu])
         if self.odom_feat_net is not None:
@@ -51,6 +57,11 @@ class DeepLIO(BaseNet):
         last = Fn.dropout(last, self.p, self.training)
         return (Fn.linear(last, self.fc_pos.weight, self.fc_pos.bias),
                 Fn.linear(last, self.fc_ori.weight, self.fc_ori.bias))
+
+    def _head_grads_hook(self, grad):
+        if self.on_head_grads_ready is not None:
+            self.on_head_grads_ready()
+        return None
 
     def get_feat_networks(self):
         nets = []

@@ -92,13 +92,19 @@ class FlowNetEncoder(_Encoder):
             if last:
                 E.conv_bn(run, t, name + ".0", name + ".1", stride, feat=feat, feat_ld=ld, feat_off=off)
             else:
-                nk, nstride = self.SPEC[i + 1][2], self.SPEC[i + 1][3]
+                cout, (ncout, nk, nstride) = self.SPEC[i][1], self.SPEC[i + 1][1:]
                 nkh, nkw = (nk, nk) if isinstance(nk, int) else nk
+                kw = k if isinstance(k, int) else k[1]
+                w_out = (t.w + 2 * ((kw - 1) // 2) - kw) // stride[1] + 1
+                # the next layer is the only consumer: no fp32 copy when it runs on the fp16 tensor-core kernels
+                f32 = not E.consumer_reads_f16_only(cout, ncout, nk, nstride, w_out)
                 if nstride[1] == 2:
                     # the next layer is W-strided: pixel-pair layout, even row pads (engine.pair_ok)
-                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, 2), out_group=2)
+                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, 2), out_group=2,
+                                  out_f32=f32)
                 else:
-                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, (nkw - 1) // 2))
+                    t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, (nkw - 1) // 2),
+                                  out_f32=f32)
 
 
 class ResNetEncoder(_Encoder):
@@ -140,7 +146,11 @@ class ResNetEncoder(_Encoder):
             for b in range(nblk):
                 q = "%s.%d." % (lname, b)
                 s = stride if b == 0 else (1, 1)
-                o = E.conv_bn(run, t, q + "conv1", q + "bn1", s, out_pad=(1, 1))
+                planes = run.params[q + "conv2.weight"].shape[0]
+                w_out = (t.w - 1) // s[1] + 1
+                # conv1's output feeds conv2 only (stride 1, planes -> planes)
+                o = E.conv_bn(run, t, q + "conv1", q + "bn1", s, out_pad=(1, 1),
+                              out_f32=not E.consumer_reads_f16_only(planes, planes, 3, (1, 1), w_out))
                 idn = t
                 if b == 0:
                     idn = E.conv_bn(run, t, q + "downsample.0", q + "downsample.1", s, relu=False)

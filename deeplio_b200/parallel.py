@@ -49,6 +49,55 @@ def broadcast_model(model, src=0):
         dist.broadcast(t.data, src)
 
 
+class OverlappedGradReducer:
+    """Gradient exchange overlapped with the encoders' backward pass.
+
+    The gradients of everything downstream of the feature nets -- fusion net, odometry net (35.7 M of the 45.8 M
+    parameters of the benchmark model) and the two heads -- are final when the gradient of the LiDAR feature vector
+    arrives, i.e. BEFORE the convolutional encoders (more than half of the step) run their backward.  ``DeepLIO``
+    calls ``model.on_head_grads_ready`` at that moment (a tensor hook); their slices of the flat gradient arena are
+    all-reduced asynchronously on NCCL's stream while the encoder backward runs, and ``finish()`` reduces the rest
+    (feature-net gradients) after ``backward()`` and joins.  Same sums as one all-reduce of the whole arena."""
+
+    def __init__(self, model, opt):
+        self.flat_grad = opt.flat_grad
+        late = set()
+        for name in ("fusion_net", "odom_feat_net", "fc_pos", "fc_ori"):
+            m = getattr(model, name, None)
+            if isinstance(m, torch.nn.Module):
+                late.update(id(p) for p in m.parameters())
+        self.late_ranges, self.early_ranges = [], []
+        ends = opt.offsets[1:] + [opt.numel]
+        for p, a, b in zip(opt.params, opt.offsets, ends):
+            rs = self.late_ranges if id(p) in late else self.early_ranges
+            if rs and rs[-1][1] == a:
+                rs[-1][1] = b
+            else:
+                rs.append([a, b])
+        self.work, self.fired = [], False
+        model.on_head_grads_ready = self._fire
+
+    def _fire(self):
+        if world_size() > 1 and not self.fired:
+            for a, b in self.late_ranges:
+                self.work.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
+        self.fired = True
+
+    def finish(self):
+        """Call after backward(): reduces what the hook did not, waits for everything.  Returns the 1/world factor
+        for the optimizer's ``grad_scale``."""
+        if world_size() > 1:
+            if self.fired:
+                for a, b in self.early_ranges:
+                    dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM)
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            for w in self.work:
+                w.wait()
+        self.work, self.fired = [], False
+        return 1.0 / world_size()
+
+
 def allreduce_grads(flat_grad):
     """Sum the flat gradient arena over all ranks (mean is applied by the optimizer's grad_scale)."""
     if world_size() > 1:

@@ -66,3 +66,74 @@ def test_shard_range_partitions_the_batch():
                 lo, hi = parallel.shard_range(total, r, world)
                 seen.extend(range(lo, hi))
             assert seen == list(range(total))
+
+
+class _ToyModel(torch.nn.Module):
+    """Feature net -> (hook point) -> fusion / odometry net / heads, with the attribute names DeepLIO uses."""
+
+    def __init__(self):
+        super().__init__()
+        self.lidar_feat_net = torch.nn.Linear(6, 5)
+        self.fusion_net = torch.nn.Linear(5, 5)
+        self.odom_feat_net = torch.nn.Linear(5, 4)
+        self.fc_pos = torch.nn.Linear(4, 3)
+        self.fc_ori = torch.nn.Linear(4, 3)
+        self.on_head_grads_ready = None
+
+    def forward(self, x):
+        feat = torch.tanh(self.lidar_feat_net(x))
+        if self.on_head_grads_ready is not None:
+            feat.register_hook(lambda g: self.on_head_grads_ready())
+        h = torch.tanh(self.odom_feat_net(torch.tanh(self.fusion_net(feat))))
+        return self.fc_pos(h), self.fc_ori(h)
+
+
+class _FlatOpt:
+    """The part of FlatAdam the reducer reads (FlatAdam itself needs a CUDA device): params as views of one arena."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
+        self.flat_grad = torch.zeros(total)
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    torch.manual_seed(3)
+    model = _ToyModel()
+    opt = _FlatOpt(model.parameters())
+    red = parallel.OverlappedGradReducer(model, opt)
+    n_late = sum(b - a for a, b in red.late_ranges)
+    n_early = sum(b - a for a, b in red.early_ranges)
+    torch.manual_seed(10 + rank)
+    x = torch.randn(4, 6)
+    pos, ori = model(x)
+    (pos.pow(2).sum() + ori.sum()).backward()
+    local = opt.flat_grad.clone()
+    fired = red.fired
+    scale = red.finish()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    out[rank] = (fired, n_late, n_early, opt.numel, float((opt.flat_grad - sum(gathered)).abs().max()), scale,
+                 red.fired, len(red.work))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_overlapped_gradient_reducer():
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_overlap_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        fired, n_late, n_early, numel, err, scale, fired_after, pending = out[rank]
+        assert fired, "the head-gradient hook did not fire during backward"
+        assert n_late > 0 and n_early > 0 and n_late + n_early == numel
+        assert err < 1e-6 and scale == 0.5
+        assert not fired_after and pending == 0
