@@ -338,10 +338,19 @@ def main():
     # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry the one JSON line only
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries the ONE JSON line and nothing else: libraries (NCCL prints its version banner from C, whatever
+    # NCCL_DEBUG says on some builds) get stderr as their fd 1 for the whole run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
