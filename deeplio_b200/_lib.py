@@ -72,7 +72,7 @@ _PROTOS = {
     "dlio_axpby": (I, [P, F, P, F, P, LL, P]),
     "dlio_sum_mid": (I, [P, P, LL, I, I, P]),
     "dlio_mul": (I, [P, P, P, LL, P]),
-    "dlio_dropout_mask": (I, [P, LL, F, C.c_ulonglong, P]),
+    "dlio_dropout_mask": (I, [P, LL, F, C.c_ulonglong, P, P]),
     "dlio_linear_fwd": (I, [P, I, P, P, I, I, I, I, P, I, P]),
     "dlio_linear_bwd": (I, [P, I, P, P, I, P, I, I, I, I, I, P, I, P, P, P, P]),
     "dlio_rnn_reserve_floats": (SZ, [I, I, I, I, I, I, I]),
@@ -89,7 +89,7 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 if _lib.dlio_abi_version() != ABI_VERSION:
     raise ImportError("deeplio_b200: ABI version mismatch (library %d, binding %d)" % (_lib.dlio_abi_version(), ABI_VERSION))
 

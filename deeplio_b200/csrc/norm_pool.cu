@@ -760,10 +760,14 @@ __global__ void mul_kernel(const float *__restrict__ a, const float *__restrict_
     for (; i < n; i += stride) out[i] = a[i] * b[i];
 }
 // counter-based keep mask: splitmix64(seed + i) -> uniform [0,1); mask = keep ? 1/(1-p) : 0
-__global__ void dropout_mask_kernel(float *mask, long long n, float p, unsigned long long seed) {
+// epoch (optional, device memory): added to the seed, so that a launch replayed from a CUDA graph draws a new mask
+// whenever the owner of the graph has advanced the counter
+__global__ void dropout_mask_kernel(float *mask, long long n, float p, unsigned long long seed,
+                                    const unsigned long long *__restrict__ epoch) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float keep_scale = 1.f / (1.f - p);
+    if (epoch) seed += *epoch * 0xD1B54A32D192ED03ULL;
     for (; i < n; i += stride) {
         unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -1046,10 +1050,11 @@ extern "C" int dlio_mul(const float *a, const float *b, float *out, long long n,
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
-extern "C" int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed, void *stream) {
+extern "C" int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed,
+                                 const unsigned long long *seed_epoch, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(mask && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad argument");
-    dropout_mask_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed);
+    dropout_mask_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, seed_epoch);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

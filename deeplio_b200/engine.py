@@ -117,13 +117,28 @@ class Run:
         self.pgrad = {}           # parameter name -> gradient tensor (absent: written in place into param.grad)
         self.keep = []            # keeps Acts alive so that id() stays unique
         self.param_objs = {}      # name -> nn.Parameter (in-place parameter gradients)
+        self._zblock, self._zoff = None, 0   # current block of the small-zeros arena
 
     # -- helpers
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, device=self.device, dtype=dtype)
 
+    ZBLOCK = 1 << 18
+
     def zeros(self, *shape, dtype=torch.float32):
-        return torch.zeros(shape, device=self.device, dtype=dtype)
+        """Zeroed tensor.  Small ones (the per-layer fp64 statistics / sums: ~6 per convolution) are carved out of
+        256 KB blocks zeroed with one fill each instead of one fill kernel per tensor."""
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if nbytes > 16384:
+            return torch.zeros(shape, device=self.device, dtype=dtype)
+        if self._zblock is None or self._zoff + nbytes > self.ZBLOCK:
+            self._zblock, self._zoff = torch.zeros(self.ZBLOCK, device=self.device, dtype=torch.uint8), 0
+        t = self._zblock[self._zoff:self._zoff + nbytes].view(dtype).view(shape)
+        self._zoff = (self._zoff + nbytes + 15) & ~15
+        return t
 
     def param_grad(self, name, like):
         """Tensor the backward kernels write the gradient of parameter ``name`` into: the parameter's own .grad
@@ -176,21 +191,23 @@ def pack_input(run, view, c_pad, ph, pw):
 
 def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
             res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0,
-            out_f32=True, out_group=1):
+            out_f32=True, out_group=1, out_c_pad=None):
     """conv(+bias)(+ReLU if pre_relu) -> BatchNorm (batch statistics when run.training) -> (+res)(ReLU)(+res)
     -> optional 3x3 max-pool, or -> global average into ``feat`` [N, feat_ld] at column feat_off.
 
     ``out_f32=False``: the caller guarantees that the output is consumed only by fp16 tensor-core convolutions
     (forward, dgrad and wgrad), so no fp32 copy of it is written.  ``out_group=2``: the output feeds W-stride-2
     convolutions only; its fp16 planes are written in the pixel-pair layout (needs an even padded width, else
-    ignored).  Returns the output Act (None when ``feat``)."""
+    ignored).  ``out_c_pad``: allocate the output with this many channels (> cout); the extra channels are zeros, so
+    that a narrow tensor (a Fire squeeze output: 16 .. 80 channels) meets the 64-channel granularity of the fp16
+    tensor-core kernels of its consumers.  Returns the output Act (None when ``feat``)."""
     p, st = run.params, stream()
     w = p[cname + ".weight"]
     b = p.get(cname + ".bias")
     gamma, beta = p[bname + ".weight"], p[bname + ".bias"]
     rm, rv = run.buffers[bname + ".running_mean"], run.buffers[bname + ".running_var"]
     cout, cin, kh, kw = w.shape
-    assert x.c >= cin and x.c - cin < 4, (cname, x.c, cin)
+    assert x.c >= cin, (cname, x.c, cin)      # extra input channels are zeros (and get zero weights)
     cin_pad = x.c
     sh, sw = stride
     cph, cpw = (kh - 1) // 2, (kw - 1) // 2
@@ -269,12 +286,16 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     else:
         oh, ow = (pool_out(ho, pool[0], ceil), pool_out(wo, pool[1], ceil)) if pool else (ho, wo)
         if out is None:
-            oc = out_c or cout
+            oc = out_c_pad or out_c or cout
             o16 = USE_TC and USE_F16 and out_bound is not None and oc % 64 == 0
             assert out_f32 or o16, (cname, "out_f32=False needs an fp16-capable output")
             out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, f32=out_f32, f16=o16,
                       split=USE_TC and out_f32 and not o16 and oc % 32 == 0)
             out.bound = out_bound
+            if out_c_pad and oc > cout:      # the BN pass writes channels [0, cout) only
+                for buf in (out.t, out.lo, out.h2):
+                    if buf is not None:
+                        buf.zero_()
             if out_group == 2 and o16 and (ow + 2 * out_pad[1]) % 2 == 0:
                 out.group = bp.out_group = 2
         assert out.h == oh and out.w == ow and out.n == n

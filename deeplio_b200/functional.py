@@ -93,6 +93,9 @@ def mul(a, b):
 
 
 _drop_counter = [0]
+# device int64 counter mixed into every dropout seed at run time (None: not used).  deeplio_b200.graph sets it while
+# it captures a train step and advances it inside the graph, so that replays draw fresh masks.
+_seed_epoch = [None]
 
 
 def dropout_mask(shape, p, device):
@@ -101,7 +104,7 @@ def dropout_mask(shape, p, device):
     mask = torch.empty(shape, device=device, dtype=torch.float32)
     _drop_counter[0] += 1
     seed = (torch.initial_seed() * 0x9E3779B1 + _drop_counter[0] * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
-    L.dropout_mask(ptr(mask), mask.numel(), float(p), seed, _stream())
+    L.dropout_mask(ptr(mask), mask.numel(), float(p), seed, ptr(_seed_epoch[0]), _stream())
     return mask
 
 

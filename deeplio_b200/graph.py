@@ -1,0 +1,74 @@
+"""Whole-step CUDA graph: forward, loss and backward of one train step captured once and replayed.
+
+A train step of this path is several hundred to ~1400 kernel launches (PointSeg) issued from Python through ctypes;
+at small per-GPU batches the host cannot issue them as fast as the GPU retires them.  Everything in the step is
+static -- shapes, the straight-line encoder programs, the arena the gradients are written into -- so the step is
+captured into ONE graph (torch.cuda.graph: the caching allocator gives the capture a private pool, so every
+intermediate keeps its address across replays) and replayed with a single launch.  Two things in the step are not
+static and are handled explicitly: dropout masks (their seed is mixed with a counter in device memory that the
+graph itself increments, ``functional._seed_epoch``) and the optimizer / gradient exchange, which stay outside the
+graph (Adam's bias correction depends on the step number; the all-reduce overlaps through a hook when eager).
+
+The reference has no counterpart (it launches op by op from Python, trainer.py:238-272).
+"""
+import gc
+
+import torch
+
+from . import _lib as L
+from . import functional as Fn
+
+
+class GraphedTrainStep:
+    """``step(inputs) -> loss`` with forward + loss + backward replayed from a CUDA graph.
+
+    ``fwd_loss(inputs) -> loss`` runs the model and the loss on a dict of device tensors; ``example`` is one such dict
+    (shapes and dtypes fix the graph).  ``zero_grad`` is called inside the graph before the forward pass (the
+    FlatAdam arena memset).  After ``step`` the parameter gradients are in place; the caller all-reduces and calls
+    the optimizer as usual.
+
+    Streams (torch autograd): the AccumulateGrad nodes of the parameters remember the stream they were created on
+    and can outlive the step that created them; if eager steps ran on the DEFAULT stream before the capture, their
+    nodes run on the legacy stream during the captured backward, which invalidates the capture (measured: capture from
+    a fresh model works, after two eager default-stream steps it fails).  So run the train loop -- eager steps, this
+    constructor, the replays -- on ONE dedicated stream (``with torch.cuda.stream(torch.cuda.Stream())``): the capture
+    then happens on the current stream.  When the current stream is the default stream, a side stream is used and no
+    eager step may have run before."""
+
+    def __init__(self, fwd_loss, example, zero_grad, warmup=3):
+        dev = next(iter(example.values())).device
+        self.static_in = {k: torch.empty_like(v) for k, v in example.items()}
+        for k, v in example.items():
+            self.static_in[k].copy_(v)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        gc.collect()       # drop autograd graphs of earlier eager steps that are only kept alive by reference cycles
+        prev = Fn._seed_epoch[0]
+        Fn._seed_epoch[0] = self.epoch
+        try:
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev) if cur == torch.cuda.default_stream(dev) else cur
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                      # warm-up off the default stream, as capture requires
+                for _ in range(warmup):
+                    zero_grad()
+                    fwd_loss(self.static_in).backward()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            n0 = L.launch_count()
+            # capture on the warm-up stream: autograd nodes that outlive an iteration (AccumulateGrad) stay on one stream
+            with torch.cuda.graph(self.graph, stream=side):
+                self.epoch.add_(1)
+                zero_grad()
+                self.static_loss = fwd_loss(self.static_in)
+                self.static_loss.backward()
+            self.captured_launches = L.launch_count() - n0     # library kernels every replay launches
+        finally:
+            Fn._seed_epoch[0] = prev
+
+    def __call__(self, inputs):
+        for k, v in inputs.items():
+            if v.data_ptr() != self.static_in[k].data_ptr():
+                self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss.detach()

@@ -195,7 +195,10 @@ class PointSegEncoder(_Encoder):
 
     def _fire(self, run, q, x, ex, bypass):
         """Fire (pointseg_modules.py:110-141): squeeze1x1 -> {expand1x1 || expand3x3} -> cat (+ x)."""
-        s = E.conv_bn(run, x, q + "squeeze", q + "squeeze_bn", out_pad=(1, 1))
+        # the squeeze output (16 .. 80 channels) is allocated with a multiple of 64 channels, zeros beyond the real
+        # ones, so that both expand convolutions run on the fp16 tensor-core kernels
+        sq = run.params[q + "squeeze.weight"].shape[0]
+        s = E.conv_bn(run, x, q + "squeeze", q + "squeeze_bn", out_pad=(1, 1), out_c_pad=(sq + 63) // 64 * 64)
         res = x if (bypass and x.c == 2 * ex) else None
         out = E.conv_bn(run, s, q + "expand1x1", q + "expand1x1_bn", res=res, res_mode=2, c_off=0, out_c=2 * ex,
                         out_pad=(1, 1))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 3
+#define DLIO_ABI_VERSION 4
 
 typedef enum {
     DLIO_OK = 0,
@@ -261,11 +261,14 @@ int dlio_channel_scale_fwd(dlio_tensor4 x, const float *x_ptr, const float *gate
 int dlio_channel_scale_bwd(const float *dout, const float *gate, const float *dmean, int n, int hw, int c,
                            float *dx, void *stream);
 /* element-wise helpers: out = alpha*a + beta*b (16-byte aligned; out may alias a or b), out = a * b,
- * out[a,c] = sum_t x[a,t,c] (ImuFeatFC time sum, imu_feat_nets.py:50), Bernoulli keep mask scaled by 1/(1-p) */
+ * out[a,c] = sum_t x[a,t,c] (ImuFeatFC time sum, imu_feat_nets.py:50), Bernoulli keep mask scaled by 1/(1-p)
+ * (counter-based generator; seed_epoch, optional, is a counter in DEVICE memory mixed into the seed at run time, so a
+ * launch captured in a CUDA graph draws a fresh mask on every replay once the graph's owner advances it) */
 int dlio_axpby(const float *a, float alpha, const float *b, float beta, float *out, long long n, void *stream);
 int dlio_sum_mid(const float *x, float *out, long long a, int t, int c, void *stream);
 int dlio_mul(const float *a, const float *b, float *out, long long n, void *stream);
-int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed, void *stream);
+int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed,
+                      const unsigned long long *seed_epoch, void *stream);
 
 /* ------------------------------------------------------------------ dense layers (small M)
  * Replaces aten::linear / addmm behind nn.Linear (fc1, IMU-FC stack, soft fusion, Odom-FC, heads:
