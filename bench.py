@@ -6,6 +6,10 @@
 One "step" = one full train step of BASELINE.json configs[1] (Simple-1 LiDAR net + bi-LSTM IMU net + soft
 fusion + LSTM odometry net, 64x2048 frame pairs, batch 8 per GPU, S = 2 pairs per sample): forward -> HWS
 loss -> backward -> gradient all-reduce (N > 1) -> Adam, dropout active, BatchNorm in train mode.
+Two timed passes of the same K steps: eager launches with the library's per-call CUDA events (the per-class
+breakdown in ``roofline.classes``, ``config.eager_ms_per_step``), then forward + loss + backward replayed from one
+CUDA graph (``value``; DLIO_GRAPH=0 keeps the eager number).  ``e2e`` feeds every step from pinned host memory
+through ``deeplio_b200.pipeline`` (copy stream one step ahead, loss read one step late).
 Prints ONE JSON line on rank 0.  ``--impl reference`` times the CPU restatement of the reference (the
 reference is pure Python / PyTorch and does not travel to the GPU box) on the host cores.
 """
