@@ -156,6 +156,8 @@ struct BnPool {
     const float *out_bound;
     int group;                  // layout of out_h2: 1 plain, 2 pixel pairs (common.cuh, st4_h2)
     uint8_t *idx;
+    float *ymax;                // optional [n, ho, wo, C]: the conv output y at the arg-max (what the BN backward
+                                // sums need from the input side: dlio_pool_bwd_sums)
 };
 __device__ __forceinline__ void bnpool_store(const BnPool &a, unsigned pix, int c, const float4 &v, float s16) {
     const size_t o = (size_t)pix * a.out.c + a.c_off + c;
@@ -267,14 +269,14 @@ __global__ void __launch_bounds__(256, 5) bn_pool3_fwd_kernel(BnPool a) {
                 continue;
             }
             const int w0 = wo * SW - 1;
-            float4 best = f4(-FLT_MAX);
+            float4 best = f4(-FLT_MAX), yb = f4(0.f);          // yb: raw conv output at the arg-max
             unsigned bi = 0;                                   // four packed window-relative arg-max bytes
-#define DLIO_POOL_TAKE(v, r)                                                          \
-    do {                                                                              \
-        if (v.x > best.x) { best.x = v.x; bi = (bi & 0xFFFFFF00u) | (r); }            \
-        if (v.y > best.y) { best.y = v.y; bi = (bi & 0xFFFF00FFu) | ((r) << 8); }     \
-        if (v.z > best.z) { best.z = v.z; bi = (bi & 0xFF00FFFFu) | ((r) << 16); }    \
-        if (v.w > best.w) { best.w = v.w; bi = (bi & 0x00FFFFFFu) | ((r) << 24); }    \
+#define DLIO_POOL_TAKE(v, r, raw)                                                                   \
+    do {                                                                                            \
+        if (v.x > best.x) { best.x = v.x; yb.x = raw.x; bi = (bi & 0xFFFFFF00u) | (r); }            \
+        if (v.y > best.y) { best.y = v.y; yb.y = raw.y; bi = (bi & 0xFFFF00FFu) | ((r) << 8); }     \
+        if (v.z > best.z) { best.z = v.z; yb.z = raw.z; bi = (bi & 0xFF00FFFFu) | ((r) << 16); }    \
+        if (v.w > best.w) { best.w = v.w; yb.w = raw.w; bi = (bi & 0x00FFFFFFu) | ((r) << 24); }    \
     } while (0)
             if (rows_ok && w0 >= 0 && w0 + 2 < a.y.w) {
                 // interior window: nine independent loads issued back to back (the kernel is bound by load latency)
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256, 5) bn_pool3_fwd_kernel(BnPool a) {
                 for (int r = 0; r < 9; ++r) {
                     float4 t = fma4(sc, v[r], sf);
                     if (RELU) t = relu4(t);
-                    DLIO_POOL_TAKE(t, (unsigned)r);
+                    DLIO_POOL_TAKE(t, (unsigned)r, v[r]);
                 }
             } else {
 #pragma unroll
@@ -297,14 +299,16 @@ __global__ void __launch_bounds__(256, 5) bn_pool3_fwd_kernel(BnPool a) {
                     for (int dx = 0; dx < 3; ++dx) {
                         const int w = w0 + dx;
                         if (w < 0 || w >= a.y.w) continue;
-                        float4 t = fma4(sc, ld4(rp[dy] + w * C), sf);
+                        const float4 raw = ld4(rp[dy] + w * C);
+                        float4 t = fma4(sc, raw, sf);
                         if (RELU) t = relu4(t);
-                        DLIO_POOL_TAKE(t, (unsigned)(dy * 3 + dx));
+                        DLIO_POOL_TAKE(t, (unsigned)(dy * 3 + dx), raw);
                     }
                 }
             }
 #undef DLIO_POOL_TAKE
             if (irow) *reinterpret_cast<unsigned *>(irow + (size_t)wo * C) = bi;
+            if (a.ymax) st4(a.ymax + ((size_t)(n * a.out.h + ho) * a.out.w + wo) * C + c, yb);
             bnpool_store(a, pix0 + x, c, best, s16);
         }
     }
@@ -538,6 +542,12 @@ struct BnApply {
     const double *sums;
     double count;
     int pre_relu, batch_stats, cg, segs;
+    // gather variant (template SH, SW > 0): dz is not read from memory but un-pooled on the fly from the gradient of
+    // the pooled output and the arg-max bytes, as backward pass 1 does (no dz round trip through HBM)
+    Geo dout;
+    const float *doutp;
+    const uint8_t *idx;
+    int pooled_h, pooled_w, c_off;
     int hs;            // dy row step: y row i lies on dy row hs * i, the other dy rows are zero (H-strided convolution
                        // whose backward runs as a stride-1 convolution over the input grid)
     float *dy_hi, *dy_lo, *dgamma, *dbeta;
@@ -546,6 +556,7 @@ struct BnApply {
     float *dy_bound;   // written by block 0: the bound that defines their scale
 };
 
+template <int SH, int SW>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
     __shared__ float red[MAX_C];
     __shared__ float wred[32];
@@ -599,7 +610,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
     // Row-structured: a work item is (row of the padded dy grid, column segment), so the pixel decode (two divisions)
     // happens once per row, and the loads of FOUR pixels are issued before any of them is used -- with one pixel per
     // iteration the kernel had two 16-byte loads in flight per thread and ran at 4.7 TB/s.
-    constexpr int U = 4;
+    constexpr bool GATHER = SH > 0;
+    constexpr int U = GATHER ? 1 : 4;
+    constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;     // candidate windows per axis (gather)
     const int wl = (int)(threadIdx.x / a.cg), WL = (int)(blockDim.x / a.cg);
     const int rows = a.dy.n * a.dy.hp, segs = a.segs, items = rows * segs;
     const int seg_w = (a.dy.wp + segs - 1) / segs;
@@ -612,7 +625,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
         const bool zero_row = h < 0 || h >= a.dy.h || (a.hs == 2 && (h & 1));
         if (a.hs == 2) h >>= 1;
         const float *yrow = zero_row ? nullptr : a.yp + a.y.off(n, h, 0) + c;
-        const float *zrow = zero_row ? nullptr : a.dz + (((size_t)n * a.y.h + h) * a.y.w) * C + c;
+        const float *zrow = (zero_row || GATHER) ? nullptr : a.dz + (((size_t)n * a.y.h + h) * a.y.w) * C + c;
+        const uint8_t *ip[NR];
+        const float *dp[NR];
+        unsigned rbase[NR];         // (window-relative row) * 3, or 255 when the window row does not exist
+        if (GATHER && !zero_row) {
+            const int ho0 = SH == 1 ? h - 1 : h >> 1;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int ho = ho0 + i;
+                const bool okh = ho >= 0 && ho < a.pooled_h && (SH == 1 || i == 0 || (h & 1));
+                const int rh = SH == 1 ? 2 - i : h + 1 - 2 * ho;
+                const int hoc = okh ? ho : 0;
+                ip[i] = a.idx + ((size_t)(n * a.pooled_h + hoc) * a.pooled_w) * C + c;
+                dp[i] = a.doutp + a.dout.off(n, hoc, 0) + a.c_off + c;
+                rbase[i] = okh ? (unsigned)(rh * 3) : 255u;
+            }
+        }
         for (int x0 = x_begin + wl; x0 < x_end; x0 += U * WL) {
             float4 y[U], dz[U];
             bool ok[U];
@@ -622,7 +651,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
                 ok[u] = !zero_row && x < x_end && w >= 0 && w < a.dy.w;
                 if (ok[u]) {
                     y[u] = ld4(yrow + (size_t)w * a.y.c);
-                    dz[u] = ld4(zrow + (size_t)w * C);
+                    if (!GATHER) {
+                        dz[u] = ld4(zrow + (size_t)w * C);
+                    } else {
+                        const int wo0 = SW == 1 ? w - 1 : w >> 1;
+                        float4 g = f4(0.f);
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) {
+                            const int wo = wo0 + j;
+                            const bool okw = wo >= 0 && wo < a.pooled_w && (SW == 1 || j == 0 || (w & 1));
+                            const int rw = SW == 1 ? 2 - j : w + 1 - 2 * wo;
+                            const int woc = okw ? wo : 0;
+#pragma unroll
+                            for (int i = 0; i < NR; ++i) {
+                                const unsigned bi = *reinterpret_cast<const unsigned *>(ip[i] + woc * C);
+                                const float4 d = ld4(dp[i] + woc * a.dout.c);
+                                const unsigned r = (okw && rbase[i] != 255u) ? rbase[i] + (unsigned)rw : 255u;
+                                const unsigned m = __vcmpeq4(bi, r * 0x01010101u);
+                                if (m & 0x000000FFu) g.x += d.x;
+                                if (m & 0x0000FF00u) g.y += d.y;
+                                if (m & 0x00FF0000u) g.z += d.z;
+                                if (m & 0xFF000000u) g.w += d.w;
+                            }
+                        }
+                        dz[u] = g;
+                    }
                 }
             }
 #pragma unroll
@@ -659,6 +712,59 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
         __syncthreads();
         for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(a.dbias + i, (double)red[i]);
     }
+}
+
+// BN-backward sums of a pooled layer WITHOUT a ReLU between BN and pool, from the pooled side: every dout is routed
+// to exactly one input position, so sum dz = sum dout and sum dz * yhat = sum dout * yhat(arg-max), with y at the
+// arg-max saved by the forward pass (ymax).  sums[2C] = windows * max |dout| bounds |dz| (up to `windows` pooled
+// outputs can select the same input).  8 bytes per POOLED element instead of a pass over the conv output.
+__global__ void __launch_bounds__(256) pool_bwd_sums_kernel(Geo dout, const float *__restrict__ doutp, int c_off,
+                                                            const float *__restrict__ ymax,
+                                                            const float *__restrict__ mean,
+                                                            const float *__restrict__ invstd, int cg, float windows,
+                                                            double *sums) {
+    __shared__ float red[2 * MAX_C];
+    const int C = cg * 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int c = (int)(threadIdx.x % cg) * 4;
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c);
+    float4 s1 = f4(0.f), s2 = f4(0.f);
+    float amax = 0.f;
+    const unsigned npix = (unsigned)(dout.n * dout.h * dout.w);
+    constexpr int U = 4;
+    const unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) / (unsigned)cg, step = (gridDim.x * blockDim.x) / (unsigned)cg;
+    for (unsigned pix = p0; pix < npix; pix += U * step) {
+        float4 d[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned p = pix + u * step;
+            if (p < npix) {
+                d[u] = ld4(doutp + (size_t)p * dout.c + c_off + c);
+                y[u] = ld4(ymax + (size_t)p * C + c);
+            } else {
+                d[u] = f4(0.f);
+                y[u] = mu;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float4 yh = make_float4((y[u].x - mu.x) * is.x, (y[u].y - mu.y) * is.y, (y[u].z - mu.z) * is.z,
+                                          (y[u].w - mu.w) * is.w);
+            s1 = add4(s1, d[u]);
+            s2 = fma4(d[u], yh, s2);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d[u].x), fabsf(d[u].y)), fmaxf(fabsf(d[u].z), fabsf(d[u].w))));
+        }
+    }
+    amax = warp_max(amax) * windows;
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long *>(sums + 2 * C), (unsigned long long)__double_as_longlong((double)amax));
+    atomicAdd(&red[c + 0], s1.x); atomicAdd(&red[c + 1], s1.y);
+    atomicAdd(&red[c + 2], s1.z); atomicAdd(&red[c + 3], s1.w);
+    atomicAdd(&red[C + c + 0], s2.x); atomicAdd(&red[C + c + 1], s2.y);
+    atomicAdd(&red[C + c + 2], s2.z); atomicAdd(&red[C + c + 3], s2.w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, (double)red[i]);
 }
 
 __global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, int n) {
@@ -844,7 +950,7 @@ static int check_cg(int c, const char *who) {
 extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                                     dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
                                     float *out_hi, float *out_lo, void *out_h2, const float *out_bound,
-                                    uint8_t *pool_idx, void *stream) {
+                                    uint8_t *pool_idx, float *pool_ymax, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(valid_t4(y) && valid_t4(out) && y_ptr && (out_hi || out_h2), "bn_act_pool_fwd: bad argument");
     DLIO_CHECK_ARG(!out_h2 || (out_bound && (((uintptr_t)out_h2) & 15) == 0), "bn_act_pool_fwd: fp16 planes need their bound");
@@ -862,7 +968,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     a.yp = y_ptr; a.scale = scale; a.shift = shift; a.resp = res_ptr;
     a.res_mode = p.res_mode; a.relu = p.relu; a.pk = p.pool_k; a.sh = p.pool_sh; a.sw = p.pool_sw;
     a.c_off = p.c_off; a.cg = y.c / 4;
-    a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx;
+    a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx; a.ymax = pool_ymax;
     a.out_h2 = (__half *)out_h2; a.out_bound = out_bound;
     a.group = p.out_group == 2 ? 2 : 1;
     DLIO_CHECK_ARG(a.group == 1 || (out_h2 && a.out.wp % 2 == 0), "bn_act_pool_fwd: the pixel-pair layout needs fp16 planes and an even padded width");
@@ -885,6 +991,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
         else DLIO_POOL3(2, 1);
 #undef DLIO_POOL3
     } else {
+        DLIO_CHECK_ARG(!pool_ymax, "bn_act_pool_fwd: pool_ymax needs a 3x3 pool without a residual");
         bn_act_pool_fwd_kernel<<<grid_for(total, block, 16), block, 0, st>>>(a);
     }
     DLIO_LAUNCH_CHECK();
@@ -953,13 +1060,16 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
     return DLIO_OK;
 }
 
-extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
-                                 long long count, const float *scale, const float *mean, const float *invstd,
-                                 int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
-                                 void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
-                                 void *stream) {
+// dz != nullptr: dz read from memory.  dz == nullptr: un-pooled on the fly from (dout, pool_idx) through the 3x3 pool p.
+static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz, const dlio_bnpool *p,
+                             dlio_tensor4 dout_t, const float *dout, const uint8_t *pool_idx, const double *sums,
+                             long long count, const float *scale, const float *mean, const float *invstd,
+                             int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
+                             void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
+                             void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && dz && (dy_hi || dy_h2), "bn_bwd_apply: bad argument");
+    DLIO_CHECK_ARG(valid_t4(y) && valid_t4(dy_t) && y_ptr && (dz || (p && dout && pool_idx)) && (dy_hi || dy_h2),
+                   "bn_bwd_apply: bad argument");
     DLIO_CHECK_ARG(!dy_h2 || (dy_bound && sums && (((uintptr_t)dy_h2) & 15) == 0), "bn_bwd_apply: fp16 planes need sums[2C] and dy_bound");
     DLIO_CHECK_ARG(!dy_h2 || y.c % 32 == 0, "bn_bwd_apply: fp16 planes need c %% 32 == 0 (whole warps in the bound reduction)");
     DLIO_CHECK_ARG(dy_hi || !dy_lo, "bn_bwd_apply: dy_lo without dy_hi");
@@ -976,11 +1086,70 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
     a.count = (double)count; a.pre_relu = pre_relu; a.batch_stats = batch_stats; a.cg = y.c / 4;
     a.dy_hi = dy_hi; a.dy_lo = dy_lo; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias_sums;
     a.dy_h2 = (__half *)dy_h2; a.dy_bound = dy_bound; a.hs = hs;
+    a.doutp = nullptr; a.idx = nullptr; a.pooled_h = a.pooled_w = a.c_off = 0;
     int block = block_for_cg(a.cg);
     DLIO_CHECK_ARG((long long)a.dy.n * a.dy.hp * a.dy.wp < (1LL << 31), "bn_bwd_apply: tensor too large");
-    const int grid = resident_grid(bn_bwd_apply_kernel, block);
-    a.segs = row_segments(a.dy.n * a.dy.hp, a.dy.wp, block / a.cg, grid);
-    bn_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DLIO_APPLY(SH_, SW_)                                                        \
+    do {                                                                            \
+        const int grid = resident_grid(bn_bwd_apply_kernel<SH_, SW_>, block);       \
+        a.segs = row_segments(a.dy.n * a.dy.hp, a.dy.wp, block / a.cg, grid);       \
+        bn_bwd_apply_kernel<SH_, SW_><<<grid, block, 0, st>>>(a);                   \
+    } while (0)
+    if (dz) {
+        DLIO_APPLY(0, 0);
+    } else {
+        DLIO_CHECK_ARG(p->pool_k == 3 && p->relu == 0 && p->res_mode == 0 && hs == 1 && (p->pool_sh == 1 || p->pool_sh == 2) &&
+                           (p->pool_sw == 1 || p->pool_sw == 2),
+                       "bn_pool_bwd_apply: needs a 3x3 pool (strides 1 or 2) directly after the BN, no ReLU / residual between");
+        DLIO_CHECK_ARG(valid_t4(dout_t) && dout_t.n == y.n && p->c_off % 4 == 0 && p->c_off + y.c <= dout_t.c && dout_t.c % 4 == 0,
+                       "bn_pool_bwd_apply: bad dout descriptor");
+        a.dout = Geo(dout_t); a.doutp = dout; a.idx = pool_idx; a.pooled_h = dout_t.h; a.pooled_w = dout_t.w;
+        a.c_off = p->c_off;
+        if (p->pool_sh == 1 && p->pool_sw == 2) DLIO_APPLY(1, 2);
+        else if (p->pool_sh == 2 && p->pool_sw == 2) DLIO_APPLY(2, 2);
+        else if (p->pool_sh == 1 && p->pool_sw == 1) DLIO_APPLY(1, 1);
+        else DLIO_APPLY(2, 1);
+    }
+#undef DLIO_APPLY
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
+                                 long long count, const float *scale, const float *mean, const float *invstd,
+                                 int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
+                                 void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
+                                 void *stream) {
+    DLIO_CHECK_ARG(dz, "bn_bwd_apply: dz is NULL");
+    return bn_bwd_apply_impl(y, y_ptr, dz, nullptr, y, nullptr, nullptr, sums, count, scale, mean, invstd, pre_relu,
+                             batch_stats, dy_t, dy_hi, dy_lo, dy_h2, dy_bound, dgamma, dbeta, dbias_sums, stream);
+}
+
+extern "C" int dlio_bn_pool_bwd_apply(dlio_tensor4 y, const float *y_ptr, dlio_bnpool p, dlio_tensor4 dout,
+                                      const float *dout_ptr, const uint8_t *pool_idx, const double *sums,
+                                      long long count, const float *scale, const float *mean, const float *invstd,
+                                      int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
+                                      void *dy_h2, float *dy_bound, float *dgamma, float *dbeta,
+                                      double *dbias_sums, void *stream) {
+    return bn_bwd_apply_impl(y, y_ptr, nullptr, &p, dout, dout_ptr, pool_idx, sums, count, scale, mean, invstd,
+                             pre_relu, batch_stats, dy_t, dy_hi, dy_lo, dy_h2, dy_bound, dgamma, dbeta, dbias_sums,
+                             stream);
+}
+
+extern "C" int dlio_pool_bwd_sums(dlio_tensor4 dout, const float *dout_ptr, int c_off, int c, const float *ymax,
+                                  const float *mean, const float *invstd, int windows, double *sums, void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
+    DLIO_CHECK_ARG(valid_t4(dout) && dout.ph == 0 && dout.pw == 0 && dout_ptr && ymax && mean && invstd && sums &&
+                       windows >= 1 && c_off % 4 == 0 && c_off + c <= dout.c && dout.c % 4 == 0,
+                   "pool_bwd_sums: bad argument");
+    int rc = check_cg(c, "pool_bwd_sums");
+    if (rc) return rc;
+    const int cg = c / 4, block = block_for_cg(cg);
+    const long long total = (long long)dout.n * dout.h * dout.w * cg;
+    DLIO_CHECK_ARG((long long)dout.n * dout.h * dout.w < (1LL << 30), "pool_bwd_sums: tensor too large");
+    pool_bwd_sums_kernel<<<grid_for((total + 3) / 4, block, 8), block, 0, (cudaStream_t)stream>>>(
+        Geo(dout), dout_ptr, c_off, ymax, mean, invstd, cg, (float)windows, sums);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

@@ -26,6 +26,9 @@ USE_F16 = True
 # arena before each backward, so the backward kernels may write parameter gradients straight into it (overwrite
 # == accumulate into zeros) and hand autograd None -- one AccumulateGrad add kernel less per parameter tensor
 # (116 launches per step).  One backward per zero_grad(), as in the reference's train loop.
+# conv -> (ReLU) -> BN -> max-pool layers: BN-backward sums from the pooled side + un-pooling inside the apply pass
+# (dlio_pool_bwd_sums / dlio_bn_pool_bwd_apply) instead of materialising dz
+FUSED_POOL_BWD = True
 # debugging aid (scripts/repeat_parity.py): when a dict, every conv_bn backward stores clones of its tensors here
 DEBUG_TRACE = None
 
@@ -277,7 +280,7 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             nbt.add_(1)
     bp = L.BnPool(1 if relu else 0, res_mode if res is not None else 0, 3 if pool else 1,
                   pool[0] if pool else 1, pool[1] if pool else 1, c_off, 1)
-    idx = None
+    idx = ymax = None
     dummy = y.t4
     if feat is not None:
         assert res is None and not pool
@@ -301,9 +304,14 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         assert out.h == oh and out.w == ow and out.n == n
         if pool and run.record:
             idx = run.empty(n, oh, ow, cout, dtype=torch.uint8)
+            # BN directly followed by the pool (Simple-1): the backward pass takes its sums from the pooled side and
+            # un-pools inside the apply pass, so dz never goes through HBM; needs y at the arg-max from this pass
+            if (FUSED_POOL_BWD and not relu and res is None and single and out.c == cout and pool[0] in (1, 2)
+                    and pool[1] in (1, 2) and n * (oh + 2 * out.ph) * (ow + 2 * out.pw) < 2 ** 31):
+                ymax = run.empty(n, oh, ow, cout)
         L.bn_act_pool_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), res.t4 if res is not None else dummy,
                           ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(out.h2),
-                          ptr(out.bound) if out.h2 is not None else None, ptr(idx), st)
+                          ptr(out.bound) if out.h2 is not None else None, ptr(idx), ptr(ymax), st)
         result = out
     if not run.record:
         return result
@@ -330,17 +338,22 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                 dg = ("f16" if (f16_ok(cout, cin_pad, stride)) else ("tf32" if tc_ok(cout, cin_pad, stride) else "simt"))
         assert wg != "simt" or x.t is not None, (cname, "wgrad on the CUDA cores needs the fp32 input plane")
         modes = (wg, dg)
-        dz = run.empty(n, ho, wo, cout)
         sums = run.zeros(2 * cout + 1, dtype=torch.float64)
-        dres, dres_c, dres_acc = None, 0, 0
-        if res is not None and res.needs_grad:
-            partial = res.c != cout
-            dres, existed = run.grad_slot(res, zeroed=partial)
-            dres_c, dres_acc = res.c, 1 if (existed or partial) else 0
-        L.bn_act_pool_bwd_reduce(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), ptr(bnv[0]), ptr(bnv[1]),
-                                 res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
-                                 bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
-                                 ptr(sums), 1 if "f16" in modes else 0, st)
+        dz = None
+        if ymax is not None:
+            windows = (3 if pool[0] == 1 else 2) * (3 if pool[1] == 1 else 2)
+            L.pool_bwd_sums(dout_t4, ptr(dout), 0, cout, ptr(ymax), ptr(bnv[0]), ptr(bnv[1]), windows, ptr(sums), st)
+        else:
+            dz = run.empty(n, ho, wo, cout)
+            dres, dres_c, dres_acc = None, 0, 0
+            if res is not None and res.needs_grad:
+                partial = res.c != cout
+                dres, existed = run.grad_slot(res, zeroed=partial)
+                dres_c, dres_acc = res.c, 1 if (existed or partial) else 0
+            L.bn_act_pool_bwd_reduce(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), ptr(bnv[0]), ptr(bnv[1]),
+                                     res.t4 if res is not None else dummy, ptr(res.t) if res is not None else None,
+                                     bpb, src, dout_t4, ptr(dout), ld, ptr(idx), ptr(dz), ptr(dres), dres_c, dres_acc,
+                                     ptr(sums), 1 if "f16" in modes else 0, st)
         # backward on the tensor cores: dy is produced as padded split planes.  wgrad wants dy on x's padded grid,
         # dgrad wants pads >= (k - 1 - pad); x's pads satisfy both for the "same" stride-1 convolutions.
         on_x_grid = wg in ("f16", "tf32")
@@ -356,10 +369,15 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dya.bound = run.empty(1) if dya.h2 is not None else None
         dgamma, dbeta = run.param_grad(bname + ".weight", gamma), run.param_grad(bname + ".bias", beta)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
-        L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
-                       1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t), ptr(dya.lo), ptr(dya.h2),
-                       ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
-        if DEBUG_TRACE is not None:
+        if dz is None:
+            L.bn_pool_bwd_apply(y.t4, ptr(y.t), bp, dout_t4, ptr(dout), ptr(idx), ptr(sums), count, ptr(bnv[2]),
+                                ptr(bnv[0]), ptr(bnv[1]), 1 if pre_relu else 0, 1 if run.training else 0, dya.t4,
+                                ptr(dya.t), ptr(dya.lo), ptr(dya.h2), ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
+        else:
+            L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
+                           1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t), ptr(dya.lo), ptr(dya.h2),
+                           ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
+        if DEBUG_TRACE is not None and dz is not None:
             DEBUG_TRACE[(id(run), cname)] = dict(dout=dout.clone(), dz=dz.clone(), sums=sums.clone(),
                                                  dy=(dya.t if dya.t is not None else dya.h2).clone(), y=y.t.clone(),
                                                  bnv=bnv.clone())
@@ -461,7 +479,7 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
     bp = L.BnPool(0, 0, 3, stride[0], stride[1], 0)
     idx = run.empty(x.n, oh, ow, x.c, dtype=torch.uint8) if run.record else None
     L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), ptr(out.lo), None, None,
-                      ptr(idx), st)
+                      ptr(idx), None, st)
     out.bound = x.bound
     if not run.record:
         return out

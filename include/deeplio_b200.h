@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 4
+#define DLIO_ABI_VERSION 5
 
 typedef enum {
     DLIO_OK = 0,
@@ -210,11 +210,12 @@ typedef struct {
  * out_lo (optional): low-order TF32 plane, v - trunc_tf32(v) (out_hi always receives the full fp32 value).
  * out_h2 / out_bound (optional): packed fp16 split planes on out's padded grid, scaled from *out_bound; out_hi
  * may then be NULL (no fp32 copy is written).  pool_idx (uint8 [n,ho,wo,c], required when pooling is
- * differentiated): window-relative arg-max, first maximum wins (torch tie-break). */
+ * differentiated): window-relative arg-max, first maximum wins (torch tie-break).  pool_ymax (optional, fp32
+ * [n,ho,wo,c], 3x3 pool without residual): the conv output y at the arg-max, for dlio_pool_bwd_sums. */
 int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const float *scale, const float *shift,
                          dlio_tensor4 res, const float *res_ptr, dlio_bnpool p, dlio_tensor4 out,
                          float *out_hi, float *out_lo, void *out_h2, const float *out_bound,
-                         uint8_t *pool_idx, void *stream);
+                         uint8_t *pool_idx, float *pool_ymax, void *stream);
 
 typedef enum { DLIO_GRAD_DIRECT = 0, DLIO_GRAD_POOL = 1, DLIO_GRAD_AVG = 2 } dlio_grad_src;
 
@@ -245,6 +246,21 @@ int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const
                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
                       void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
                       void *stream);
+/* The two backward passes of a layer  conv -> (ReLU) -> BN -> 3x3 max-pool  (no ReLU / residual between BN and pool:
+ * Simple-1, lidar_feat_nets.py:306-322) without materialising dz:
+ *   dlio_pool_bwd_sums: the BN-backward sums from the POOLED side -- every dout is routed to exactly one input, so
+ *   sums[0:c] += sum dout, sums[c:2c] += sum dout * yhat(arg-max) with y at the arg-max saved by the forward pass
+ *   (pool_ymax); sums[2c] = windows * max |dout| >= max |dz| (`windows`: how many pooling windows can contain one
+ *   input position: 3 or 2 per axis for stride 1 or 2).  8 bytes per pooled element.
+ *   dlio_bn_pool_bwd_apply: dlio_bn_bwd_apply with dz un-pooled on the fly from (dout, pool_idx) through pool p.
+ * Against pass 1 + pass 2 above this saves writing and re-reading dz and one read of y per conv-output element. */
+int dlio_pool_bwd_sums(dlio_tensor4 dout, const float *dout_ptr, int c_off, int c, const float *ymax,
+                       const float *mean, const float *invstd, int windows, double *sums, void *stream);
+int dlio_bn_pool_bwd_apply(dlio_tensor4 y, const float *y_ptr, dlio_bnpool p, dlio_tensor4 dout,
+                           const float *dout_ptr, const uint8_t *pool_idx, const double *sums, long long count,
+                           const float *scale, const float *mean, const float *invstd, int pre_relu,
+                           int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo, void *dy_h2,
+                           float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums, void *stream);
 int dlio_f64_to_f32(const double *src, float *dst, int n, void *stream);
 
 /* global average pooling (adaptive_avg_pool2d((1,1)), lidar_feat_nets.py:84-85,131,175,340; SE squeeze,

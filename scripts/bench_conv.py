@@ -72,7 +72,7 @@ for name, cin, cout, h, w, kh, kw in LAYERS:
             n_, hp_, wp_, c_ = t.shape
             t4 = L.Tensor4(n_, hp_, wp_, c_, 0, 0)
             L.bn_act_pool_fwd(t4, t.data_ptr(), None, None, t4, None, L.BnPool(0, 0, 1, 1, 1, 0), t4, hi.data_ptr(),
-                              lo.data_ptr(), None, None, None, st)
+                              lo.data_ptr(), None, None, None, None, st)
             return hi, lo
         xhi, xlo = split(x)
         dyhi, dylo = split(dy)

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in decl if s not in exported]
     assert not missing, missing
     assert sorted(lib.EXPORTS) == decl          # the ctypes binding covers the whole header
-    assert lib.abi_version() == lib.ABI_VERSION == 4
+    assert lib.abi_version() == lib.ABI_VERSION == 5
 
 
 def test_library_is_sm100a_with_no_other_arch(lib):

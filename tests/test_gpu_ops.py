@@ -106,7 +106,7 @@ def split_padded(L, x, ph, pw):
     lo = torch.empty_like(hi)
     t_src, t_dst = L.Tensor4(n, h, w, c, 0, 0), L.Tensor4(n, h, w, c, ph, pw)
     L.bn_act_pool_fwd(t_src, src.data_ptr(), None, None, t_src, None, L.BnPool(0, 0, 1, 1, 1, 0), t_dst, hi.data_ptr(),
-                      lo.data_ptr(), None, None, None, _st())
+                      lo.data_ptr(), None, None, None, None, _st())
     return hi, lo
 
 
@@ -335,11 +335,11 @@ def test_conv_pair_view_strided_fwd_dgrad_wgrad(case):
     x_f32 = torch.empty(n, hp, wp, cin, device=DEV)
     t_in, t_out = L.Tensor4(n, h, w, cin, 0, 0), L.Tensor4(n, h, w, cin, tph, tpw)
     L.bn_act_pool_fwd(t_in, xs.data_ptr(), None, None, t_in, None, L.BnPool(0, 0, 1, 1, 1, 0, 2), t_out,
-                      x_f32.data_ptr(), None, x_h2.data_ptr(), x_b.data_ptr(), None, _st())
+                      x_f32.data_ptr(), None, x_h2.data_ptr(), x_b.data_ptr(), None, None, _st())
     # the same planes in the plain layout, regrouped on the host: [n,hp,wp/2,pixel,plane,c] -> [.., plane, pixel, c]
     plain = torch.full((n, hp, wp, 2, cin), float("nan"), dtype=torch.float16, device=DEV)
     L.bn_act_pool_fwd(t_in, xs.data_ptr(), None, None, t_in, None, L.BnPool(0, 0, 1, 1, 1, 0, 1), t_out,
-                      x_f32.data_ptr(), None, plain.data_ptr(), x_b.data_ptr(), None, _st())
+                      x_f32.data_ptr(), None, plain.data_ptr(), x_b.data_ptr(), None, None, _st())
     regrouped = plain.view(n, hp, wp // 2, 2, 2, cin).permute(0, 1, 2, 4, 3, 5).contiguous()
     assert torch.equal(regrouped.view(-1).view(torch.int16), x_h2.view(-1).view(torch.int16))
 
@@ -393,7 +393,10 @@ def test_conv_pair_view_strided_fwd_dgrad_wgrad(case):
 
 @pytest.mark.parametrize("cfg", [
     # c, h, w, pre_relu, relu, pool, ceil, res_mode
-    (64, 9, 20, True, False, (1, 2), True, 0),
+    (64, 9, 20, True, False, (1, 2), True, 0),       # Simple-1 blocks: BN directly followed by the pool -> backward
+    (128, 10, 33, True, False, (2, 2), True, 0),     # sums from the pooled side, un-pooling inside the apply pass
+    (64, 12, 9, True, False, (2, 2), False, 0),
+    (64, 9, 20, True, False, (1, 2), True, 0, "two-pass"),   # the same block through dz (reduce + apply passes)
     (128, 10, 33, False, True, (2, 2), True, 0),
     (48, 8, 16, False, True, (1, 2), False, 0),
     (64, 7, 11, False, True, None, False, 1),
@@ -405,7 +408,8 @@ def test_conv_bn_block_vs_torch(cfg):
     same block written with torch.nn.functional on the CPU.  Tolerance 2e-5 relative (BN divides by a
     batch std computed in a different summation order)."""
     from deeplio_b200 import engine as E
-    c, h, w, pre_relu, relu, pool, ceil, res_mode = cfg
+    c, h, w, pre_relu, relu, pool, ceil, res_mode = cfg[:8]
+    E.FUSED_POOL_BWD = len(cfg) == 8
     n, cin = 2, 32
     g = torch.Generator().manual_seed(7)
     x = torch.randn(n, cin, h, w, generator=g)
@@ -441,8 +445,11 @@ def test_conv_bn_block_vs_torch(cfg):
     run = E.Run(params, bufs, torch.device(DEV), True, True)
     xa = E.Act(n, h, w, cin, 1, 1, t=to_padded_nhwc(x, 1, 1))
     ra = E.Act(n, h, w, c, 0, 0, t=to_padded_nhwc(res, 0, 0)) if res_mode else None
-    out = E.conv_bn(run, xa, "cv", "bn", (1, 1), pre_relu=pre_relu, relu=relu, pool=pool, ceil=ceil, res=ra,
-                    res_mode=res_mode, out_pad=(1, 2))
+    try:
+        out = E.conv_bn(run, xa, "cv", "bn", (1, 1), pre_relu=pre_relu, relu=relu, pool=pool, ceil=ceil, res=ra,
+                        res_mode=res_mode, out_pad=(1, 2))
+    finally:
+        E.FUSED_POOL_BWD = True
     got = from_nhwc(out.t[:, 1:1 + out.h, 2:2 + out.w])
     assert got.shape == ref.shape
     assert relerr(got, ref.detach()) < 2e-5
