@@ -556,8 +556,9 @@ struct BnApply {
     float *dy_bound;   // written by block 0: the bound that defines their scale
 };
 
+// (the gather variant is latency-bound on its candidate loads: registers capped for four resident blocks per SM)
 template <int SH, int SW>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnApply a) {
+__global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApply a) {
     __shared__ float red[MAX_C];
     __shared__ float wred[32];
     const int C = a.cg * 4;
