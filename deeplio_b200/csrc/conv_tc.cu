@@ -599,7 +599,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
 struct TcWgradArgs {
     int kh, kw, ph, pw, wp;
     int cin, cout, bn, stages;
-    int swap;          // operands swapped (narrow Cin): A = x tiles of FOUR taps (M = 4 x 32 ci), B = dy (N = 128 co)
+    int swap;          // operands swapped (Cin == one TMA box): A = x tiles of 128 / Cin taps, B = dy (N = 128 co)
     long long rows, rows_per_split;
     float *dw;
     int f16;
@@ -637,16 +637,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     // few rows) are served by L2 -- with the split index fastest, every tap streamed both tensors from DRAM again
     // (ncu: 1.7 GB read for 0.42 GB of operands in Simple-1 conv2, 50 % DRAM utilisation)
     //
-    // swap mode (Cin == 32: the first layer through its space-to-depth view).  With dy as the A operand, a 128 x 32
-    // tile costs one MMA per 32 bytes of K that reads the whole 4 KB dy slice from shared memory for 32 columns of
-    // output: ~60 clocks per MMA against a 16-clock floor, shared-memory bound.  Swapped, the M = 128 rows of A are the
-    // 32 input channels of FOUR taps (four x boxes at four row shifts -- a tap is nothing but a row shift) and dy is
-    // the B operand with N = 128 output channels: a quarter of the MMAs for the same shared-memory bytes each.
-    // Then blockIdx.x = group of four taps, blockIdx.z = 128-channel block of Cout, the tile is dw^T.
+    // swap mode (Cin == one TMA box: 32 in TF32 mode -- the first layer through its space-to-depth view -- or 64 in
+    // fp16 mode -- Simple-1 conv2, FlowNet conv2).  With dy as the A operand, a 128 x Cin tile costs one MMA per 32
+    // bytes of K that reads the whole 4 KB dy slice from shared memory for Cin columns of output: shared-memory bound
+    // (~60 clocks per MMA against a 16-clock floor at Cin = 32; 50 % tensor-pipe activity at Cin = 64).  Swapped, the
+    // M = 128 rows of A are the input channels of 128 / Cin taps (x boxes at different row shifts -- a tap is nothing
+    // but a row shift) and dy is the B operand with N = 128 output channels: 1/4 or 1/2 of the MMAs for the same
+    // shared-memory bytes each.  Then blockIdx.x = tap group, blockIdx.z = 128-channel block of Cout, the tile is dw^T.
     const int nblk = a.cin / a.bn;
     const bool swap = a.swap != 0;
     const int taps_all = a.kh * a.kw;
-    const int tap = swap ? blockIdx.x * 4 : blockIdx.x / nblk;
+    const int tap = swap ? blockIdx.x * (TC_BM / (F16 ? 64 : 32)) : blockIdx.x / nblk;
     const int ci0 = swap ? 0 : (blockIdx.x - tap * nblk) * a.bn;
     const int co0 = blockIdx.z * TC_BM;
     const int dy_ = tap / a.kw, dx_ = tap - dy_ * a.kw;
@@ -759,10 +760,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
         const int co = co0 + quad * 32 + lane;
         const bool co_ok = co < a.cout;      // Cout % 128 == 64: the upper half of the last tile is TMA zero fill
         const int taps = a.kh * a.kw;
-        // swap: TMEM lane = (tap quad, ci lane), column = output channel
-        float *orow = swap ? a.dw + ((size_t)co0 * taps + (tap + quad)) * a.cin + lane
+        // swap: TMEM lane m = (tap m / Cin, input channel m % Cin), column = output channel
+        const int sm_ = quad * 32 + lane, st_ = sm_ / a.cin;
+        float *orow = swap ? a.dw + ((size_t)co0 * taps + (tap + st_)) * a.cin + (sm_ - st_ * a.cin)
                            : a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
-        const bool row_ok = !swap || tap + quad < taps;
+        const bool row_ok = !swap || tap + st_ < taps;
         float inv = 1.f, corr = 1.f;
         if (f16) {
             inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.yb));
@@ -824,7 +826,8 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     for (int c : {128, 64, 32})
         if (a.cin % c == 0 && c % bc == 0) { bn = c; break; }
     if (!bn) return 0;
-    const bool swap = !f16 && a.cin == 32 && a.cout % TC_BM == 0;   // see the kernel: four taps' x tiles as A, dy as B
+    const bool swap = a.cin == bc && a.cout % TC_BM == 0;   // see the kernel: x tiles of 128 / Cin taps as A, dy as B
+    const int tpg = TC_BM / bc;                              // taps per CTA in swap mode
     if (swap) bn = TC_BM;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
     if (rows >= (1LL << 31) - 4096) return 0;
@@ -833,7 +836,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
 
     const int taps = a.kh * a.kw;
     const int mblocks = (a.cout + TC_BM - 1) / TC_BM;
-    const int tiles = swap ? ((taps + 3) / 4) * mblocks : taps * (a.cin / bn) * mblocks;
+    const int tiles = swap ? ((taps + tpg - 1) / tpg) * mblocks : taps * (a.cin / bn) * mblocks;
     // K splits: one CTA per SM (192 KB of smem), so the grid should fill whole waves of 148 CTAs -- a grid of
     // 450 CTAs (3.04 waves) ran at 76 % of a 444-CTA one.  Pick the split count whose total is closest below a
     // multiple of 148 among 2..4 waves, keeping at least 64 K chunks per CTA.
@@ -876,8 +879,9 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
-    dim3 grid((unsigned)(swap ? (taps + 3) / 4 : taps * (a.cin / bn)), (unsigned)splits, (unsigned)mblocks);
-    if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
+    dim3 grid((unsigned)(swap ? (taps + tpg - 1) / tpg : taps * (a.cin / bn)), (unsigned)splits, (unsigned)mblocks);
+    if (f16 && swap) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mdh, mdl, t);   // x as A, dy as B
+    else if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     else if (swap) wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mdh, mdl, t);   // x as A, dy as B
     else wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);
     DLIO_LAUNCH_CHECK();
