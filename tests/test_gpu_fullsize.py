@@ -19,11 +19,11 @@ NETS = [dict(lidar="lidar-feat-simple-1"), dict(lidar="lidar-feat-pointseg"),
         dict(lidar="lidar-feat-flownet")]
 
 
-def build(cfg, B, sd):
+def build(cfg, B, sd, hw=(H, W)):
     from deeplio_b200 import nets
     from deeplio_b200.config import build_config_container
     build_config_container(cfg, argparse.Namespace(device=DEV, batch_size=B))
-    model = nets.get_model((3, H, W), cfg, DEV)
+    model = nets.get_model((3,) + tuple(hw), cfg, DEV)
     model.load_state_dict(sd)
     return model
 
@@ -136,3 +136,51 @@ def test_one_adam_step_matches_oracle():
     ropt.step()
     for k, p in model.named_parameters():
         assert (p.detach().cpu() - leaves[k].detach()).abs().max().item() < 2e-6, k
+
+
+@pytest.mark.parametrize("kw", NETS, ids=lambda k: k["lidar"])
+def test_reference_default_resolution_57x720(kw):
+    """The reference's own default image size (config.yaml:7-8: 57 x 720): odd heights and, deeper in the nets, odd
+    widths -- ceil-mode pools with overhanging windows, H-stride-2 layers over an odd number of rows, W-strided
+    layers whose input width is odd (no pixel-pair view: they take the CUDA-core path).  Train-mode forward at 2e-5
+    and every parameter gradient against an fp64 run of the oracle, with the conditioning-aware bar of
+    tests/test_gpu_model.py: max(2e-4 of the tensor's largest entry, 4 x sensitivity), sensitivity = the larger of the
+    fp32 oracle's own distance from fp64 and the change of the fp64 gradient under 2e-6 .. 4e-6 relative perturbations
+    of all weights and inputs (ReLU / arg-max decisions flip at that level; measured here: the fp32 oracle itself is
+    1e-2 away from fp64 on FlowNet conv3.weight)."""
+    from tests.helpers import oracle_train_step
+    h, w, B, S, T = 57, 720, 2, 2, 15
+    cfg = make_cfg(height=h, width=w, seq=S, odom_hidden=64, **kw)
+    sd = O.synthetic_state(cfg, seed=33)
+    inputs = O.synthetic_batch(B, S, h, w, T, seed=33)
+    model = build(cfg, B, sd, (h, w))
+    model.train()
+    pos, ori = model(dev(inputs))
+    ((pos ** 2).sum() + (ori ** 2).sum()).backward()
+    opos, oori, g32, _ = oracle_train_step(cfg, sd, inputs)
+    assert rel_err(pos.detach().cpu(), opos) < 2e-5
+    assert rel_err(ori.detach().cpu(), oori) < 2e-5
+
+    def f64(t):
+        return t.double() if t.is_floating_point() else t
+    sd64 = {k: f64(v) for k, v in sd.items()}
+    in64 = tuple(t.double() for t in inputs)
+    g64 = oracle_train_step(cfg, sd64, in64)[2]
+    gperts = []
+    for seed, amp in ((7, 2e-6), (8, 4e-6), (9, 4e-6)):
+        gen = torch.Generator().manual_seed(seed)
+
+        def jitter(t):
+            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
+        gperts.append(oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))[2])
+    gmax = max(g.abs().max().item() for g in g64.values())
+    n_tight = 0
+    params = dict(model.named_parameters())
+    for k, p in params.items():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        scale = g64[k].abs().max().item()
+        sens = max((g32[k].double() - g64[k]).abs().max().item(), max((gp[k] - g64[k]).abs().max().item() for gp in gperts))
+        e = (p.grad.cpu().double() - g64[k]).abs().max().item()
+        assert e <= max(2e-4 * scale, 4 * sens) + 1e-5 * gmax, (k, e, sens, scale)
+        n_tight += e <= 2e-4 * scale + 1e-5 * gmax
+    assert n_tight >= 0.5 * len(params), (n_tight, len(params))
