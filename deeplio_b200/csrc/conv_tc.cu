@@ -1,24 +1,29 @@
-// tcgen05 implicit-GEMM convolution for sm_100a: stride-1 convolutions with Cin % 32 == 0, computed in
-// error-compensated TF32 ("3xTF32": hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM), which keeps the
-// result within ~1e-6 of an fp32 convolution (the 1e-4 pose gate rules out single-pass TF32 / BF16).
+// tcgen05 implicit-GEMM convolutions for sm_100a: stride-1 "same" convolutions computed with error-compensated
+// split operands -- three MMAs per fp32-accurate product (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), which
+// keeps the result within ~1e-6 of an fp32 convolution (the 1e-4 pose gate rules out single-pass TF32 / BF16).
+// Two operand formats share the kernels (template F16): packed fp16 hi|lo planes with per-tensor power-of-two scales
+// ("3xF16", kind::f16, Cin % 64 == 0: the main path) and fp32 + TF32-residual planes ("3xTF32", kind::tf32,
+// Cin % 32 == 0: the first layer through its space-to-depth view).  Strided layers arrive here as stride-1 problems
+// through views of the same memory (conv_s2d.cu), with an optional row decimation in the epilogue (hdec).
 //
 // Formulation ("shifted GEMM over the padded grid").  The input is a padded NHWC tensor whose zero pads are
 // real memory, viewed as a matrix X[R = n*hp*wp, Cin].  For EVERY padded position q the kernel computes
 //     Y[q, co] = sum_{tap=(dy,dx)} sum_ci X[q + (dy-ph)*wp + (dx-pw), ci] * W[co, tap, ci]
 // which is the convolution at interior positions; rows that fall on pads are discarded in the epilogue
-// (2-15 % extra MMA work, no im2col, no gather).  Each (tap, 32-channel chunk) is one pipeline stage: a plain
-// 2-D TMA box [128 rows x 32 floats] of X at row offset q0 + shift (out-of-range rows are zero-filled by TMA
-// and only feed discarded rows) and a [BN x 32] box of W, both 128B-swizzled, hi and lo planes.
+// (2-15 % extra MMA work, no im2col, no gather).  Each (tap, 128-byte channel chunk) is one pipeline stage: a plain
+// 2-D TMA box [128 rows x 128 bytes] of X at row offset q0 + shift (out-of-range rows are zero-filled by TMA
+// and only feed discarded rows) and a [BN x 128 bytes] box of W, both 128B-swizzled, hi and lo planes.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane) + TMEM owner,
-// warps 2-5 epilogue (TMEM -> registers -> bias / ReLU -> global, per-channel BN statistics).
-// One 128 x BN output tile per CTA.
+// conv_tc_kernel (forward and dgrad): persistent, one CTA per SM, 10 warps: warp 0 TMA producer, warp 1 tcgen05.mma
+// issuer (one elected lane of the converged warp) + TMEM owner, warps 2-9 epilogue (TMEM -> registers -> scale /
+// bias / ReLU -> global, per-channel BN statistics); the epilogue of tile t overlaps the main loop of tile t + 1.
+// wgrad_tc_kernel: one 128 x BN tile of dw per CTA, split-K over pixel ranges, both operands MN-major.
 //
-// Accumulation accuracy.  The tensor core adds each K=8 MMA into the fp32 accumulator with truncation, so the
+// Accumulation accuracy.  The tensor core adds each MMA into the fp32 accumulator with truncation, so the
 // error of ONE accumulator grows linearly with the number of MMA steps (measured: 8e-9 * K relative, 3.7e-5 at
-// K = 4608 -- too much for gradient parity).  The tile therefore owns FOUR accumulators of BN columns: the
-// hi*hi products go round-robin (by K chunk) into three of them and the small lo*hi + hi*lo corrections into
-// the fourth; the epilogue adds the four in fp32.  Each main accumulator sees 1/9 of the steps.
+// K = 4608 -- too much for gradient parity).  The forward kernel therefore drains its main accumulator into
+// registers (round-to-nearest adds) every 8 K stages and keeps the small lo*hi + hi*lo corrections in a separate
+// accumulator (see the kernel); wgrad spreads the hi*hi products round-robin over three accumulators.
 #include <cuda.h>
 
 #include "common.cuh"

@@ -171,14 +171,12 @@ __global__ void __launch_bounds__(256) rnn_step_bwd_kernel(BwdArgs a) {
 }
 
 // ------------------------------------------------------------------ whole-sequence kernels (short hidden size)
-// For the IMU nets (H = 128, T = 15 .. 50) one launch runs ALL T steps of a layer.  A CLUSTER OF TWO CTAs serves one
-// (direction, chunk of RB batch rows): each CTA keeps the W_hh rows of half of the hidden units in shared memory
-// for the whole sequence (4 * 64 * 128 floats = 128 KB at H = 128), h_{t-1} in shared memory and c_{t-1} in
-// registers of the lane that owns (unit, batch row).  Every warp owns hidden units warp, warp + 16, ...; the G*RB
-// partial dot products of a unit are reduced with ONE 31-shuffle transpose-reduce (lane l ends with gate l / RB of
-// batch row l % RB) and three more shuffles bring the gates of a batch row together.  The two CTAs exchange their
-// halves of h_t through the layer output in global memory (which has to be written anyway): cluster barrier with
-// release / acquire, then an L1-bypassing reload of h_t.  60 step launches per IMU window become 4.
+// For the IMU nets (H = 128, T = 15 .. 50) one launch runs ALL T steps of a layer.  A CLUSTER OF FOUR CTAs serves
+// one (direction, chunk of RB batch rows): each CTA keeps the W_hh rows of a quarter of the hidden units in shared
+// memory for the whole sequence (4 * 32 * 128 floats = 64 KB at H = 128), h_{t-1} in shared memory and c_{t-1} in
+// registers of the thread that owns (unit, batch row).  Every CTA writes its part of h_t into the NEXT h buffer of
+// all four CTAs (its peers' through distributed shared memory); one cluster barrier per step.  60 step launches per
+// IMU window become 4.
 constexpr int SEQ_WARPS = 16;
 constexpr int SEQ_CLUSTER = 4;     // CTAs per (direction, batch chunk): each owns H / 4 hidden units
 
