@@ -31,6 +31,12 @@ CASES = {
     "resnet_lstm_rnn": (dict(lidar="lidar-feat-resnet", imu="imu-feat-rnn", odom="odom-feat-rnn", odom_hidden=64), 2, 2, 16, 128, 7, 15),
     "imu_only_lstm": (dict(lidar=None, imu="imu-feat-rnn", odom="odom-feat-rnn", odom_hidden=64), 3, 3, 16, 64, 9, 16),
     "lidar_only_simple1": (dict(lidar="lidar-feat-simple-1", imu=None, odom="odom-feat-fc"), 2, 2, 16, 64, 5, 17),
+    # BASELINE.json configs[4] shape: FlowNet + bi-LSTM over a 50-step IMU window
+    "flownet_add_lstm_t50": (dict(lidar="lidar-feat-flownet", imu="imu-feat-rnn", odom="odom-feat-rnn", odom_hidden=64,
+                                  lidar_fusion="add"), 2, 2, 16, 128, 50, 18),
+    # odd image height, odd batch, widths that turn odd inside the net (ceil-mode pools with overhanging windows)
+    "simple1_gru_fc_19x76": (dict(lidar="lidar-feat-simple-1", imu="imu-feat-rnn", rnn_type="gru", odom="odom-feat-fc"),
+                             3, 2, 19, 76, 7, 19),
 }
 GRAD_HEAD = 6
 
@@ -67,7 +73,8 @@ def run_case(name):
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for name in CASES:
+    only = sys.argv[1:]          # optional: case names to (re)generate; default all
+    for name in (only or CASES):
         rec = run_case(name)
         path = os.path.join(out_dir, name + ".pt")
         torch.save(rec, path)
