@@ -1,0 +1,45 @@
+"""SASS evidence that the hot kernels are Blackwell-native: per kernel of libdeeplio_b200.so, the counts of the
+mnemonics B200_PROFILING.md lists (UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG = TMA loads,
+HMMA = legacy mma.sync) plus cluster / distributed-shared-memory instructions, and the ptxas resource lines.
+usage: python scripts/sass_evidence.py > profiles/r01_sass_evidence.md   (CPU only: cuobjdump + nvcc -Xptxas -v)"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "deeplio_b200", "libdeeplio_b200.so")
+sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+PAT = collections.OrderedDict([
+    ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA\b"), ("UTCBAR (tcgen05.commit)", r"\bUTCBAR\b"), ("LDTM (tcgen05.ld)", r"\bLDTM\b"),
+    ("UTMALDG (TMA load)", r"\bUTMALDG\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"), ("UCGABAR (cluster barrier)", r"\bUCGABAR"),
+    ("MEMBAR.ALL.GPU", r"\bMEMBAR\.ALL\.GPU"), ("REDG (global reduction)", r"\bREDG\."),
+    ("HMMA (legacy mma.sync)", r"\bHMMA\b"), ("FFMA", r"\bFFMA\b"),
+])
+kern, counts, order = None, {}, []
+for line in sass.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = re.sub(r"\(.*", "", kern).replace("void ", "").replace("dlio::", "")
+        counts[kern] = collections.Counter()
+        order.append(kern)
+        continue
+    if kern and "/*" in line:
+        for name, pat in PAT.items():
+            if re.search(pat, line):
+                counts[kern][name] += 1
+print("# SASS evidence (cuobjdump -sass deeplio_b200/libdeeplio_b200.so, sm_100a)\n")
+print("Static instruction counts per kernel of the mnemonics `B200_PROFILING.md` names.  tcgen05 / TMA / TMEM appear in the")
+print("convolution kernels only; no kernel uses the legacy `HMMA` tensor path; the whole-sequence RNN kernels use cluster")
+print("barriers (each release-arrive carries a `MEMBAR.ALL.GPU`: part of their ~5 us per time step, DESIGN.md section 9).")
+print("Kernels without any of these (the HBM-bound passes, dense layers, Adam) are omitted: %d kernels in the library.\n" % len(order))
+cols = list(PAT)
+print("| kernel | " + " | ".join(cols) + " |")
+print("|---|" + "---:|" * len(cols))
+for k in order:
+    c = counts[k]
+    if not (c["UTC*MMA (tcgen05.mma)"] or c["UTMALDG (TMA load)"] or c["UCGABAR (cluster barrier)"] or k.startswith("conv_")):
+        continue
+    print("| `%s` | " % k[:60] + " | ".join(str(c[n]) for n in cols) + " |")
