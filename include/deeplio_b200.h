@@ -4,7 +4,7 @@
  * The reference (ArashJavan/DeepLIO) has no FFI: its hot path is four nn.Module subsystems under
  * deeplio/models/nets that dispatch to ATen / cuDNN / cuBLAS.  Each entry point below replaces one
  * family of those implicit library calls; the reference call sites are cited per function.  The
- * Python host side (deeplio_b200/nets.py) mirrors the reference's module interface on top of this
+ * Python host side (deeplio_b200/nets/) mirrors the reference's module interface on top of this
  * ABI; INTEGRATION.md shows the binding a maintainer of the reference would add.
  *
  * Conventions
