@@ -9,5 +9,5 @@ __version__ = "0.1.0"
 
 
 def install():
-    from .install import install as _install
+    from .dropin import install as _install
     return _install()

@@ -60,12 +60,12 @@ _PROTOS = {
     "dlio_conv2d_fwd_f16": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
     "dlio_conv2d_bwd_data_f16": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, P]),
     "dlio_conv2d_bwd_weight_f16": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
-    "dlio_bn_finalize": (I, [P, LL, I, P, P, P, P, F, F, I, P, P, P, P, P, P, P]),
+    "dlio_bn_finalize": (I, [P, LL, I, P, P, P, P, F, F, I, P, P, P, P, P, P, P, P]),
     "dlio_bn_act_pool_fwd": (I, [Tensor4, P, P, P, Tensor4, P, BnPool, Tensor4, P, P, P, P, P, P, P]),
     "dlio_pool_bwd_sums": (I, [Tensor4, P, I, I, P, P, P, I, P, P]),
     "dlio_bn_pool_bwd_apply": (I, [Tensor4, P, BnPool, Tensor4, P, P, P, LL, P, P, P, I, I, Tensor4, P, P, P, P, P, P, P, P]),
     "dlio_bn_act_pool_bwd_reduce": (I, [Tensor4, P, P, P, P, P, Tensor4, P, BnPool, I, Tensor4, P, I, P, P, P, I, I, P, I, P]),
-    "dlio_bn_bwd_apply": (I, [Tensor4, P, P, P, LL, P, P, P, I, I, Tensor4, P, P, P, P, P, P, P, P]),
+    "dlio_bn_bwd_apply": (I, [Tensor4, P, P, P, LL, P, P, P, I, I, Tensor4, P, P, P, P, P, P, P, P, I, P]),
     "dlio_f64_to_f32": (I, [P, P, I, P]),
     "dlio_spatial_mean_fwd": (I, [Tensor4, P, P, P, I, P, I, I, P]),
     "dlio_spatial_dot": (I, [Tensor4, P, Tensor4, P, P, P]),
@@ -91,7 +91,7 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 if _lib.dlio_abi_version() != ABI_VERSION:
     raise ImportError("deeplio_b200: ABI version mismatch (library %d, binding %d)" % (_lib.dlio_abi_version(), ABI_VERSION))
 

@@ -101,9 +101,19 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const double *__restr
                                    const float *__restrict__ gamma, const float *__restrict__ beta,
                                    float *running_mean, float *running_var, float momentum, float eps,
                                    int use_running, float *mean, float *invstd, float *scale, float *shift,
-                                   const float *res_bound, float *out_bound) {
+                                   const float *res_bound, float *out_bound, long long *num_batches_tracked) {
     __shared__ float red[32];
     float bmax = 0.f;
+    // momentum < 0: nn.BatchNorm2d(momentum=None), the cumulative moving average with factor 1 / num_batches_tracked
+    // (after this step's increment).  Every thread reads the counter before thread 0 bumps it.
+    if (num_batches_tracked && !use_running) {
+        const long long seen = *num_batches_tracked + 1;
+        if (momentum < 0.f) momentum = 1.f / (float)seen;
+        __syncthreads();
+        if (threadIdx.x == 0) *num_batches_tracked = seen;
+    } else if (momentum < 0.f) {
+        momentum = 1.f;
+    }
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         float m, is;
         double mu = 0.0, var = 0.0;
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
             if (!(v.w > 0.f)) g.w = 0.f;
         }
         if (a.res_mode == 1 && a.dres) st4(a.dres + ro, a.dres_acc ? add4(ld4(a.dres + ro), g) : g);
-        st4(a.dz + (size_t)pix * C + c, g);
+        if (a.dz) st4(a.dz + (size_t)pix * C + c, g);
         if (a.sums) {
             float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
             s1 = add4(s1, g);
@@ -538,10 +548,11 @@ __global__ void __launch_bounds__(256, 4) bn_pool3_bwd_reduce_kernel(BnBwd a) {
 // backward pass 2: dy = scale * (dz - mean(dz) - yhat * mean(dz * yhat)) [* (y > 0)]
 struct BnApply {
     Geo y, dy;
-    const float *yp, *dz, *scale, *mean, *invstd;
+    const float *yp, *dz, *scale, *shift, *mean, *invstd;
     const double *sums;
     double count;
     int pre_relu, batch_stats, cg, segs;
+    int post_relu;     // dz is the gradient BEFORE the ReLU that follows the BN: masked here by scale*y + shift > 0
     // gather variant (template SH, SW > 0): dz is not read from memory but un-pooled on the fly from the gradient of
     // the pooled output and the arg-max bytes, as backward pass 1 does (no dz round trip through HBM)
     Geo dout;
@@ -587,8 +598,9 @@ __global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApp
         __syncthreads();
     }
     const int c = (int)(threadIdx.x % a.cg) * 4;
-    float4 sc = f4(1.f), mu = f4(0.f), is = f4(1.f), m1 = f4(0.f), m2 = f4(0.f);
+    float4 sc = f4(1.f), sf = f4(0.f), mu = f4(0.f), is = f4(1.f), m1 = f4(0.f), m2 = f4(0.f);
     if (a.scale) sc = ld4(a.scale + c);
+    if (a.post_relu && a.shift) sf = ld4(a.shift + c);
     if (a.mean) {
         mu = ld4(a.mean + c);
         is = ld4(a.invstd + c);
@@ -693,6 +705,13 @@ __global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApp
                 }
                 const float4 yh = make_float4((y[u].x - mu.x) * is.x, (y[u].y - mu.y) * is.y, (y[u].z - mu.z) * is.z,
                                               (y[u].w - mu.w) * is.w);
+                if (!GATHER && a.post_relu) {
+                    const float4 v = fma4(sc, y[u], sf);     // the forward pass's BN output, same fma
+                    if (!(v.x > 0.f)) dz[u].x = 0.f;
+                    if (!(v.y > 0.f)) dz[u].y = 0.f;
+                    if (!(v.z > 0.f)) dz[u].z = 0.f;
+                    if (!(v.w > 0.f)) dz[u].w = 0.f;
+                }
                 float4 d = make_float4(sc.x * (dz[u].x - m1.x - yh.x * m2.x), sc.y * (dz[u].y - m1.y - yh.y * m2.y),
                                        sc.z * (dz[u].z - m1.z - yh.z * m2.z), sc.w * (dz[u].w - m1.w - yh.w * m2.w));
                 if (a.pre_relu) {
@@ -931,14 +950,15 @@ extern "C" int dlio_pack_input(const float *src, long long sn, long long st, lon
 extern "C" int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma,
                                 const float *beta, float *running_mean, float *running_var, float momentum,
                                 float eps, int use_running, float *mean, float *invstd, float *scale,
-                                float *shift, const float *res_bound, float *out_bound, void *stream) {
+                                float *shift, const float *res_bound, float *out_bound,
+                                long long *num_batches_tracked, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(c > 0 && mean && invstd && scale && shift, "bn_finalize: bad argument");
     DLIO_CHECK_ARG(use_running ? (running_mean && running_var) : (stats && count > 0), "bn_finalize: missing statistics");
     DLIO_CHECK_ARG(!out_bound || (stats && count > 0), "bn_finalize: the output bound needs the batch statistics");
     bn_finalize_kernel<<<1, c >= 1024 ? 1024 : (c + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(
         stats, (double)count, c, gamma, beta, running_mean, running_var, momentum, eps, use_running, mean, invstd,
-        scale, shift, res_bound, out_bound);
+        scale, shift, res_bound, out_bound, num_batches_tracked);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }
@@ -1006,7 +1026,7 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
                                            const uint8_t *pool_idx, float *dz, float *dres, int dres_c,
                                            int dres_accumulate, double *sums, int sums_absmax, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(valid_t4(y) && y_ptr && dout_ptr && dz, "bn_act_pool_bwd_reduce: bad argument");
+    DLIO_CHECK_ARG(valid_t4(y) && y_ptr && dout_ptr && (dz || sums), "bn_act_pool_bwd_reduce: bad argument");
     int rc = check_cg(y.c, "bn_act_pool_bwd_reduce");
     if (rc) return rc;
     DLIO_CHECK_ARG(grad_src == DLIO_GRAD_AVG || valid_t4(dout), "bn_act_pool_bwd_reduce: bad dout");
@@ -1027,7 +1047,7 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
     long long total = (long long)y.n * y.h * y.w * a.cg;
     const int grid = grid_for(total, block, 8);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = a.pk == 3 && a.res_mode == 0 && !a.dres && a.sums && y.c % 32 == 0 &&
+    const bool fast = a.pk == 3 && a.res_mode == 0 && !a.dres && a.sums && a.dz && y.c % 32 == 0 &&
                       (long long)y.n * y.h * y.w < (1LL << 31);
     if (fast) {
         const int rows = y.n * y.h;
@@ -1062,7 +1082,8 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
 }
 
 // dz != nullptr: dz read from memory.  dz == nullptr: un-pooled on the fly from (dout, pool_idx) through the 3x3 pool p.
-static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz, const dlio_bnpool *p,
+static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz, const float *shift, int post_relu,
+                             const dlio_bnpool *p,
                              dlio_tensor4 dout_t, const float *dout, const uint8_t *pool_idx, const double *sums,
                              long long count, const float *scale, const float *mean, const float *invstd,
                              int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
@@ -1084,6 +1105,8 @@ static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz
     BnApply a;
     a.y = Geo(y); a.dy = Geo(dy_t);
     a.yp = y_ptr; a.dz = dz; a.scale = scale; a.mean = mean; a.invstd = invstd; a.sums = sums;
+    a.shift = shift; a.post_relu = post_relu;
+    DLIO_CHECK_ARG(!post_relu || (dz && (shift || !scale)), "bn_bwd_apply: post_relu needs dz and the BN shift");
     a.count = (double)count; a.pre_relu = pre_relu; a.batch_stats = batch_stats; a.cg = y.c / 4;
     a.dy_hi = dy_hi; a.dy_lo = dy_lo; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias_sums;
     a.dy_h2 = (__half *)dy_h2; a.dy_bound = dy_bound; a.hs = hs;
@@ -1121,9 +1144,9 @@ extern "C" int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float
                                  long long count, const float *scale, const float *mean, const float *invstd,
                                  int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
                                  void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
-                                 void *stream) {
+                                 const float *shift, int post_relu, void *stream) {
     DLIO_CHECK_ARG(dz, "bn_bwd_apply: dz is NULL");
-    return bn_bwd_apply_impl(y, y_ptr, dz, nullptr, y, nullptr, nullptr, sums, count, scale, mean, invstd, pre_relu,
+    return bn_bwd_apply_impl(y, y_ptr, dz, shift, post_relu, nullptr, y, nullptr, nullptr, sums, count, scale, mean, invstd, pre_relu,
                              batch_stats, dy_t, dy_hi, dy_lo, dy_h2, dy_bound, dgamma, dbeta, dbias_sums, stream);
 }
 
@@ -1133,7 +1156,7 @@ extern "C" int dlio_bn_pool_bwd_apply(dlio_tensor4 y, const float *y_ptr, dlio_b
                                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
                                       void *dy_h2, float *dy_bound, float *dgamma, float *dbeta,
                                       double *dbias_sums, void *stream) {
-    return bn_bwd_apply_impl(y, y_ptr, nullptr, &p, dout, dout_ptr, pool_idx, sums, count, scale, mean, invstd,
+    return bn_bwd_apply_impl(y, y_ptr, nullptr, nullptr, 0, &p, dout, dout_ptr, pool_idx, sums, count, scale, mean, invstd,
                              pre_relu, batch_stats, dy_t, dy_hi, dy_lo, dy_h2, dy_bound, dgamma, dbeta, dbias_sums,
                              stream);
 }

@@ -10,13 +10,23 @@ Reference semantics implemented here: base_net.py:55-71 (conv helper), lidar_fea
 (Simple-1 blocks), pointseg_modules.py:110-141,203-221 (Fire / SE), torchvision resnet.py:88-103
 (BasicBlock), BatchNorm2d train/eval statistics.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from ._lib import ptr
 
+# defaults of nn.BatchNorm2d; the values actually used come from the BatchNorm2d module that owns the layer's
+# parameters (Run.bn_cfg: PointSeg passes momentum=bn_d, pointseg_modules.py:98-106)
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+# the two encoders of the siamese pair are independent until their feature vectors meet: with ENC_STREAMS they are
+# enqueued on two streams, so the HBM-bound BN / pool passes of one overlap the tensor-bound convolutions of the other
+ENC_STREAMS = os.environ.get("DLIO_ENC_STREAMS", "0") == "1"
+# layers without pooling / residual: the gradient at the BN output is the incoming gradient (masked by the ReLU inside
+# the apply pass), so backward pass 1 only takes the sums and dz never goes through HBM
+SKIP_DZ = os.environ.get("DLIO_SKIP_DZ", "1") == "1"
 # tcgen05 (3xTF32) convolution path: stride-1 convolutions whose input has a multiple of 32 channels
 USE_TC = True
 # tcgen05 fp16 split path ("3xF16", twice the TF32 rate): stride-1 convolutions, input channels a multiple of 64;
@@ -51,16 +61,19 @@ def pair_ok(x, cin, cout, kh, kw, stride):
             and x.pw // 2 >= (1 if kw > 1 else 0) and x.ph >= (kh - 1) // 2 and (sh == 1 or x.h > 1))
 
 
-def consumer_reads_f16_only(cin, cout, k, stride, w_out):
-    """True when a convolution (cin -> cout, kernel k, stride) that is the ONLY consumer of a tensor of width ``w_out``
-    runs its forward, dgrad and wgrad on the fp16 tensor-core kernels, so that the producer may skip the fp32 copy
-    (``conv_bn(out_f32=False)``) -- the stride-1 path or the pixel-pair view of a W-stride-2 layer."""
+def consumer_reads_f16_only(cin, cout, k, stride, w_out, h_out=2):
+    """True when a convolution (cin -> cout, kernel k, stride) that is the ONLY consumer of a tensor of extent
+    ``h_out`` x ``w_out`` runs its forward, dgrad and wgrad on the fp16 tensor-core kernels, so that the producer may
+    skip the fp32 copy (``conv_bn(out_f32=False)``) -- the stride-1 path or the pixel-pair view of a W-stride-2 layer.
+    Same predicate as ``f16_ok`` / ``pair_ok`` for a producer that pads for this consumer (even row pads >= 2 when
+    the consumer is W-strided)."""
     kh, kw = (k, k) if isinstance(k, int) else k
     if not (USE_TC and USE_F16) or cout % 64 != 0:
         return False
     if tuple(stride) == (1, 1):
         return cin % 64 == 0
-    return stride[1] == 2 and stride[0] in (1, 2) and kw in (1, 3, 5) and cin % 32 == 0 and w_out % 2 == 0
+    return (stride[1] == 2 and stride[0] in (1, 2) and kw in (1, 3, 5) and cin % 32 == 0 and w_out % 2 == 0
+            and (stride[0] == 1 or h_out > 1))
 
 
 def stream():
@@ -120,6 +133,8 @@ class Run:
         self.pgrad = {}           # parameter name -> gradient tensor (absent: written in place into param.grad)
         self.keep = []            # keeps Acts alive so that id() stays unique
         self.param_objs = {}      # name -> nn.Parameter (in-place parameter gradients)
+        self.bn_cfg = {}          # BatchNorm2d name -> (momentum or None, eps)
+        self.accum = []           # (param.grad, temporary): gradients to ADD after the tape (second backward)
         self._zblock, self._zoff = None, 0   # current block of the small-zeros arena
 
     # -- helpers
@@ -149,7 +164,14 @@ class Run:
         p = self.param_objs.get(name)
         if (p is not None and getattr(p, "_dlio_grad_inplace", False) and p.grad is not None and p.grad.is_contiguous()
                 and p.grad.shape == like.shape and p.grad.dtype == torch.float32):
-            return p.grad
+            if not getattr(p, "_dlio_grad_dirty", False):
+                p._dlio_grad_dirty = True      # cleared by FlatAdam.zero_grad()
+                return p.grad
+            # the slice already holds a gradient (a second backward before zero_grad(): gradient accumulation, as
+            # AccumulateGrad would do): the kernels write a temporary that is added after the tape
+            g = torch.empty_like(like)
+            self.accum.append((p.grad, g))
+            return g
         g = torch.empty_like(like)
         self.pgrad[name] = g
         return g
@@ -178,6 +200,9 @@ class Run:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        for dst, tmp in self.accum:
+            L.axpby(ptr(dst), 1.0, ptr(tmp), 1.0, ptr(dst), dst.numel(), stream())
+        self.accum = []
 
 
 def pack_input(run, view, c_pad, ph, pw):
@@ -271,13 +296,14 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     out_bound = run.empty(1) if (single and feat is None) else None
     if res is not None and out_bound is not None and res.bound is None:
         out_bound = None
-    L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), BN_MOMENTUM, BN_EPS,
+    momentum, eps = run.bn_cfg.get(bname, (BN_MOMENTUM, BN_EPS))
+    # num_batches_tracked is advanced by the finalize kernel itself; momentum None = cumulative average (-1)
+    nbt = run.buffers.get(bname + ".num_batches_tracked") if run.training else None
+    L.bn_finalize(ptr(stats), count, cout, ptr(gamma), ptr(beta), ptr(rm), ptr(rv),
+                  -1.0 if momentum is None else float(momentum), float(eps),
                   0 if run.training else 1, ptr(bnv[0]), ptr(bnv[1]), ptr(bnv[2]), ptr(bnv[3]),
-                  ptr(res.bound) if (res is not None and out_bound is not None) else None, ptr(out_bound), st)
-    if run.training:
-        nbt = run.buffers.get(bname + ".num_batches_tracked")
-        if nbt is not None:
-            nbt.add_(1)
+                  ptr(res.bound) if (res is not None and out_bound is not None) else None, ptr(out_bound),
+                  ptr(nbt), st)
     bp = L.BnPool(1 if relu else 0, res_mode if res is not None else 0, 3 if pool else 1,
                   pool[0] if pool else 1, pool[1] if pool else 1, c_off, 1)
     idx = ymax = None
@@ -344,7 +370,11 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
             windows = (3 if pool[0] == 1 else 2) * (3 if pool[1] == 1 else 2)
             L.pool_bwd_sums(dout_t4, ptr(dout), 0, cout, ptr(ymax), ptr(bnv[0]), ptr(bnv[1]), windows, ptr(sums), st)
         else:
-            dz = run.empty(n, ho, wo, cout)
+            # no pooling, no residual, one producer: dz is dout itself (masked by the ReLU, if any, inside the apply
+            # pass), so this pass only takes the sums
+            direct = (SKIP_DZ and src == L.GRAD_DIRECT and res is None and single and out.c == cout
+                      and dout.is_contiguous())
+            dz = None if direct else run.empty(n, ho, wo, cout)
             dres, dres_c, dres_acc = None, 0, 0
             if res is not None and res.needs_grad:
                 partial = res.c != cout
@@ -369,14 +399,15 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         dya.bound = run.empty(1) if dya.h2 is not None else None
         dgamma, dbeta = run.param_grad(bname + ".weight", gamma), run.param_grad(bname + ".bias", beta)
         dbs = run.zeros(cout, dtype=torch.float64) if b is not None else None
-        if dz is None:
+        if ymax is not None:
             L.bn_pool_bwd_apply(y.t4, ptr(y.t), bp, dout_t4, ptr(dout), ptr(idx), ptr(sums), count, ptr(bnv[2]),
                                 ptr(bnv[0]), ptr(bnv[1]), 1 if pre_relu else 0, 1 if run.training else 0, dya.t4,
                                 ptr(dya.t), ptr(dya.lo), ptr(dya.h2), ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
         else:
-            L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz), ptr(sums), count, ptr(bnv[2]), ptr(bnv[0]), ptr(bnv[1]),
-                           1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t), ptr(dya.lo), ptr(dya.h2),
-                           ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs), st)
+            L.bn_bwd_apply(y.t4, ptr(y.t), ptr(dz if dz is not None else dout), ptr(sums), count, ptr(bnv[2]),
+                           ptr(bnv[0]), ptr(bnv[1]), 1 if pre_relu else 0, 1 if run.training else 0, dya.t4, ptr(dya.t),
+                           ptr(dya.lo), ptr(dya.h2), ptr(dya.bound), ptr(dgamma), ptr(dbeta), ptr(dbs),
+                           ptr(bnv[3]), 1 if (dz is None and bpb.relu) else 0, st)
         if DEBUG_TRACE is not None and dz is not None:
             DEBUG_TRACE[(id(run), cname)] = dict(dout=dout.clone(), dz=dz.clone(), sums=sums.clone(),
                                                  dy=(dya.t if dya.t is not None else dya.h2).clone(), y=y.t.clone(),

@@ -22,6 +22,32 @@ def _check(t, name):
                            % (name, t.dtype, t.device))
 
 
+def _grad_buffer(p, pending):
+    """Where a backward kernel writes the gradient of input ``p``: returns (buffer, value handed to autograd).
+
+    Parameters owned by ``optim.FlatAdam`` carry ``_dlio_grad_inplace``: their ``.grad`` is a zeroed slice of the flat
+    gradient arena, so the kernel overwrites it directly and autograd gets None (no AccumulateGrad add kernel, no
+    temporary).  A slice that already holds a gradient (``_dlio_grad_dirty``: the parameter is used more than once in
+    a backward pass -- the IMU RNN runs once per window -- or gradients are being accumulated over several backward
+    passes) receives a temporary instead, added by ``_flush_pending``.  Anything else: a fresh tensor for autograd."""
+    g = p.grad
+    if (getattr(p, "_dlio_grad_inplace", False) and g is not None and g.is_contiguous() and g.shape == p.shape
+            and g.dtype == torch.float32):
+        if not getattr(p, "_dlio_grad_dirty", False):
+            p._dlio_grad_dirty = True
+            return g, None
+        tmp = torch.empty_like(g)
+        pending.append((g, tmp))
+        return tmp, None
+    buf = torch.empty(p.shape, device=p.device, dtype=torch.float32)
+    return buf, buf
+
+
+def _flush_pending(pending):
+    for dst, tmp in pending:
+        L.axpby(ptr(dst), 1.0, ptr(tmp), 1.0, ptr(dst), dst.numel(), _stream())
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, act):
@@ -38,6 +64,7 @@ class _Linear(torch.autograd.Function):
         L.linear_fwd(ptr(x2), x2.stride(0), ptr(w), ptr(b), m, n, k, act, ptr(y), n, _stream())
         ctx.save_for_backward(x2, w, y)
         ctx.act, ctx.has_b, ctx.in_shape = act, b is not None, x.shape
+        ctx.bias = b if (b is not None and b.requires_grad) else None     # the bias is only needed for its .grad slot
         return y.view(*x.shape[:-1], n)
 
     @staticmethod
@@ -50,12 +77,14 @@ class _Linear(torch.autograd.Function):
             dy2 = dy2.contiguous()
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_b and ctx.needs_input_grad[2]
         dx = torch.empty((m, k), device=dy.device, dtype=torch.float32) if need_x else None
-        dw = torch.empty_like(w) if need_w else None
-        db = torch.empty((n,), device=dy.device, dtype=torch.float32) if need_b else None
+        pending = []
+        dw, dw_ret = _grad_buffer(w, pending) if need_w else (None, None)
+        db, db_ret = _grad_buffer(ctx.bias, pending) if need_b else (None, None)
         scr = torch.empty((m, n), device=dy.device, dtype=torch.float32) if ctx.act != L.ACT_NONE else None
         L.linear_bwd(ptr(x2), x2.stride(0), ptr(w), ptr(y), n, ptr(dy2), dy2.stride(0), m, n, k, ctx.act, ptr(dx), k,
                      ptr(dw), ptr(db), ptr(scr), _stream())
-        return (dx.view(ctx.in_shape) if need_x else None), dw, db, None
+        _flush_pending(pending)
+        return (dx.view(ctx.in_shape) if need_x else None), dw_ret, db_ret, None
 
 
 def linear(x, w, b=None, act=None):
@@ -183,6 +212,7 @@ class _Rnn(torch.autograd.Function):
         L.rnn_fwd(kind, L_, D, B, T, I, H, L.ptr_array(ws), ptr(x), ptr(h0c), ptr(c0c), ptr(drop_mask), ptr(out),
                   ptr(hn), ptr(cn), ptr(reserve), _stream())
         ctx.save_for_backward(x, reserve, drop_mask, *ws)
+        ctx.weight_objs = weights      # the parameters themselves (their .grad slots), not contiguous copies
         ctx.dims = (kind, L_, D, B, T, I, H)
         ctx.has_state = (h0 is not None, c0 is not None)
         ctx.mark_non_differentiable()
@@ -193,7 +223,9 @@ class _Rnn(torch.autograd.Function):
         x, reserve, drop_mask, *ws = ctx.saved_tensors
         kind, L_, D, B, T, I, H = ctx.dims
         dev = x.device
-        grads = [torch.empty_like(w) for w in ws]
+        pending = []
+        bufs = [_grad_buffer(w, pending) for w in ctx.weight_objs]
+        grads = [b for b, _ in bufs]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dh0 = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
         dc0 = torch.empty((L_ * D, B, H), device=dev, dtype=torch.float32)
@@ -204,8 +236,10 @@ class _Rnn(torch.autograd.Function):
         dcn = dcn.contiguous() if (dcn is not None and kind == 0) else None
         L.rnn_bwd(kind, L_, D, B, T, I, H, L.ptr_array(ws), ptr(x), ptr(drop_mask), ptr(dout), ptr(dhn), ptr(dcn),
                   ptr(reserve), L.ptr_array(grads), ptr(dx), ptr(dh0), ptr(dc0), ptr(scratch), nscr, _stream())
+        _flush_pending(pending)
+        rets = [r if need else None for (_, r), need in zip(bufs, ctx.needs_input_grad[8:])]
         return (dx, dh0 if ctx.has_state[0] else None, dc0 if ctx.has_state[1] else None,
-                None, None, None, None, None, *grads)
+                None, None, None, None, None, *rets)
 
 
 def rnn(x, state, kind, num_layers, bidirectional, hidden_size, weights, dropout_p=0.0, training=False):

@@ -35,7 +35,10 @@ class GraphedTrainStep:
     then happens on the current stream.  When the current stream is the default stream, a side stream is used and no
     eager step may have run before."""
 
-    def __init__(self, fwd_loss, example, zero_grad, warmup=3):
+    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None):
+        """``model`` (optional): its buffers (BatchNorm running statistics and ``num_batches_tracked``) and the dropout
+        call counter are snapshotted before the warm-up passes and restored before the capture, so that building the
+        graph leaves the training state exactly as an eager run would find it."""
         dev = next(iter(example.values())).device
         self.static_in = {k: torch.empty_like(v) for k, v in example.items()}
         for k, v in example.items():
@@ -49,10 +52,17 @@ class GraphedTrainStep:
             cur = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev) if cur == torch.cuda.default_stream(dev) else cur
             side.wait_stream(cur)
+            saved = [(b, b.clone()) for b in model.buffers()] if model is not None else []
+            drop0 = Fn._drop_counter[0]
             with torch.cuda.stream(side):                      # warm-up off the default stream, as capture requires
                 for _ in range(warmup):
                     zero_grad()
                     fwd_loss(self.static_in).backward()
+                with torch.no_grad():
+                    for b, v in saved:
+                        b.copy_(v)
+            Fn._drop_counter[0] = drop0
+            del saved
             cur.wait_stream(side)
             torch.cuda.synchronize(dev)
             n0 = L.launch_count()

@@ -129,7 +129,11 @@ def load_state_dict(module, model_path):
     net_logger.info("loading %s's state dict (%s).", getattr(module, "name", type(module).__name__), model_path)
     if not os.path.isfile(model_path):
         net_logger.error("%s: No model found (%s)!", getattr(module, "name", type(module).__name__), model_path)
-    dev = next(iter(module.parameters())).device
+    # a parameter-free module (DeepLIOFusionCat) has no tensor to take the device from
+    first = next(iter(module.parameters()), None)
+    if first is None:
+        first = next(iter(module.buffers()), None)
+    dev = first.device if first is not None else getattr(module, "device", "cpu")
     state = torch.load(model_path, map_location=dev)
     module.load_state_dict(state["state_dict"])
 

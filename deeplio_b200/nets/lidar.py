@@ -36,6 +36,14 @@ class _Encoder(ParamTree):
     def _bn(self, name, c, momentum=0.1):
         return self.put(name, nn.BatchNorm2d(c, momentum=momentum))
 
+    def bn_cfg(self):
+        """BatchNorm2d name -> (momentum, eps) as the modules declare them (engine.conv_bn)."""
+        cfg = self.__dict__.get("_bn_cfg")
+        if cfg is None:
+            cfg = {k: (m.momentum, m.eps) for k, m in self.named_modules() if isinstance(m, nn.BatchNorm2d)}
+            self.__dict__["_bn_cfg"] = cfg
+        return cfg
+
     def program(self, run, x, feat, ld, off):
         raise NotImplementedError
 
@@ -94,10 +102,11 @@ class FlowNetEncoder(_Encoder):
             else:
                 cout, (ncout, nk, nstride) = self.SPEC[i][1], self.SPEC[i + 1][1:]
                 nkh, nkw = (nk, nk) if isinstance(nk, int) else nk
-                kw = k if isinstance(k, int) else k[1]
+                kh, kw = (k, k) if isinstance(k, int) else k
                 w_out = (t.w + 2 * ((kw - 1) // 2) - kw) // stride[1] + 1
+                h_out = (t.h + 2 * ((kh - 1) // 2) - kh) // stride[0] + 1
                 # the next layer is the only consumer: no fp32 copy when it runs on the fp16 tensor-core kernels
-                f32 = not E.consumer_reads_f16_only(cout, ncout, nk, nstride, w_out)
+                f32 = not E.consumer_reads_f16_only(cout, ncout, nk, nstride, w_out, h_out)
                 if nstride[1] == 2:
                     # the next layer is W-strided: pixel-pair layout, even row pads (engine.pair_ok)
                     t = E.conv_bn(run, t, name + ".0", name + ".1", stride, out_pad=((nkh - 1) // 2, 2), out_group=2,
@@ -174,6 +183,10 @@ class PointSegEncoder(_Encoder):
 
     def __init__(self, cin, bypass="simple", bn_d=0.1):
         super().__init__()
+        if bypass not in (None, False, "simple"):
+            # the reference's "complex" bypass adds a 1x1 `upsample` convolution per Fire (pointseg_modules.py
+            # :110-113,134-137): different parameters and state_dict keys -- not built here, so refuse loudly
+            raise ValueError("lidar-feat-pointseg: bypass=%r is not implemented (supported: null, 'simple')" % (bypass,))
         self.bypass = bypass
         self._conv("conv1a.0", cin, 64, (3, 5), True)
         self._bn("conv1a.1", 64, bn_d)
@@ -239,14 +252,18 @@ class _EncoderPair(torch.autograd.Function):
         feats = [torch.empty((n, 2 * c if cat else c), device=dev, dtype=torch.float32)]
         feats.append(feats[0] if cat else torch.empty((n, c), device=dev, dtype=torch.float32))
         runs = []
+        streams = _fork(dev)
         for e, view in enumerate((xyz, normals)):
             pd = dict(zip(names[e], groups[e]))
             bufs = dict(enc[e].named_buffers())
             run = E.Run(pd, bufs, dev, net.training, record)
             run.param_objs = dict(enc[e].named_parameters())
-            x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)   # row pads of 4 pixels: space-to-depth first layer
-            enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)
+            run.bn_cfg = enc[e].bn_cfg()
+            with torch.cuda.stream(streams[e]):
+                x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)   # row pads of 4 pixels: space-to-depth first layer
+                enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)
             runs.append(run)
+        _join(streams)
         if cat:
             y = feats[0]
         else:
@@ -262,16 +279,42 @@ class _EncoderPair(torch.autograd.Function):
         dy = dy.contiguous()
         runs, feats = ctx.runs, ctx.feats
         grads = []
+        ds = [dy, dy]
+        if ctx.fusion not in ("cat", "add"):
+            ds[1] = torch.empty_like(dy)
+            L.axpby(ptr(dy), -1.0, ptr(dy), 0.0, ptr(ds[1]), dy.numel(), E.stream())
+        streams = _fork(dy.device)
         for e, run in enumerate(runs):
-            d = dy
-            if e == 1 and ctx.fusion not in ("cat", "add"):
-                d = torch.empty_like(dy)
-                L.axpby(ptr(dy), -1.0, ptr(dy), 0.0, ptr(d), dy.numel(), E.stream())
-            run.fgrad[id(feats[e])] = d
-            run.backward()
+            run.fgrad[id(feats[e])] = ds[e]
+            with torch.cuda.stream(streams[e]):
+                run.backward()
             grads.extend(run.pgrad.get(k) for k in ctx.names[e])
+        _join(streams)
         ctx.runs = None
         return (None, None, None, None, *grads)
+
+
+_side_streams = {}
+
+
+def _fork(dev):
+    """Streams the two encoders are enqueued on: (current, current) or, with engine.ENC_STREAMS, (current, side) with
+    the side stream ordered after everything enqueued on the current one so far.  Everything a run allocates stays
+    on its stream for the forward AND the backward pass, and every fork starts with this wait, so the caching
+    allocator's per-stream reuse is safe."""
+    cur = torch.cuda.current_stream(dev)
+    if not E.ENC_STREAMS:
+        return (cur, cur)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(cur)
+    return (cur, side)
+
+
+def _join(streams):
+    if streams[1] is not streams[0]:
+        streams[0].wait_stream(streams[1])
 
 
 class BaseLidarFeatNet(BaseNet):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 5
+#define DLIO_ABI_VERSION 6
 
 typedef enum {
     DLIO_OK = 0,
@@ -187,11 +187,14 @@ int dlio_pack_f16(const float *src, long long rows, int c, float *bound, void *d
  *   out_bound (optional, needs stats): an upper bound of |scale*y + shift| over the tensor (+ *res_bound when
  *   a residual will be added), from |y - mean_b| <= sqrt(count * var_b); it scales the fp16 planes that
  *   dlio_bn_act_pool_fwd writes.
+ *   num_batches_tracked (optional, device int64, the BatchNorm2d buffer): incremented in train mode by the kernel
+ *   itself (no separate add launch); momentum < 0 means nn.BatchNorm2d(momentum=None): the cumulative average
+ *   with factor 1 / num_batches_tracked.
  */
 int dlio_bn_finalize(const double *stats, long long count, int c, const float *gamma, const float *beta,
                      float *running_mean, float *running_var, float momentum, float eps, int use_running,
                      float *mean, float *invstd, float *scale, float *shift, const float *res_bound,
-                     float *out_bound, void *stream);
+                     float *out_bound, long long *num_batches_tracked, void *stream);
 
 typedef struct {
     int relu;       /* 1: apply ReLU after scale*y + shift (+ residual if res_mode == 1) */
@@ -240,12 +243,15 @@ int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float 
  * max |dz|): dy as packed fp16 split planes, and the bound it was scaled from (OUTPUT, for dgrad / wgrad);
  * dy_hi may then be NULL.  dy_t.h == y.h: dy on y's own grid.  dy_t.h == the input height of an H-stride-2
  * convolution ((dy_t.h - 1) / 2 + 1 == y.h): y row i is written to dy row 2 i and the odd rows are zero, which is
- * the dy operand of that convolution's backward run as a stride-1 convolution over its input grid. */
+ * the dy operand of that convolution's backward run as a stride-1 convolution over its input grid.
+ * post_relu != 0 (needs `shift`): `dz` is the gradient of the ReLU OUTPUT (BN -> ReLU layers, base_net.py:55-71) and
+ * the kernel masks it with scale*y + shift > 0 itself -- pass 1 then runs with dz == NULL (sums only) and the masked
+ * gradient never goes through HBM. */
 int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
                       long long count, const float *scale, const float *mean, const float *invstd,
                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
                       void *dy_h2, float *dy_bound, float *dgamma, float *dbeta, double *dbias_sums,
-                      void *stream);
+                      const float *shift, int post_relu, void *stream);
 /* The two backward passes of a layer  conv -> (ReLU) -> BN -> 3x3 max-pool  (no ReLU / residual between BN and pool:
  * Simple-1, lidar_feat_nets.py:306-322) without materialising dz:
  *   dlio_pool_bwd_sums: the BN-backward sums from the POOLED side -- every dout is routed to exactly one input, so

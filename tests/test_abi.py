@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in decl if s not in exported]
     assert not missing, missing
     assert sorted(lib.EXPORTS) == decl          # the ctypes binding covers the whole header
-    assert lib.abi_version() == lib.ABI_VERSION == 5
+    header = open(os.path.join(ROOT, "include", "deeplio_b200.h")).read()
+    assert lib.abi_version() == lib.ABI_VERSION == int(re.search(r"#define DLIO_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_library_is_sm100a_with_no_other_arch(lib):
@@ -97,7 +98,7 @@ def test_install_rebinds_reference_registry():
         setattr(fake, n, object)
     sys.modules["fake_ref_nets"] = fake
     from deeplio_b200 import nets
-    from deeplio_b200.install import install
+    from deeplio_b200.dropin import install
     done = install("fake_ref_nets")
     assert set(done) == {"DeepLIO", "LidarSimpleFeat1", "OdomFeatRNN"}
     assert fake.LidarSimpleFeat1 is nets.LidarSimpleFeat1

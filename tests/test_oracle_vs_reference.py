@@ -44,3 +44,39 @@ def test_oracle_equals_reference(kw, B, S, H, W, T, tmp_path, monkeypatch):
     for k, v in model.state_dict().items():
         if "running_" in k:
             assert torch.allclose(v, sd_after[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_install_into_the_real_reference_factory(tmp_path, monkeypatch):
+    """``deeplio_b200.install()`` rebinds the class names the UNMODIFIED reference factory resolves from its module
+    globals (nets/__init__.py:6-10,95-102,141-144,173-176,206-209); the reference's own ``nets.get_model`` then
+    builds deeplio_b200 modules whose state_dict keys and shapes are the reference's (checkpoint compatibility)."""
+    import argparse
+    monkeypatch.chdir(tmp_path)
+    import deeplio_b200
+    from deeplio_b200 import nets as ours
+    from deeplio_b200.dropin import _NAMES
+    ref_nets, ref_misc = ref_loader.import_reference()
+    cfg = ref_loader.patch_cfg(make_cfg(height=16, width=64, seq=2, lidar="lidar-feat-simple-1", imu="imu-feat-rnn",
+                                        odom="odom-feat-rnn", odom_hidden=32))
+    ref_keys = {k: tuple(v.shape) for k, v in ref_loader.build_reference_model(cfg, 16, 64).state_dict().items()}
+    saved = {n: getattr(ref_nets, n) for n in _NAMES if hasattr(ref_nets, n)}
+    try:
+        done = deeplio_b200.install()
+        assert set(done) == set(saved)
+        ref_misc.build_config_container(cfg, argparse.Namespace(device="cpu", batch_size=1))
+        model = ref_nets.get_model(input_shape=(3, 16, 64), cfg=cfg, device="cpu")    # the reference's factory code
+        assert type(model) is ours.DeepLIO
+        assert type(model.lidar_feat_net) is ours.LidarSimpleFeat1
+        assert type(model.imu_feat_net) is ours.ImufeatRNN0
+        assert type(model.fusion_net) is ours.DeepLIOFusionSoft
+        assert type(model.odom_feat_net) is ours.OdomFeatRNN
+        got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        assert got == ref_keys
+        # what trainer.py:60-61,156,165-170 reads
+        assert model.name == "deeplio" and [n.name for n in model.get_feat_networks()] == [
+            "odomfeatrnn", "deepliofusionsoft", "imufeatrnn0", "lidarsimplefeat1"]
+        # a reference checkpoint loads into it
+        model.load_state_dict(O.synthetic_state(cfg, seed=3))
+    finally:
+        for n, cls in saved.items():
+            setattr(ref_nets, n, cls)
