@@ -41,6 +41,24 @@ USE_F16 = True
 FUSED_POOL_BWD = True
 # debugging aid (scripts/repeat_parity.py): when a dict, every conv_bn backward stores clones of its tensors here
 DEBUG_TRACE = None
+# test aid: when a dict, every conv_bn forward stores the ReLU mask of its layer (bool, NCHW) under
+# Run.trace_prefix + conv name, so that tests can count mask disagreements with the oracle (oracle.TRACE)
+MASK_TRACE = None
+
+
+def _trace_mask(run, cname, y, bnv, pre_relu, relu, res, res_mode, c_off):
+    if pre_relu:
+        m = y.t > 0                                       # y holds relu(conv + bias): positive <=> the ReLU passed it
+    elif relu:
+        v = torch.addcmul(bnv[3], y.t, bnv[2])
+        if res is not None and res_mode == 1:
+            if res.t is None:
+                return
+            v = v + res.t[:, res.ph:res.ph + res.h, res.pw:res.pw + res.w, c_off:c_off + y.c]
+        m = v > 0
+    else:
+        return
+    MASK_TRACE[getattr(run, "trace_prefix", "") + cname] = m.permute(0, 3, 1, 2).cpu()
 
 
 def tc_ok(cin, cout, stride):
@@ -304,6 +322,8 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                   0 if run.training else 1, ptr(bnv[0]), ptr(bnv[1]), ptr(bnv[2]), ptr(bnv[3]),
                   ptr(res.bound) if (res is not None and out_bound is not None) else None, ptr(out_bound),
                   ptr(nbt), st)
+    if MASK_TRACE is not None:
+        _trace_mask(run, cname, y, bnv, pre_relu, relu, res, res_mode, c_off)
     bp = L.BnPool(1 if relu else 0, res_mode if res is not None else 0, 3 if pool else 1,
                   pool[0] if pool else 1, pool[1] if pool else 1, c_off, 1)
     idx = ymax = None

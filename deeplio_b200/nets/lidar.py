@@ -259,6 +259,7 @@ class _EncoderPair(torch.autograd.Function):
             run = E.Run(pd, bufs, dev, net.training, record)
             run.param_objs = dict(enc[e].named_parameters())
             run.bn_cfg = enc[e].bn_cfg()
+            run.trace_prefix = "encoder%d." % (e + 1)
             with torch.cuda.stream(streams[e]):
                 x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)   # row pads of 4 pixels: space-to-depth first layer
                 enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)

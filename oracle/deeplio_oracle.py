@@ -46,6 +46,18 @@ def _bn(sd, p, x, training):
     return y
 
 
+# When a dict, every ReLU of the LiDAR encoders stores its mask (input > 0, bool NCHW) here under the name of the
+# convolution that feeds it (tests count ReLU-mask disagreements between the B200 path and this oracle:
+# tests/test_gpu_model.py, tests/test_gpu_fullsize.py)
+TRACE = None
+
+
+def _relu(x, key):
+    if TRACE is not None:
+        TRACE[key] = x.detach() > 0
+    return F.relu(x)
+
+
 def _conv(sd, p, x, stride=(1, 1)):
     w = sd[p + ".weight"]
     pad = ((w.shape[2] - 1) // 2, (w.shape[3] - 1) // 2)
@@ -60,7 +72,7 @@ def _drop(x, p, training):
 def simple1_encoder(sd, p, x, training, bypass=False):
     """FeatureNetSimple1 (lidar_feat_nets.py:279-342): conv -> ReLU -> BN, ceil-mode pools."""
     def blk(i, t, stride=(1, 1)):
-        return _bn(sd, "%sbn%d" % (p, i), F.relu(_conv(sd, "%sconv%d" % (p, i), t, stride)), training)
+        return _bn(sd, "%sbn%d" % (p, i), _relu(_conv(sd, "%sconv%d" % (p, i), t, stride), "%sconv%d" % (p, i)), training)
 
     def pool(t, stride):
         return F.max_pool2d(t, 3, stride, 1, ceil_mode=True)
@@ -93,7 +105,7 @@ def flownet_encoder(sd, p, x, training):
     conv(no bias) -> BN -> ReLU, nine times, then global mean."""
     t = x
     for name, stride in _FLOWNET:
-        t = F.relu(_bn(sd, "%s%s.1" % (p, name), _conv(sd, "%s%s.0" % (p, name), t, stride), training))
+        t = _relu(_bn(sd, "%s%s.1" % (p, name), _conv(sd, "%s%s.0" % (p, name), t, stride), training), "%s%s.0" % (p, name))
     return t.mean(dim=(2, 3))
 
 
@@ -103,25 +115,25 @@ _RESNET_LAYERS = [("layer1", 3, (1, 2)), ("layer2", 3, (1, 2)), ("layer3", 3, (2
 def resnet_encoder(sd, p, x, training):
     """ResNetEncoder (resnet.py:36-108) over torchvision BasicBlock
     (torchvision/models/resnet.py:59-105, v0.26.0)."""
-    t = F.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x), training))
+    t = _relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x), training), p + "conv1")
     t = F.max_pool2d(t, 3, (1, 2), 1)
     for lname, nblk, stride in _RESNET_LAYERS:
         for b in range(nblk):
             q = "%s%s.%d." % (p, lname, b)
             s = stride if b == 0 else (1, 1)
-            o = F.relu(_bn(sd, q + "bn1", _conv(sd, q + "conv1", t, s), training))
+            o = _relu(_bn(sd, q + "bn1", _conv(sd, q + "conv1", t, s), training), q + "conv1")
             o = _bn(sd, q + "bn2", _conv(sd, q + "conv2", o), training)
             if (q + "downsample.0.weight") in sd:
                 t = _bn(sd, q + "downsample.1", _conv(sd, q + "downsample.0", t, s), training)
-            t = F.relu(o + t)
+            t = _relu(o + t, q + "conv2")
     return t.mean(dim=(2, 3))
 
 
 def _fire(sd, q, x, training, bypass):
     """Fire (pointseg_modules.py:86-142): squeeze1x1 -> {expand1x1 || expand3x3} -> cat (+x)."""
-    s = F.relu(_bn(sd, q + "squeeze_bn", _conv(sd, q + "squeeze", x), training))
-    e1 = F.relu(_bn(sd, q + "expand1x1_bn", _conv(sd, q + "expand1x1", s), training))
-    e3 = F.relu(_bn(sd, q + "expand3x3_bn", _conv(sd, q + "expand3x3", s), training))
+    s = _relu(_bn(sd, q + "squeeze_bn", _conv(sd, q + "squeeze", x), training), q + "squeeze")
+    e1 = _relu(_bn(sd, q + "expand1x1_bn", _conv(sd, q + "expand1x1", s), training), q + "expand1x1")
+    e3 = _relu(_bn(sd, q + "expand3x3_bn", _conv(sd, q + "expand3x3", s), training), q + "expand3x3")
     out = torch.cat([e1, e3], 1)
     if bypass == "simple" and out.shape[1] == x.shape[1]:
         out = out + x
@@ -143,7 +155,7 @@ _POINTSEG = [("fire_blk1", ["F", "F", "S", "P12"]), ("fire_blk2", ["F", "F", "S"
 
 def pointseg_encoder(sd, p, x, training, bypass="simple"):
     """PSEncoder (pointseg_net.py:18-71)."""
-    t = F.relu(_bn(sd, p + "conv1a.1", _conv(sd, p + "conv1a.0", x, (1, 2)), training))
+    t = _relu(_bn(sd, p + "conv1a.1", _conv(sd, p + "conv1a.0", x, (1, 2)), training), p + "conv1a.0")
     t = F.max_pool2d(t, 3, (1, 2), 1)
     for bname, entries in _POINTSEG:
         for i, e in enumerate(entries):

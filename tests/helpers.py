@@ -39,3 +39,60 @@ def oracle_train_step(cfg, sd, inputs):
 def rel_err(a, b, floor=0.0):
     """max|a-b| / (max|b| + floor)."""
     return (a - b).abs().max().item() / (b.abs().max().item() + floor + 1e-30)
+
+
+# ----------------------------------------------------------------------------- gradient-parity bookkeeping
+def diag(record):
+    """Appends one JSON line to gpurun_out/parity_diag.jsonl (the per-tensor numbers behind the parity assertions
+    travel back from the GPU box with the rest of gpurun_out/)."""
+    import json
+    root = os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_diag.jsonl"), "a") as f:
+            f.write(json.dumps(record) + "\n")
+    except OSError:
+        pass
+
+
+def f64_state(sd, inputs):
+    return ({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()},
+            tuple(t.double() for t in inputs))
+
+
+def perturbed_grads(cfg, sd64, in64, draws):
+    """fp64 oracle gradients under relative perturbations of every weight and input: [(seed, amplitude), ...]."""
+    out = []
+    for seed, amp in draws:
+        gen = torch.Generator().manual_seed(seed)
+
+        def jitter(t):
+            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
+        out.append(oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))[2])
+    return out
+
+
+def count_relu_flips(ours, oracle, prefix="lidar_feat_net."):
+    """ReLU-mask disagreements between the B200 path (engine.MASK_TRACE: bool masks, NCHW) and the oracle
+    (oracle.TRACE, same form): {layer: (flipped elements, total elements)} for the layers both sides recorded."""
+    flips = {}
+    for k, m in ours.items():
+        ref = oracle.get(prefix + k)
+        if ref is None or tuple(ref.shape) != tuple(m.shape):
+            continue
+        flips[k] = (int((m != ref).sum()), m.numel())
+    return flips
+
+
+def grad_rows(grads, g64, g32=None, gperts=()):
+    """Per-tensor parity numbers: [(name, err, scale, e_ref, e_pert)], all max-abs against the fp64 gradient."""
+    rows = []
+    for k, g in grads.items():
+        ref = g64[k]
+        scale = ref.abs().max().item()
+        e = (g.double() - ref).abs().max().item()
+        e_ref = (g32[k].double() - ref).abs().max().item() if g32 is not None else 0.0
+        e_pert = max(((gp[k] - ref).abs().max().item() for gp in gperts), default=0.0)
+        rows.append((k, e, scale, e_ref, e_pert))
+    return rows

@@ -8,7 +8,7 @@ import torch
 
 from oracle import deeplio_oracle as O
 from oracle.configs import make_cfg
-from tests.helpers import rel_err
+from tests.helpers import count_relu_flips, diag, f64_state, grad_rows, oracle_train_step, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -68,6 +68,65 @@ def test_full_resolution_forward_parity_and_properties(kw):
         parts = [model(dev(tuple(t[i:i + 1] for t in inputs))) for i in range(B)]
     assert rel_err(torch.cat([p for p, _ in parts]).cpu(), pb.cpu()) < 1e-5
     assert rel_err(torch.cat([o for _, o in parts]).cpu(), ob.cpu()) < 1e-5
+
+
+def _full_size_gradient_parity(kw, B, S, T, odom_hidden, tag):
+    """Train-mode forward + backward at 64x2048 against an fp64 run of the oracle: forward at 2e-5, EVERY parameter
+    gradient at the plain 2e-4 bar (of the tensor's largest entry).  At this size BatchNorm averages over 10^5 .. 10^6
+    samples per channel, so there is no conditioning excuse: the only tolerated deviation is a tensor whose layer (or
+    a layer downstream of it in the backward pass) has RECORDED ReLU-mask flips against the oracle, and even then at
+    most 2e-3.  This is where the split-K wgrad over ~2 M rows, its swapped-operand mode, the row-decimating strided
+    path and the space-to-depth first layer are gradient-checked at their real shapes."""
+    from deeplio_b200 import engine as E
+    cfg = make_cfg(height=H, width=W, seq=S, odom_hidden=odom_hidden, **kw)
+    sd = O.synthetic_state(cfg, seed=31)
+    inputs = O.synthetic_batch(B, S, H, W, T, seed=31)
+    model = build(cfg, B, sd)
+    model.train()
+    E.MASK_TRACE = {}
+    try:
+        pos, ori = model(dev(inputs))
+        mtrace = E.MASK_TRACE
+    finally:
+        E.MASK_TRACE = None
+    ((pos ** 2).sum() + (ori ** 2).sum()).backward()
+    torch.cuda.synchronize()
+    ours = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    pos, ori = pos.detach().cpu(), ori.detach().cpu()
+    del model
+    torch.cuda.empty_cache()
+    sd64, in64 = f64_state(sd, inputs)
+    O.TRACE = {}
+    try:
+        opos, oori, g64, _ = oracle_train_step(cfg, sd64, in64)
+        otrace = O.TRACE
+    finally:
+        O.TRACE = None
+    assert rel_err(pos.double(), opos) < 2e-5
+    assert rel_err(ori.double(), oori) < 2e-5
+    flips = count_relu_flips(mtrace, otrace)
+    n_flips = sum(f for f, _ in flips.values())
+    rows = grad_rows(ours, g64)
+    gmax = max(s_ for _, _, s_, _, _ in rows)
+    over = [(k, e / (s_ + 1e-30)) for k, e, s_, _, _ in rows if e > 2e-4 * s_ + 1e-6 * gmax]
+    worst = max(rows, key=lambda r: r[1] / (r[2] + 1e-30))
+    diag({"test": "fullsize_grad", "case": tag, "tensors": len(rows), "over_2e-4": over, "relu_flips": n_flips,
+          "relu_elems": sum(t for _, t in flips.values()), "worst": (worst[0], worst[1] / (worst[2] + 1e-30)),
+          "flips_by_layer": {k: f for k, (f, _) in flips.items() if f}})
+    for k, rel in over:
+        assert k.startswith("lidar_feat_net.encoder") and n_flips > 0 and rel <= 2e-3, (k, rel, n_flips)
+    assert len(over) <= len(rows) // 10, over
+
+
+@pytest.mark.parametrize("kw", NETS, ids=lambda k: k["lidar"])
+def test_full_resolution_gradient_parity(kw):
+    _full_size_gradient_parity(kw, 2, 2, 15, 256, kw["lidar"] + "_b2")
+
+
+def test_bench_batch_gradient_parity():
+    """BASELINE.json configs[1] at its real batch: Simple-1 + bi-LSTM + LSTM odometry net (hidden 1024), batch 8,
+    S = 2 -- the shapes bench.py times."""
+    _full_size_gradient_parity(dict(lidar="lidar-feat-simple-1"), 8, 2, 15, 1024, "cfg1_b8")
 
 
 def test_one_adam_step_matches_oracle():
@@ -191,4 +250,4 @@ def test_reference_default_resolution_57x720(kw):
     # largest entry.
     assert len(over) <= max(1, len(params) // 50), over
     assert all(e <= 5e-2 * scale + 1e-5 * gmax for _, e, _, scale in over), over
-    assert n_tight >= 0.5 * len(params), (n_tight, len(params))
+    assert n_tight >= 0.9 * len(params), (n_tight, len(params))

@@ -11,7 +11,8 @@ import pytest
 import torch
 
 from oracle import deeplio_oracle as O
-from tests.helpers import GOLDEN_CASES, case_setup, load_golden, oracle_train_step, rel_err
+from tests.helpers import (GOLDEN_CASES, case_setup, count_relu_flips, diag, f64_state, grad_rows, load_golden,
+                           oracle_train_step, perturbed_grads, rel_err)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -40,7 +41,13 @@ def test_model_matches_oracle_and_golden(name):
     cfg, sd, inputs = case_setup(rec)
     model = build_b200_model(cfg, rec["H"], rec["W"], rec["B"], sd)
     model.train()
-    pos, ori = model(to_dev(inputs))
+    from deeplio_b200 import engine as E
+    E.MASK_TRACE = {}
+    try:
+        pos, ori = model(to_dev(inputs))
+        mtrace = E.MASK_TRACE
+    finally:
+        E.MASK_TRACE = None
     loss = (pos ** 2).sum() + (ori ** 2).sum()
     loss.backward()
     torch.cuda.synchronize()
@@ -50,47 +57,50 @@ def test_model_matches_oracle_and_golden(name):
     opos, oori, ograds, osd = oracle_train_step(cfg, sd, inputs)
     assert rel_err(pos.detach().cpu(), opos) < FWD_TOL
     assert rel_err(ori.detach().cpu(), oori) < FWD_TOL
-    # gradients: every parameter, against an fp64 evaluation of the oracle.  Most tensors are held to GRAD_TOL
-    # (2e-4 of the tensor's largest entry).  A few are ill-conditioned in ANY fp32 arithmetic: ReLU / arg-max
-    # decisions flip with round-off, and in these small fixtures BatchNorm runs over as few as 32 samples, so a
-    # near-constant channel multiplies noise by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5
-    # turns a 1e-6 input change into a 30 % change of its weight gradient).  The bar per tensor is therefore
-    # max(GRAD_TOL, 4 x its measured sensitivity), where the sensitivity is the larger of (a) the fp32
-    # reference's own distance from fp64 and (b) the largest change of the fp64 gradient over several draws of a
-    # 2e-6 .. 4e-6 relative perturbation of every weight and input (the size of fp32 / split-precision round-off).
-    # Several draws, because the dominant effect is discrete: one ReLU input within ~1e-6 of zero flips its mask
-    # in some draws and not in others (scripts/repeat_parity.py shows the B200 path itself landing on either
-    # side from run to run, through the summation order of the fp64 statistics atomics), and with 64 samples
-    # per channel one flip moves that layer's gradients by 10-30 %.
-    def f64(t):
-        return t.double() if t.is_floating_point() else t
-    sd64 = {k: f64(v) for k, v in sd.items()}
-    in64 = tuple(t.double() for t in inputs)
-    _, _, g64, _ = oracle_train_step(cfg, sd64, in64)
-    gperts = []
-    for seed, amp in ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)):
-        gen = torch.Generator().manual_seed(seed)
-
-        def jitter(t):
-            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
-        gperts.append(oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))[2])
+    # gradients: every parameter, against an fp64 evaluation of the oracle.  The plain bar is GRAD_TOL (2e-4 of the
+    # tensor's largest entry) and at least 90 % of the tensors must meet it.  A few are ill-conditioned in ANY fp32
+    # arithmetic: (a) in these small fixtures BatchNorm runs over as few as 32 samples, so a near-constant channel
+    # multiplies round-off by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5 turns a 1e-6 input change
+    # into a 30 % change of its weight gradient) -- visible as a large response of the fp64 oracle itself to a
+    # 2e-6 .. 4e-6 relative perturbation of every weight and input (e_pert), or as the fp32 oracle missing the bar
+    # (e_ref); (b) a ReLU input within ~1e-6 of zero flips its mask -- RECORDED here by comparing the masks the B200
+    # path applied (engine.MASK_TRACE) with the oracle's ReLU inputs.  A tensor over the plain bar must show one of
+    # these causes, and stays under 4 x its measured sensitivity.
+    sd64, in64 = f64_state(sd, inputs)
+    O.TRACE = {}
+    try:
+        _, _, g64, _ = oracle_train_step(cfg, sd64, in64)
+        otrace = O.TRACE
+    finally:
+        O.TRACE = None
+    flips = count_relu_flips(mtrace, otrace)
+    n_flips = sum(f for f, _ in flips.values())
+    gperts = perturbed_grads(cfg, sd64, in64, ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)))
     gmax = max(float(n) for n, _ in rec["grads"].values())
     params = dict(model.named_parameters())
     assert set(params) == set(ograds)
-    n_tight = 0
-    for k, p in params.items():
-        g = p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])
-        scale = g64[k].abs().max().item()
-        e_ref = (ograds[k].double() - g64[k]).abs().max().item()
-        e_pert = max((gp[k] - g64[k]).abs().max().item() for gp in gperts)
-        e_ours = (g.double() - g64[k]).abs().max().item()
+    ours = {k: (p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])) for k, p in params.items()}
+    rows = grad_rows(ours, g64, ograds, gperts)
+    n_tight, worst = 0, (None, 0.0)
+    for k, e_ours, scale, e_ref, e_pert in rows:
         sens = max(e_ref, e_pert)
+        tight = e_ours <= GRAD_TOL * scale + 1e-5 * gmax
+        n_tight += tight
+        if e_ours / (scale + 1e-30) > worst[1]:
+            worst = (k, e_ours / (scale + 1e-30))
         assert e_ours <= max(GRAD_TOL * scale, 4 * sens) + 1e-5 * gmax, (k, e_ours, e_ref, e_pert, scale)
-        n_tight += e_ours <= GRAD_TOL * scale + 1e-5 * gmax
+        if not tight:
+            in_encoder = k.startswith("lidar_feat_net.encoder")
+            assert sens > GRAD_TOL * scale or (in_encoder and n_flips > 0), \
+                ("over the plain bar without a recorded cause", k, e_ours, e_ref, e_pert, scale, n_flips)
         norm, head = rec["grads"][k]
         bar = GRAD_TOL + 4 * sens / (scale + 1e-30)
-        assert abs(g.double().norm().item() - float(norm)) <= bar * float(norm) + 1e-5 * gmax, k
-    assert n_tight >= 0.5 * len(params)
+        assert abs(ours[k].double().norm().item() - float(norm)) <= bar * float(norm) + 1e-5 * gmax, k
+    diag({"test": "golden", "case": name, "tensors": len(rows), "n_tight": int(n_tight), "relu_flips": n_flips,
+          "relu_elems": sum(t for _, t in flips.values()), "worst": worst,
+          "over": [(k, e / (s_ + 1e-30), er / (s_ + 1e-30), ep / (s_ + 1e-30)) for k, e, s_, er, ep in rows
+                   if e > GRAD_TOL * s_ + 1e-5 * gmax]})
+    assert n_tight >= 0.9 * len(params), (n_tight, len(params))
     # dead-direction RNN parameters still get (zero) gradient tensors, so Adam + L2 decay updates them
     for k, p in params.items():
         if "_l1_reverse" in k:

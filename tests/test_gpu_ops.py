@@ -130,6 +130,11 @@ F16_CASES = [
     (2, 768, 64, 6, 10, (1, 1), True, 0, 1, 1.0, 1.0),
     (4, 64, 256, 8, 16, (3, 3), True, 0, 0, 40.0, 1.0),
     (1, 64, 64, 20, 70, (3, 3), False, 0, 0, 1.0, 1.0),
+    # real layer shapes of the BASELINE.json workloads (one or two 64x2048-derived images): Simple-1 conv2 (wgrad in
+    # swapped-operand mode, Cin = 64), conv4, conv6 -- split-K wgrad over 34 k .. 68 k padded rows, odd widths
+    (2, 64, 128, 64, 513, (3, 5), True, 1, 0, 1.0, 1.0),
+    (1, 128, 256, 64, 257, (3, 3), True, 1, 0, 1.0, 1.0),
+    (1, 256, 512, 33, 129, (3, 3), True, 1, 0, 1.0, 1.0),
 ]
 
 
@@ -304,6 +309,10 @@ PAIR_CASES = [
     (3, 64, 64, 6, 20, (3, 3), (1, 2), True),        # ResNet layer1.0.conv1 (Cout = 64: half-filled wgrad tile)
     (2, 64, 128, 7, 16, (1, 1), (2, 2), False),      # ResNet 1x1 downsample, odd height
     (1, 32, 64, 4, 8, (1, 1), (1, 2), False),
+    # real layer shapes: FlowNet conv4 (3x3 stride (2,2) on 256 x 64 x 256: row decimation in the epilogue, dy spread
+    # over the even rows) and conv2 (3x5 stride (1,2) on 64 x 64 x 1024)
+    (1, 256, 512, 64, 256, (3, 3), (2, 2), False),
+    (1, 64, 128, 64, 1024, (3, 5), (1, 2), False),
 ]
 
 
@@ -467,6 +476,65 @@ def test_conv_bn_block_vs_torch(cfg):
     assert relerr(run.pgrad["bn.bias"].cpu(), leaves[4].grad) < tol
     if res_mode:
         assert relerr(from_nhwc(run.agrad[id(ra)]), leaves[5].grad) < tol
+
+
+@pytest.mark.parametrize("k,stride,pre_relu,pool,first_ph", [
+    ((5, 7), (1, 2), True, (1, 2), 2),      # Simple-1 conv1 (+ ceil-mode pool); FlowNet conv1 has the same convolution
+    ((3, 5), (1, 2), False, (1, 2), 1),     # PointSeg conv1a
+    ((5, 7), (1, 1), False, (1, 2), 2),     # ResNet conv1 (stride 1: four output pixels per space-to-depth group)
+])
+def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_ph):
+    """The first convolution of every encoder at its real size (two 6-channel 64 x 2048 images): dlio_pack_input from
+    the strided [N, T, C, H, W] view, the 3xTF32 tcgen05 kernel over the space-to-depth view (csrc/conv_s2d.cu), BN,
+    pool; backward through the swapped-operand wgrad.  Against the same block in torch fp64."""
+    from deeplio_b200 import engine as E
+    n, h, w, cout = 2, 64, 2048, 64
+    kh, kw = k
+    g = torch.Generator().manual_seed(kh * 10 + kw + stride[1])
+    pairs = torch.randn(n, 2, 6, h, w, generator=g) * torch.tensor([0.13, 0.1, 0.01, 0.34, 0.44, 0.57]).view(1, 1, 6, 1, 1)
+    wt = torch.randn(cout, 6, kh, kw, generator=g) / (6 * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    x = pairs[:, :, 0:3].reshape(n, 6, h, w)
+    leaves = [t.double().requires_grad_(True) for t in (wt, b, gamma, beta)]
+    y = F.conv2d(x.double(), leaves[0], leaves[1], stride, ((kh - 1) // 2, (kw - 1) // 2))
+    if pre_relu:
+        y = F.relu(y)
+    y = F.batch_norm(y, None, None, leaves[2], leaves[3], True, 0.1, 1e-5)
+    if not pre_relu:
+        y = F.relu(y)
+    ref = F.max_pool2d(y, 3, pool, 1, ceil_mode=pre_relu)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+
+    params = {"cv.weight": wt.to(DEV), "cv.bias": b.to(DEV), "bn.weight": gamma.to(DEV), "bn.bias": beta.to(DEV)}
+    bufs = {"bn.running_mean": torch.zeros(cout, device=DEV), "bn.running_var": torch.ones(cout, device=DEV)}
+    run = E.Run(params, bufs, torch.device(DEV), True, True)
+    view = pairs.to(DEV)[:, :, 0:3]                       # the non-contiguous channel slice the trainer hands over
+    x0 = E.pack_input(run, view, 8, first_ph, 4)
+    L = _lib()
+    L.profile_enable(1)
+    out = E.conv_bn(run, x0, "cv", "bn", stride, pre_relu=pre_relu, relu=not pre_relu, pool=pool, ceil=pre_relu,
+                    out_pad=(1, 2))
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert "conv_fwd_tc" in prof and "conv_fwd_simt" not in prof, prof
+    got = from_nhwc(out.t[:, 1:1 + out.h, 2:2 + out.w]).double()
+    assert got.shape == ref.shape
+    assert relerr(got, ref.detach()) < 2e-5
+    run.agrad[id(out)] = to_padded_nhwc(dout, 0, 0)
+    L.profile_enable(1)
+    run.backward()
+    torch.cuda.synchronize()
+    prof = L.profile_read()
+    L.profile_enable(0)
+    assert "conv_wgrad_tc" in prof and "conv_wgrad_simt" not in prof, prof
+    tol = 5e-5
+    assert relerr(run.pgrad["cv.weight"].cpu().double(), leaves[0].grad) < tol
+    assert (run.pgrad["cv.bias"].cpu().double() - leaves[1].grad).abs().max() < tol * leaves[0].grad.abs().max() * 10
+    assert relerr(run.pgrad["bn.weight"].cpu().double(), leaves[2].grad) < tol
+    assert relerr(run.pgrad["bn.bias"].cpu().double(), leaves[3].grad) < tol
 
 
 @pytest.mark.parametrize("variant", ["simple1", "bn_relu", "eval"])
