@@ -25,6 +25,11 @@ class BnPool(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("relu", "res_mode", "pool_k", "pool_sh", "pool_sw", "c_off", "out_group")]
 
 
+class LossTerm(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("gt", C.c_void_p), ("dpred", C.c_void_p)] + \
+               [(k, C.c_int) for k in ("B", "G", "C", "pred_sb", "pred_ss", "gt_sb", "gt_ss", "d_sb", "d_ss")]
+
+
 class DlioError(RuntimeError):
     pass
 
@@ -83,6 +88,12 @@ _PROTOS = {
     "dlio_rnn_bwd": (I, [I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "dlio_hws_loss": (I, [P, P, P, P, I, F, F, P, P, P, P]),
     "dlio_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
+    "dlio_pose_loss": (I, [LossTerm, LossTerm, LossTerm, LossTerm, P, P, I, F, P, P, P, P, P]),
+    "dlio_se3_chain_fwd": (I, [P, P, I, I, P, P, P, P]),
+    "dlio_se3_chain_bwd": (I, [P, P, I, I, P, P, P, P, P]),
+    "dlio_gt_relative": (I, [P, I, I, P, I, P, P, P, P]),
+    "dlio_finite_check": (I, [P, P, I, P, P]),
+    "dlio_pair_gather": (I, [P, LL, LL, LL, I, I, P, I, I, I, Tensor4, P, P, P, I, P]),
 }
 EXPORTS = sorted(_PROTOS)
 

@@ -21,6 +21,7 @@ from .. import functional as Fn
 from .. import _lib as L
 from .._lib import ptr
 from ..config import get_config_container
+from ..data import PairedFrames, pair_gather
 from .base import BaseNet, ParamTree, conv_params, require_cuda
 
 
@@ -248,7 +249,7 @@ class _EncoderPair(torch.autograd.Function):
         dev = xyz.device
         c = enc[0].out_channels
         cat = net.fusion == "cat"
-        n = xyz.shape[0]
+        n = xyz.shape[0] * xyz.shape[1] if isinstance(xyz, PairedFrames) else xyz.shape[0]
         feats = [torch.empty((n, 2 * c if cat else c), device=dev, dtype=torch.float32)]
         feats.append(feats[0] if cat else torch.empty((n, c), device=dev, dtype=torch.float32))
         runs = []
@@ -261,7 +262,14 @@ class _EncoderPair(torch.autograd.Function):
             run.bn_cfg = enc[e].bn_cfg()
             run.trace_prefix = "encoder%d." % (e + 1)
             with torch.cuda.stream(streams[e]):
-                x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)   # row pads of 4 pixels: space-to-depth first layer
+                # row pads of 4 pixels: space-to-depth first layer
+                if isinstance(view, PairedFrames):
+                    # frames paired on the fly (deeplio_b200.data): no [B,S,2,C,H,W] tensor, no reshape copy
+                    hi, lo = pair_gather(dev, view, 8, enc[e].first_pad[0], 4, E.USE_TC)
+                    x0 = E.Act(n, view.shape[4], view.shape[5], 8, enc[e].first_pad[0], 4, t=hi, lo=lo, needs_grad=False)
+                    run.keep.append((x0, view.frames))
+                else:
+                    x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)
                 enc[e].program(run, x0, feats[e], feats[e].shape[1], c if (cat and e == 1) else 0)
             runs.append(run)
         _join(streams)
@@ -350,7 +358,8 @@ class BaseLidarFeatNet(BaseNet):
             return v.as_strided((b * s, t, c, h, w), (v.stride(1),) + tuple(v.stride()[2:]), v.storage_offset())
         params = [p for e in (self.encoder1, self.encoder2) for _, p in e.named_parameters()]
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        y = _EncoderPair.apply(self, record, as5(imgs_xyz), as5(imgs_normals), *params)
+        views = [v if isinstance(v, PairedFrames) else as5(v) for v in (imgs_xyz, imgs_normals)]
+        y = _EncoderPair.apply(self, record, views[0], views[1], *params)
         y = self._tail(y)
         return y.view(b, s, -1)
 

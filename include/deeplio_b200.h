@@ -343,6 +343,56 @@ int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_a
 int dlio_hws_loss(const float *pos, const float *ori, const float *gt_pos, const float *gt_ori, int n,
                   float sx, float sq, float *loss, float *dpos, float *dori, void *stream);
 
+/* Full HWSLoss / LWSLoss and their gradients (deeplio/losses/losses.py:11-96 as trainer.py:246-263 calls them).
+ * Four mean-squared-error terms: t, w (frame to frame: translation, so(3) rotation) and p, q (frame to start:
+ * position, quaternion), each described by a dlio_loss_term -- a strided 3-D view [B, G, C] of the prediction and of
+ * the ground truth (last dimension contiguous), so the slices the trainer takes need no copies; pred == NULL
+ * switches a term off (the reference's loss_Types).
+ *   lws == 0 (HWSLoss): loss = (L_p + L_t) e^-sx + sx + (L_q + L_w) e^-sq + sq, sx / sq DEVICE scalars (the
+ *   nn.Parameters); lws != 0 (LWSLoss): loss = (L_p + L_t) + beta (L_q + L_w).
+ * Outputs, each optional: loss[1]; term.dpred = upstream * d loss / d pred (written through d_sb / d_ss); d_sx, d_sq.
+ * upstream (optional DEVICE scalar, default 1): the gradient flowing into the loss. */
+typedef struct {
+    const float *pred, *gt;
+    float *dpred;
+    int B, G, C;
+    int pred_sb, pred_ss, gt_sb, gt_ss, d_sb, d_ss;   /* element strides of the first two dimensions */
+} dlio_loss_term;
+int dlio_pose_loss(dlio_loss_term t, dlio_loss_term w, dlio_loss_term p, dlio_loss_term q, const float *sx,
+                   const float *sq, int lws, float beta, const float *upstream, float *loss, float *d_sx, float *d_sq,
+                   void *stream);
+
+/* ------------------------------------------------------------------ caller-side glue (N1, N2)
+ * Pose chaining, Trainer.se3_to_SE3 (deeplio/models/trainer.py:324-351): per sample b, R_0 = I, t_0 = 0 and for
+ * s = 0 .. S-1:  t <- R t_s + t,  R <- R exp(w_s);  f2g_x[b,s] = t,  f2g_q[b,s] = quaternion (w,x,y,z) of R (projected
+ * onto SO(3) when it fails liegroups' 1e-6 validity test).  The reference runs a Python loop over B x S with ~20
+ * tiny kernels and two torch.det host synchronisations per pair; here one launch.  *status (optional, device int,
+ * caller zeroes) receives OR-ed flags instead of the reference's exceptions: 1 a non-finite input, 2 det(exp(w))
+ * not close to 1 (trainer.py:341), 4 det(R) not close to 1 (:347).  S <= 64.
+ * bwd: d_x, d_w [B,S,3] from g_x [B,S,3], g_q [B,S,4] (either may be NULL = zeros); recomputes the chain. */
+int dlio_se3_chain_fwd(const float *f2f_x, const float *f2f_w, int B, int S, float *f2g_x, float *f2g_q, int *status,
+                       void *stream);
+int dlio_se3_chain_bwd(const float *f2f_x, const float *f2f_w, int B, int S, const float *g_x, const float *g_q,
+                       float *d_x, float *d_w, void *stream);
+/* Ground-truth pairing, DataCombiCreater.process_ground_turth (deeplio/models/misc.py:83-125): gts [B,F,15] =
+ * (t 3, R 9 row-major, v 3) per frame (kitti.py:292-301), combinations: HOST array of S (i, j) frame-index pairs.
+ * gt_f2f[b,s] = (R_i^T (t_j - t_i), log(R_i^T R_j)), gt_f2g[b,s] = (R_0^T (t_j - t_0), quaternion(R_0^T R_j)).
+ * *status flags: 1 non-finite, 8 a relative rotation fails the validity test (the reference raises there). */
+int dlio_gt_relative(const float *gts, int B, int F, const int *combinations, int S, float *gt_f2f, float *gt_f2g,
+                     int *status, void *stream);
+/* The NaN / Inf guards of the train loop (trainer.py:221-229,240-243: six isnan().any() / isinf().any() pairs, each
+ * a reduction plus a host synchronisation) as ONE pass: tensors / sizes are HOST arrays of `count` <= 8 device
+ * pointers / element counts; bit t of *flags (device int, caller zeroes) is raised when tensor t is not finite. */
+int dlio_finite_check(const float *const *tensors, const long long *sizes, int count, int *flags, void *stream);
+/* Pairing gather, DataCombiCreater.process_images (misc.py:65-69: imgs[:, combinations], channel split) fused
+ * with the encoders' input reshape (lidar_feat_nets.py:216-218): frames [B, F, *, H, W] (element strides sb, sf,
+ * sc; H, W contiguous) -> padded NHWC dst with dst.n = B*S images and channels (frame combinations[s][0]: c0 ..
+ * c0+C-1, frame combinations[s][1]: c0 .. c0+C-1, zeros up to dst.c).  No [B,S,2,C,H,W] copy of the pairs is made.
+ * dst_lo (optional): TF32 low-order plane.  flags (optional): bit `flag_bit` is raised on a NaN / Inf input. */
+int dlio_pair_gather(const float *frames, long long sb, long long sf, long long sc, int B, int F,
+                     const int *combinations, int S, int c0, int C, dlio_tensor4 dst, float *dst_ptr, float *dst_lo,
+                     int *flags, int flag_bit, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ from oracle import deeplio_oracle as O
 from oracle.configs import make_cfg
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt"))
+GOLDEN_CASES = sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith("pose_"))
 
 
 def load_golden(name):
@@ -96,3 +96,10 @@ def grad_rows(grads, g64, g32=None, gperts=()):
         e_pert = max(((gp[k] - ref).abs().max().item() for gp in gperts), default=0.0)
         rows.append((k, e, scale, e_ref, e_pert))
     return rows
+
+
+def quat_tol(q_ref, base=5e-6):
+    """Per-entry tolerance for quaternions [.., 4] (wxyz) obtained from rotation matrices: ``base`` amplified by
+    1 / (4 |qw|) where the conversion divides by 4 qw (capped at the near-zero branch, |qw| < 1e-6 -> other formulas)."""
+    qw = q_ref[..., 0:1].abs()
+    return base * (1.0 + 1.0 / (4.0 * qw.clamp_min(1e-3))).expand_as(q_ref)
