@@ -8,6 +8,7 @@
 // the number of channel groups), accumulate in registers, combine through shared-memory atomics and
 // finish with one fp64 global atomic per channel per block.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -17,11 +18,25 @@ constexpr int MAX_C = 1024;  // channel limit of the reducing kernels (largest o
 
 // threads per block: a multiple of the channel-group count (fixed channel group per thread) and, whenever that
 // fits in 256 threads, of the warp size (the reducing kernels use full-warp shuffles)
+// DLIO_EW_BLOCK (environment, 64 .. 256, default 256) caps the block size: 128-thread blocks fit beside a resident
+// tcgen05 convolution CTA (320 threads x 168 registers, ~205 KB of shared memory), so that with the two encoders on two
+// streams (engine.ENC_STREAMS) these HBM-bound passes run under the other encoder's tensor-bound convolutions
+static int ew_block_cap() {
+    static int cap = 0;
+    if (!cap) {
+        const char *e = getenv("DLIO_EW_BLOCK");
+        int v = e ? atoi(e) : 256;
+        cap = v < 64 ? 64 : (v > 256 ? 256 : v);
+    }
+    return cap;
+}
 static inline int block_for_cg(int cg) {
+    const int cap = ew_block_cap();
     int g = cg, b = 32;
     while (b) { int t = g % b; g = b; b = t; }          // g = gcd(cg, 32)
     const int unit = cg * (32 / g);
-    if (unit <= 256) return unit * (256 / unit);
+    if (unit <= cap) return unit * (cap / unit);
+    if (unit <= 256) return unit;
     return cg * (256 / cg > 0 ? 256 / cg : 1);
 }
 // persistent grid of a row-structured kernel: exactly the number of blocks that are resident at once
