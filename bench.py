@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the DeepLIO training hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the DeepLIO training hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--batch B]
 
-One "step" = one full train step of BASELINE.json configs[1] (Simple-1 LiDAR net + bi-LSTM IMU net + soft
-fusion + LSTM odometry net, 64x2048 frame pairs, batch 8 per GPU, S = 2 pairs per sample): forward -> HWS
-loss -> backward -> gradient all-reduce (N > 1) -> Adam, dropout active, BatchNorm in train mode.
-Two timed passes of the same K steps: eager launches with the library's per-call CUDA events (the per-class
-breakdown in ``roofline.classes``, ``config.eager_ms_per_step``), then forward + loss + backward replayed from one
-CUDA graph (``value``; DLIO_GRAPH=0 keeps the eager number).  ``e2e`` feeds every step from pinned host memory
-through ``deeplio_b200.pipeline`` (copy stream one step ahead, loss read one step late).
-Prints ONE JSON line on rank 0.  ``--impl reference`` times the CPU restatement of the reference (the
-reference is pure Python / PyTorch and does not travel to the GPU box) on the host cores.
+One "step" = one full train step of BASELINE.json configs[1] (Simple-1 LiDAR net + bi-LSTM IMU net + soft fusion +
+LSTM odometry net, 64x2048 frames, batch 8 per GPU, S = 2 frame pairs per sample) as the reference's Trainer runs it
+(trainer.py:197-281): ground-truth pairing -> pairing of the frames -> forward -> pose chaining se(3) -> SE(3) -> HWS
+loss (local + global, learnable sx / sq) -> backward -> gradient all-reduce (N > 1) -> Adam; dropout active,
+BatchNorm in train mode.  Everything is deeplio_b200 code: data.ground_truth / PairedFrames, nets.get_model,
+pose.se3_to_SE3, losses.HWSLoss, optim.FlatAdam.
+
+Two timed passes of the same K steps: eager launches with the library's per-call CUDA events (the per-class breakdown
+in ``roofline.classes``; one stream, so every class is timed in isolation), then forward + loss + backward replayed
+from CUDA graphs (``value``; DLIO_GRAPH=0 keeps the eager number).  ``e2e`` feeds every step from pinned host memory
+([B, S+1, 6, H, W] frames -- not pairs --, IMU windows, ground-truth poses) through ``deeplio_b200.pipeline`` and reads
+the loss back.  Prints ONE JSON line on rank 0.
+
+``--impl reference``: the reference's CPU path -- the oracle restatement (oracle/; the reference is pure Python /
+PyTorch, does not travel to the GPU box and has nothing to compile) -- on all host cores, SAME workload, batch and
+step counts (steps are only cut when the run would exceed ~4 minutes; the line says so).
 """
 import argparse
 import itertools
@@ -31,34 +38,27 @@ UNIT = "frame-pairs/s"
 WORKLOAD = "cfg1_simple1_lstm_b8"     # BASELINE.json configs[1]
 H, W = 64, 2048
 LR, WD = 1e-3, 1e-4                   # reference defaults (deeplio/train.py:39,45)
+G0, G1 = 1, 3                         # global-loss slice 1 .. max_glob_seq (trainer.py:42,261)
+STD = (0.1269, 0.0951, 0.0108, 0.3436, 0.4445, 0.5664)    # per-channel std of the mean-subtracted images (config.yaml:26-27)
 
 
-# ----------------------------------------------------------------------------- workload description
-def conv_flops_simple1(n_images):
-    """Algorithmic conv FLOPs of ONE Simple-1 encoder over n_images 64x2048 images, split by
-    the kernel class that runs each layer: {class: flops}.  Every layer runs on tcgen05: conv2..conv7 (stride 1,
-    Cin % 64 == 0) as 3xF16, conv1 (Cin = 6, 5x7 stride (1,2)) as 3xTF32 through the space-to-depth view
-    (csrc/conv_s2d.cu; its 2.3x extra MACs are NOT counted -- these are algorithmic FLOPs).  conv1 needs no dgrad
-    (the input has no gradient)."""
-    from deeplio_b200.engine import pool_out
-    spec = [(6, 64, 5, 7, (1, 2), (1, 2)), (64, 128, 3, 5, (1, 1), (1, 2)), (128, 128, 3, 3, (1, 1), None),
-            (128, 256, 3, 3, (1, 1), (2, 2)), (256, 256, 3, 3, (1, 1), None), (256, 512, 3, 3, (1, 1), (2, 2)),
-            (512, 512, 3, 3, (1, 1), None)]
-    h, w = H, W
-    out = {k: 0.0 for k in ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc",
-                            "conv_wgrad_tc")}
-    for i, (ci, co, kh, kw, (sh, sw), pool) in enumerate(spec):
-        ho, wo = (h + 2 * ((kh - 1) // 2) - kh) // sh + 1, (w + 2 * ((kw - 1) // 2) - kw) // sw + 1
-        f = 2.0 * co * ho * wo * ci * kh * kw * n_images
-        tc = ((sh, sw) == (1, 1) and ci % 32 == 0) or i == 0
-        out["conv_fwd_tc" if tc else "conv_fwd_simt"] += f
-        out["conv_wgrad_tc" if (tc and (co % 128 == 0 or i == 0)) else "conv_wgrad_simt"] += f
-        if i > 0:
-            out["conv_dgrad_tc" if ((sh, sw) == (1, 1) and co % 32 == 0 and ci % 16 == 0) else "conv_dgrad_simt"] += f
-        h, w = ho, wo
-        if pool:
-            h, w = pool_out(h, pool[0], True), pool_out(w, pool[1], True)
-    return out
+def workload_dict(workload, B, S, T, world, n_params):
+    """The workload-defining part of ``config``: identical in the B200 arm and the reference arm."""
+    return {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "pairs_per_sample": S,
+            "image": "64x2048x6 per frame (xyz, normals), %d frames per sample" % (S + 1), "imu_window": T,
+            "loss": "HWSLoss local+global, learnable sx/sq", "optimizer": "adam lr 1e-3 wd 1e-4",
+            "params_M": round(n_params / 1e6, 3)}
+
+
+def synthetic_host_batch(B, S, T, seed):
+    """per-channel N(0, sigma_c) frames with ~15 % empty pixels, N(0,1) IMU windows, smooth trajectories."""
+    import torch
+    from deeplio_b200.workloads import synthetic_gts
+    g = torch.Generator().manual_seed(seed)
+    std = torch.tensor(STD).view(1, 1, 6, 1, 1)
+    frames = torch.randn(B, S + 1, 6, H, W, generator=g) * std
+    frames *= (torch.rand(B, S + 1, 1, H, W, generator=g) >= 0.15).float()
+    return {"frames": frames, "imus": torch.randn(B, S, T, 6, generator=g), "gts": synthetic_gts(B, S + 1, seed)}
 
 
 class ClockSampler(threading.Thread):
@@ -102,50 +102,75 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_train_steps(steps, warmup, batch=1, seq=2, t_imu=15):
-    """The reference's CPU path (oracle restatement, fp32 torch CPU, all host threads): full train steps of the
-    same model on a bounded sample (batch ``batch``).  Returns (frame-pairs/s, seconds per step, cores)."""
+def cpu_train_steps(workload, steps, warmup, batch, budget_s=None):
+    """The reference's CPU path (oracle restatement, fp32 torch CPU, all host threads): full train steps of the same
+    model and the same step definition (ground-truth pairing, forward, pose chaining, HWS loss, backward, Adam).
+    Returns (frame-pairs/s, seconds per step, cores, steps actually timed, warm-up steps actually run)."""
     import torch
     from oracle import deeplio_oracle as O
+    from oracle import pose_oracle as P
     from oracle.configs import BASELINE_CONFIGS, make_cfg
-    kw, _, _, _ = BASELINE_CONFIGS[WORKLOAD]
+    kw, _, seq, t_imu = BASELINE_CONFIGS[workload]
     cfg = make_cfg(no_dropout=False, height=H, width=W, **kw)
+    combos = cfg["datasets"]["combinations"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = O.synthetic_state(cfg, seed=0)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k}
     state = dict(sd)
     state.update(leaves)
-    opt = torch.optim.Adam(list(leaves.values()), lr=LR, weight_decay=WD)
-    xyz, normals, imus = O.synthetic_batch(batch, seq, H, W, t_imu, seed=0)
-    g = torch.Generator().manual_seed(5)
-    gt_pos, gt_ori = torch.randn(batch, seq, 3, generator=g) * 0.1, torch.randn(batch, seq, 3, generator=g) * 0.01
-    times = []
-    for i in range(warmup + steps):
+    sx, sq = torch.tensor(0.0, requires_grad=True), torch.tensor(-3.0, requires_grad=True)
+    opt = torch.optim.Adam([{"params": list(leaves.values())}, {"params": [sx, sq]}], lr=LR, weight_decay=WD)
+    d = synthetic_host_batch(batch, seq, t_imu, seed=100)
+    idx = torch.tensor(combos)
+    times, done_warm = [], 0
+    i = 0
+    while len(times) < steps:
         t0 = time.perf_counter()
         opt.zero_grad()
-        pos, ori = O.deeplio_forward(state, cfg, xyz, normals, imus, training=True)
-        mse = torch.nn.functional.mse_loss
-        loss = mse(pos, gt_pos) * 1.0 + mse(ori, gt_ori) * float(torch.exp(torch.tensor(3.0))) - 3.0
+        gt_f2f, gt_f2g = P.ground_truth(d["gts"], combos)
+        pairs = d["frames"][:, idx]                                           # misc.py:65-69
+        pos, ori = O.deeplio_forward(state, cfg, pairs[:, :, :, 0:3], pairs[:, :, :, 3:].contiguous(), d["imus"],
+                                     training=True)
+        p, q, _ = P.se3_to_SE3(pos, ori)
+        loss = P.pose_loss(pos, ori, p[:, G0:G1], q[:, G0:G1], gt_f2f[:, :, 0:3], gt_f2f[:, :, 3:],
+                           gt_f2g[:, G0:G1, 0:3], gt_f2g[:, G0:G1, 3:7], sx=sx, sq=sq)
         loss.backward()
         opt.step()
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        else:
+            done_warm += 1
+            if budget_s is not None and i == 0:
+                # bound the whole run: keep >= 3 timed steps and >= 1 warm-up step
+                fit = int(budget_s / max(dt, 1e-3))
+                if fit < steps + warmup:
+                    warmup = max(1, min(warmup, fit // 4))
+                    steps = max(3, min(steps, fit - warmup))
+        i += 1
     sec = sum(times) / len(times)
-    return batch * seq / sec, sec, cores
+    return batch * seq / sec, sec, cores, len(times), done_warm, sum(p.numel() for p in leaves.values()) + 2
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    fps, sec, cores = cpu_train_steps(steps, warmup)
-    sample = "batch 1 x S=2 (2 frame pairs of 64x2048) per step, %d timed steps after %d warm-up" % (steps, warmup)
+    from oracle.configs import BASELINE_CONFIGS
+    workload = args.workload or WORKLOAD
+    _, B, S, T = BASELINE_CONFIGS[workload]
+    B = args.batch or (B if workload == WORKLOAD else max(1, B // 8))
+    fps, sec, cores, steps, warm, n_params = cpu_train_steps(workload, args.steps, args.warmup, B, budget_s=240.0)
+    cut = "" if (steps == args.steps and warm == args.warmup) else \
+        " (cut from %d / %d so that the run stays within ~4 minutes)" % (args.steps, args.warmup)
+    sample = "batch %d x S=%d (%d frame pairs of 64x2048) per step, %d timed steps after %d warm-up%s" % (
+        B, S, B * S, steps, warm, cut)
+    cfg = workload_dict(workload, B, S, T, 1, n_params)
+    cfg["impl_note"] = "CPU restatement of the reference path (oracle/), torch CPU fp32, %d threads" % cores
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (oracle/), torch CPU fp32"},
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -156,7 +181,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from deeplio_b200 import _lib, functional as Fn, nets, parallel
+    from deeplio_b200 import _lib, data, engine as E, losses, nets, parallel, pose
     from deeplio_b200.config import build_config_container
     from deeplio_b200.optim import FlatAdam
     from deeplio_b200.pipeline import DevicePrefetcher, LaggedScalar
@@ -173,51 +198,45 @@ def run_b200(args):
     torch.cuda.set_stream(torch.cuda.Stream(dev))
     workload = args.workload or WORKLOAD
     cfg, B, S, T = workload_config(workload, H, W)
-    B = args.batch or B                       # per-GPU batch (weak scaling)
+    B = args.batch or (B if workload == WORKLOAD else max(1, B // 8))      # per-GPU batch (weak scaling)
+    combos = cfg["datasets"]["combinations"]
     build_config_container(cfg, argparse.Namespace(device=str(dev), batch_size=B))
     torch.manual_seed(1234)
     model = nets.get_model((3, H, W), cfg, str(dev))
+    criterion = losses.get_loss_function(cfg, str(dev))              # HWSLoss, local+global, learnable sx / sq
     parallel.broadcast_model(model)
     model.train()
-    opt = FlatAdam(model.parameters(), lr=LR, weight_decay=WD)
-    n_params = sum(p.numel() for p in model.parameters())
-    # N > 1: the all-reduce of the odometry-net / fusion / head gradients (78 % of the bytes) overlaps the encoders'
-    # backward; DLIO_OVERLAP=0 falls back to one all-reduce after backward
-    reducer = parallel.OverlappedGradReducer(model, opt) if os.environ.get("DLIO_OVERLAP", "1") != "0" else None
+    # trainer.py:56-58: two parameter groups, the model's and the criterion's
+    opt = FlatAdam([{"params": model.parameters()}, {"params": criterion.parameters()}], lr=LR, weight_decay=WD)
+    n_params = sum(p.numel() for p in model.parameters()) + sum(p.numel() for p in criterion.parameters())
+    reducer = parallel.OverlappedGradReducer(model, opt) if world > 1 else None
 
-    # synthetic batch of this rank: pinned host copy + device-resident copy
-    g = torch.Generator().manual_seed(100 + rank)
-    std = torch.tensor([0.1269, 0.0951, 0.0108, 0.3436, 0.4445, 0.5664]).view(1, 1, 6, 1, 1)
-    frames = torch.randn(B, S + 1, 6, H, W, generator=g) * std
-    frames *= (torch.rand(B, S + 1, 1, H, W, generator=g) >= 0.15).float()
-    idx = torch.tensor([[i, i + 1] for i in range(S)])
-    host = {"pairs": frames[:, idx].contiguous().pin_memory(),            # [B,S,2,6,H,W]
-            "imus": torch.randn(B, S, T, 6, generator=g).pin_memory(),
-            "gt_pos": (torch.randn(B, S, 3, generator=g) * 0.1).pin_memory(),
-            "gt_ori": (torch.randn(B, S, 3, generator=g) * 0.01).pin_memory()}
-    h2d_bytes = sum(t.numel() * 4 for t in host.values())
+    host = {k: v.pin_memory() for k, v in synthetic_host_batch(B, S, T, seed=100 + rank).items()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
-
-    def split(d):
-        pairs = d["pairs"]
-        return [[pairs[:, :, :, 0:3], pairs[:, :, :, 3:].contiguous()], d["imus"]]   # as misc.py:65-69 does
+    state = {"resident": resident}
 
     def fwd_loss(d):
-        pos, ori = model(split(d))
-        return Fn.hws_loss(pos, ori, d["gt_pos"], d["gt_ori"])
+        gt_f2f, gt_f2g = data.ground_truth(d["gts"], combos)                 # misc.py:83-125 on the device
+        xyz = data.PairedFrames(d["frames"], combos, 0, 3)                  # misc.py:65-69 without the gather copy
+        normals = data.PairedFrames(d["frames"], combos, 3, 3)
+        pos, ori = model([[xyz, normals], d["imus"]])
+        p, q = pose.se3_to_SE3(pos, ori, check=False)                        # trainer.py:245
+        return criterion(pos, ori, p[:, G0:G1], q[:, G0:G1], gt_f2f[:, :, 0:3], gt_f2f[:, :, 3:],
+                         gt_f2g[:, G0:G1, 0:3], gt_f2g[:, G0:G1, 3:7])      # trainer.py:260-263
 
     def eager_step(d):
         opt.zero_grad()
         loss = fwd_loss(d)
         loss.backward()
-        scale = reducer.finish() if reducer is not None else parallel.allreduce_grads(opt.flat_grad)
+        scale = reducer.finish() if reducer is not None else 1.0
         opt.step(scale)
         return loss.detach()      # no reference to the autograd graph survives the step (deeplio_b200.graph)
 
     gstep = [None]
 
     def graph_step(d):
-        loss = gstep[0](d)                       # forward + loss + backward: one graph launch
+        loss = gstep[0](d)                       # forward + loss + backward: graph launches
         opt.step(parallel.allreduce_grads(opt.flat_grad))
         return loss
 
@@ -244,18 +263,20 @@ def run_b200(args):
 
     def resident_steps(steps):
         for _ in range(steps):
-            train_step(resident)
+            train_step(state["resident"])
 
     # pass 1 times every kernel class in isolation (one stream); the graph pass may put the two encoders on two streams
-    from deeplio_b200 import engine as E
     enc_streams = E.ENC_STREAMS
     E.ENC_STREAMS = False
-    for _ in range(args.warmup):
+    E.FLOPS = {}
+    train_step(resident)                          # also counts the algorithmic conv FLOPs of one step, per class
+    flops, E.FLOPS = E.FLOPS, None
+    for _ in range(max(0, args.warmup - 1)):
         train_step(resident)
+    assert pose.raise_for_status(dev) == 0
     torch.cuda.reset_peak_memory_stats(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # pass 1, eager launches with the library's per-call CUDA events: the per-class breakdown (roofline.classes)
     _lib.profile_enable(1)
     n0 = _lib.launch_count()
     ms_eager = timed(resident_steps, args.steps)
@@ -263,8 +284,8 @@ def run_b200(args):
     prof = _lib.profile_read()
     _lib.profile_enable(0)
     ms_total, launch_mode = ms_eager, "eager (one C-ABI call per kernel)"
-    # pass 2, the same step with forward + loss + backward replayed from ONE CUDA graph (deeplio_b200.graph); the
-    # gradient exchange and the optimizer stay outside the graph.  `value` is this pass; DLIO_GRAPH=0 keeps pass 1.
+    # pass 2, the same step with forward + loss + backward replayed from CUDA graphs (deeplio_b200.graph); the
+    # gradient exchange and the optimizer stay outside.  `value` is this pass; DLIO_GRAPH=0 keeps pass 1.
     if os.environ.get("DLIO_GRAPH", "1") != "0":
         try:
             from deeplio_b200.graph import GraphedTrainStep
@@ -273,8 +294,9 @@ def run_b200(args):
                 reducer = None
             E.ENC_STREAMS = enc_streams
             gstep[0] = GraphedTrainStep(fwd_loss, resident, opt.zero_grad, model=model)
+            state["resident"] = gstep[0].input_slots[0]     # the graph's own input buffers: resident steps copy nothing
             for _ in range(args.warmup):
-                train_step(resident)
+                train_step(state["resident"])
             n0 = _lib.launch_count()
             ms_total = timed(resident_steps, args.steps)
             launches = _lib.launch_count() - n0 + gstep[0].captured_launches * args.steps
@@ -287,16 +309,18 @@ def run_b200(args):
     # end to end through the public API: every step's inputs come from pinned host memory (copied on a copy stream
     # one step ahead, deeplio_b200.pipeline.DevicePrefetcher) and every step's loss is read back on the host (one
     # step late, LaggedScalar); all copies and reads happen inside the timed region
-    losses = []
+    losses_seen = []
 
     def e2e_steps(steps):
         lag = LaggedScalar()
-        for d in DevicePrefetcher(itertools.repeat(host, steps), dev):
-            losses.append(lag.push(train_step(d)))
-        losses.append(lag.flush())
+        bufs = gstep[0].input_slots if gstep[0] is not None else None     # copy straight into the graphs' inputs
+        for d in DevicePrefetcher(itertools.repeat(host, steps), dev, buffers=bufs):
+            losses_seen.append(lag.push(train_step(d)))
+        losses_seen.append(lag.flush())
     e2e_steps(2)
     ms_e2e = timed(e2e_steps, args.steps)
-    assert all(v is None or v == v for v in losses), "non-finite loss in the end-to-end run"
+    assert all(v is None or v == v for v in losses_seen), "non-finite loss in the end-to-end run"
+    assert pose.raise_for_status(dev) == 0, "pose / ground-truth status flags raised"
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
@@ -305,10 +329,10 @@ def run_b200(args):
     value = pairs_per_step * args.steps / (ms_total / 1e3)
     e2e = pairs_per_step * args.steps / (ms_e2e / 1e3)
 
-    # roofline of the dominant kernel class (largest share of the step among the profiled conv classes)
-    # per-class FLOP accounting exists for the headline workload's encoder (Simple-1); other workloads (secondary
-    # runs, --workload) report class times only
-    flops = {k: 2 * v for k, v in conv_flops_simple1(B * S).items()} if "simple1" in workload else {}    # two encoders
+    # roofline of the dominant kernel class: the conv class with the largest share of the step.  Algorithmic FLOPs
+    # per class are counted by the executor while it runs the step (engine.FLOPS): 2 * Cout * Ho * Wo * Cin * kh * kw
+    # per image, real channel counts -- no padding, no split-precision factor, none of the extra MACs of the
+    # space-to-depth / pixel-pair views.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -323,46 +347,56 @@ def run_b200(args):
         per_step_ms = ms / args.steps
         classes[name] = {"ms_per_step": per_step_ms, "launches_per_step": n / args.steps,
                          "share_of_step": per_step_ms / (ms_eager / args.steps)}
-        if name in flops:
+        if flops.get(name):
             classes[name]["gflop_per_step"] = flops[name] / 1e9
             classes[name]["tflops"] = flops[name] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None
     roofline = None
-    if classes and flops:
-        dom = max((k for k in classes if k in flops), key=lambda k: classes[k]["ms_per_step"])
+    cands = [k for k in classes if classes[k].get("tflops")]
+    if cands:
+        dom = max(cands, key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
         tc = dom.endswith("_tc")
         # the tcgen05 kernels issue 3 fp16 MMAs per fp32-accurate product (hi*hi, lo*hi, hi*lo), and fp16 runs at the
         # bf16 rate, so the tensor-pipe ceiling for fp32-equivalent algorithmic FLOPs is bf16_peak / 3
         # (frac_of_3xf16_ceiling); `frac` is against the measured bf16 peak itself, as the contract asks.
-        # traffic: dram bytes per launch of this class from the committed ncu pass (profiles/r01_traffic.json)
+        # traffic: dram bytes per launch of this class from the committed ncu pass (profiles/*_traffic.json)
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        for f in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", f)))
+                if workload == WORKLOAD and dom in t:
+                    traffic = t[dom].get("dram_bytes_per_launch")
+                    break
+            except Exception:
+                pass
+        conv_ms = sum(classes[k]["ms_per_step"] for k in cands)
+        conv_fl = sum(flops[k] for k in cands)
         roofline = {"bound": "tensor", "kernel": dom, "achieved": c["tflops"], "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": c["tflops"] / bf16_peak, "traffic": traffic, "peak_source": peak_src,
                     "frac_of_3xf16_ceiling": (c["tflops"] / (bf16_peak / 3.0)) if tc else None,
                     "math": ("3xF16 tcgen05: three kind::f16 MMAs per fp32-accurate product, fp32 accumulation "
                              "(fp32-equivalent algorithmic FLOPs)") if tc else "fp32 FMA (CUDA cores)",
-                    "launch_ms": c["ms_per_step"] / c["launches_per_step"], "classes": classes}
+                    "launch_ms": c["ms_per_step"] / c["launches_per_step"],
+                    "conv_path": {"gflop_per_step": conv_fl / 1e9, "ms_per_step": conv_ms,
+                                  "tflops": conv_fl / (conv_ms * 1e-3) / 1e12,
+                                  "frac_of_3xf16_ceiling": conv_fl / (conv_ms * 1e-3) / 1e12 / (bf16_peak / 3.0)},
+                    "classes": classes}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and workload == WORKLOAD:
-        fps, sec, cores = cpu_train_steps(3, 1)
+        fps, sec, cores, st, wm, _ = cpu_train_steps(workload, 3, 1, 2)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "batch 1 x S=2 (2 frame pairs) per step, 3 timed steps after 1 warm-up, %.2f s/step" % sec}
+                        "sample": "batch 2 x S=2 (4 frame pairs of 64x2048) per step, %d timed steps after %d warm-up, %.2f s/step "
+                                  "(the --impl reference arm runs the full batch)" % (st, wm, sec)}
 
     if rank == 0:
+        cfgd = workload_dict(workload, B, S, T, world, n_params)
+        cfgd.update({"parallelism": "dp%d" % world, "launch": launch_mode, "eager_ms_per_step": ms_eager / args.steps,
+                     "encoder_streams": 2 if E.ENC_STREAMS else 1,
+                     "l2": "working set per step (%.1f GB peak, activations) exceeds the 126 MB L2; no explicit flush" % peak_gb})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "pairs_per_sample": S,
-                           "image": "64x2048x6 x2 (xyz, normals)", "imu_window": T, "parallelism": "dp%d" % world,
-                           "launch": launch_mode, "eager_ms_per_step": ms_eager / args.steps,
-                           "encoder_streams": 2 if E.ENC_STREAMS else 1,
-                           "params_M": n_params / 1e6, "optimizer": "adam lr 1e-3 wd 1e-4 (fused, flat arena)",
-                           "l2": "working set per step (%.1f GB peak, activations) exceeds the 126 MB L2; no explicit flush" % peak_gb},
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline}
@@ -379,7 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's, 8)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="", help="secondary runs: another BASELINE.json workload "
                     "(deeplio_b200.workloads.WORKLOADS); the default is the headline workload")

@@ -41,6 +41,10 @@ USE_F16 = True
 FUSED_POOL_BWD = True
 # debugging aid (scripts/repeat_parity.py): when a dict, every conv_bn backward stores clones of its tensors here
 DEBUG_TRACE = None
+# bench aid: when a dict, conv_bn adds the ALGORITHMIC FLOPs (2 * Cout * Ho * Wo * Cin * kh * kw per image; real channel
+# counts, no padding, no split-precision factor) of every convolution it runs to the kernel class that runs it
+# (the dlio_prof_kind names), so bench.py can quote a roofline for any workload
+FLOPS = None
 # test aid: when a dict, every conv_bn forward stores the ReLU mask of its layer (bool, NCHW) under
 # Run.trace_prefix + conv name, so that tests can count mask disagreements with the oracle (oracle.TRACE)
 MASK_TRACE = None
@@ -268,6 +272,10 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
     s2d = (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7 and x.w % 4 == 0
            and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0 and not x.needs_grad)
     assert fwd_f16 or pair or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
+    flops = 2.0 * cout * ho * wo * cin * kh * kw * x.n
+    if FLOPS is not None:
+        k = "conv_fwd_tc" if (s2d or pair or fwd_f16 or fwd_tc) else "conv_fwd_simt"
+        FLOPS[k] = FLOPS.get(k, 0.0) + flops
     y = Act(n, ho, wo, cout, device=run.device)
     # the batch statistics also bound the BN output (-> scale of the fp16 planes), so they are taken in eval mode too
     stats = run.zeros(2 * cout, dtype=torch.float64)
@@ -384,6 +392,12 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
                 dg = ("f16" if (f16_ok(cout, cin_pad, stride)) else ("tf32" if tc_ok(cout, cin_pad, stride) else "simt"))
         assert wg != "simt" or x.t is not None, (cname, "wgrad on the CUDA cores needs the fp32 input plane")
         modes = (wg, dg)
+        if FLOPS is not None:
+            k = "conv_wgrad_simt" if wg == "simt" else "conv_wgrad_tc"
+            FLOPS[k] = FLOPS.get(k, 0.0) + flops
+            if dg is not None:
+                k = "conv_dgrad_simt" if dg == "simt" else "conv_dgrad_tc"
+                FLOPS[k] = FLOPS.get(k, 0.0) + flops
         sums = run.zeros(2 * cout + 1, dtype=torch.float64)
         dz = None
         if ymax is not None:

@@ -35,16 +35,24 @@ class GraphedTrainStep:
     then happens on the current stream.  When the current stream is the default stream, a side stream is used and no
     eager step may have run before."""
 
-    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None):
+    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None, slots=2):
         """``model`` (optional): its buffers (BatchNorm running statistics and ``num_batches_tracked``) and the dropout
         call counter are snapshotted before the warm-up passes and restored before the capture, so that building the
-        graph leaves the training state exactly as an eager run would find it."""
+        graph leaves the training state exactly as an eager run would find it.
+
+        ``slots``: number of static input sets, one captured graph each (``input_slots``).  An input pipeline that
+        writes batch i + 1 into one set while the step on batch i reads the other (pipeline.DevicePrefetcher with
+        ``buffers=step.input_slots``) then feeds the graphs without a device-to-device copy of the inputs.  The
+        graphs share one memory pool (they are replayed one at a time, on one stream), so the activations exist once."""
         dev = next(iter(example.values())).device
-        self.static_in = {k: torch.empty_like(v) for k, v in example.items()}
-        for k, v in example.items():
-            self.static_in[k].copy_(v)
+        self.input_slots = [{k: torch.empty_like(v) for k, v in example.items()} for _ in range(max(1, slots))]
+        for slot in self.input_slots:
+            for k, v in example.items():
+                slot[k].copy_(v)
+        self.static_in = self.input_slots[0]
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.graph = torch.cuda.CUDAGraph()
+        self.graphs, self.static_losses = [], []
+        self._next = 0
         gc.collect()       # drop autograd graphs of earlier eager steps that are only kept alive by reference cycles
         prev = Fn._seed_epoch[0]
         Fn._seed_epoch[0] = self.epoch
@@ -61,24 +69,37 @@ class GraphedTrainStep:
                 with torch.no_grad():
                     for b, v in saved:
                         b.copy_(v)
-            Fn._drop_counter[0] = drop0
             del saved
             cur.wait_stream(side)
             torch.cuda.synchronize(dev)
-            n0 = L.launch_count()
-            # capture on the warm-up stream: autograd nodes that outlive an iteration (AccumulateGrad) stay on one stream
-            with torch.cuda.graph(self.graph, stream=side):
-                self.epoch.add_(1)
-                zero_grad()
-                self.static_loss = fwd_loss(self.static_in)
-                self.static_loss.backward()
-            self.captured_launches = L.launch_count() - n0     # library kernels every replay launches
+            pool = None
+            for slot in self.input_slots:
+                Fn._drop_counter[0] = drop0            # every graph draws the same mask streams (seed + device epoch)
+                graph = torch.cuda.CUDAGraph()
+                n0 = L.launch_count()
+                # capture on the warm-up stream: autograd nodes that outlive an iteration (AccumulateGrad) stay on one stream
+                with torch.cuda.graph(graph, stream=side, pool=pool):
+                    self.epoch.add_(1)
+                    zero_grad()
+                    loss = fwd_loss(slot)
+                    loss.backward()
+                self.captured_launches = L.launch_count() - n0     # library kernels every replay launches
+                pool = graph.pool()
+                self.graphs.append(graph)
+                self.static_losses.append(loss)
+            self.graph, self.static_loss = self.graphs[0], self.static_losses[0]
         finally:
             Fn._seed_epoch[0] = prev
 
     def __call__(self, inputs):
-        for k, v in inputs.items():
-            if v.data_ptr() != self.static_in[k].data_ptr():
-                self.static_in[k].copy_(v, non_blocking=True)
-        self.graph.replay()
-        return self.static_loss.detach()
+        """``inputs``: one of ``input_slots`` (replayed in place) or any dict of tensors with the captured shapes
+        (copied into the next slot first)."""
+        k = next((i for i, s in enumerate(self.input_slots) if inputs is s), None)
+        if k is None:
+            k = self._next
+            self._next = (k + 1) % len(self.input_slots)
+            for name, v in inputs.items():
+                if v.data_ptr() != self.input_slots[k][name].data_ptr():
+                    self.input_slots[k][name].copy_(v, non_blocking=True)
+        self.graphs[k].replay()
+        return self.static_losses[k].detach()

@@ -14,14 +14,24 @@ class DevicePrefetcher:
     while the caller computes on batch i.  A yielded dict is valid until the caller asks for the batch after
     the next one (its buffers are then overwritten)."""
 
-    def __init__(self, batches, device, depth=2):
+    def __init__(self, batches, device, depth=2, buffers=None):
+        """``buffers`` (optional): a list of >= 2 dicts of device tensors to copy into instead of buffers of its own --
+        e.g. ``graph.GraphedTrainStep.input_slots``, so that the host batch lands directly in a captured graph's
+        static inputs and the yielded dict IS that slot."""
         self.it = iter(batches)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher: device must be a CUDA device (no CPU fallback)")
         self.copy_stream = torch.cuda.Stream(self.device)
+        if buffers is not None:
+            if len(buffers) < 2:
+                raise ValueError("DevicePrefetcher: at least two buffer sets are needed to copy one batch ahead")
+            depth = len(buffers)
         self.depth = depth
-        self.bufs = [None] * depth
+        self.bufs = list(buffers) if buffers is not None else [None] * depth
+        if buffers is not None:
+            # the sets may hold the previous user's data in flight on the current stream
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         self.ready = [torch.cuda.Event() for _ in range(depth)]      # copy of slot k finished
         self.free = [None] * depth                                   # compute on slot k finished
         self.bytes_per_batch = 0
@@ -38,6 +48,7 @@ class DevicePrefetcher:
         k = self.slot
         if self.bufs[k] is None:
             self.bufs[k] = {n: torch.empty(t.shape, dtype=t.dtype, device=self.device) for n, t in host.items()}
+        if not self.bytes_per_batch:
             self.bytes_per_batch = sum(t.numel() * t.element_size() for t in host.values())
         with torch.cuda.stream(self.copy_stream):
             if self.free[k] is not None:

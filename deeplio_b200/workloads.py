@@ -2,6 +2,7 @@
 for the structure and default hyper-parameters).  Used by bench.py and the examples; tests check that these
 agree with the oracle-side copies."""
 import copy
+import math
 
 DEFAULT_CONFIG = {
     "datasets": {
@@ -62,3 +63,31 @@ def workload_config(name, height=64, width=2048):
     cfg[lidar]["fusion"] = lfusion
     cfg["imu-feat-rnn"]["type"] = rnn_type
     return cfg, batch, seq, t_imu
+
+
+def synthetic_gts(batch, frames, seed=0):
+    """Synthetic ground-truth poses [batch, frames, 15] = (t 3, R 9 row-major, v 3) per frame, the layout of
+    ``Kitti.load_ground_truth`` (deeplio/datasets/kitti.py:292-301): smooth yaw-dominated forward motion from a
+    random start pose (float64 arithmetic, returned as float32 torch tensor)."""
+    import numpy as np
+    import torch
+
+    def rodrigues(w):
+        th = float(np.linalg.norm(w))
+        if th < 1e-12:
+            return np.eye(3)
+        a = w / th
+        K = np.array([[0.0, -a[2], a[1]], [a[2], 0.0, -a[0]], [-a[1], a[0], 0.0]])
+        return np.eye(3) + math.sin(th) * K + (1.0 - math.cos(th)) * (K @ K)
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, frames, 15))
+    for b in range(batch):
+        R = rodrigues(rng.standard_normal(3) * 0.5)
+        t = rng.standard_normal(3) * 10.0
+        for f in range(frames):
+            w = np.array([0.002, 0.004, 0.03]) * (1.0 + rng.standard_normal(3))
+            v = np.array([1.2, 0.02, 0.01]) * (1.0 + 0.3 * rng.standard_normal(3))
+            out[b, f, 0:3], out[b, f, 3:12], out[b, f, 12:15] = t, R.reshape(9), v
+            t = t + R @ v
+            R = R @ rodrigues(w)
+    return torch.from_numpy(out).float()

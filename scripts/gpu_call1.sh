@@ -13,4 +13,5 @@ DLIO_ENC_STREAMS=1 DLIO_EW_BLOCK=128 timeout 300 python bench.py --steps 10 --wa
 DLIO_SKIP_DZ=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c1_bench_nodzskip.json 2> gpurun_out/c1_bench_nodzskip.err
 DLIO_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/c1_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/c1_ncu_bench.log 2>&1
+timeout 400 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/c1_bench_reference.json 2> gpurun_out/c1_bench_reference.err
 echo done
