@@ -94,6 +94,9 @@ _PROTOS = {
     "dlio_gt_relative": (I, [P, I, I, P, I, P, P, P, P]),
     "dlio_finite_check": (I, [P, P, I, P, P]),
     "dlio_pair_gather": (I, [P, LL, LL, LL, I, I, P, I, I, I, Tensor4, P, P, P, I, P]),
+    "dlio_scan_scratch_bytes": (SZ, [I, I]),
+    "dlio_scan_project": (I, [P, I, I, I, F, F, F, F, P, I, P, P, P, P, P, P]),
+    "dlio_imu_windows": (I, [P, P, I, P, I, I, P, P, P, P, P]),
 }
 EXPORTS = sorted(_PROTOS)
 
@@ -130,6 +133,7 @@ def _checked(name):
 for _name, (_res, _args) in _PROTOS.items():
     if _res is I and _name != "dlio_abi_version":
         globals()[_name[5:]] = _checked(_name)
+scan_scratch_bytes = _lib.dlio_scan_scratch_bytes
 rnn_reserve_floats = _lib.dlio_rnn_reserve_floats
 rnn_bwd_scratch_floats = _lib.dlio_rnn_bwd_scratch_floats
 abi_version = _lib.dlio_abi_version

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdeeplio_b200.so")
-SOURCES = ["lib.cu", "conv_simt.cu", "conv_tc.cu", "conv_f16.cu", "conv_s2d.cu", "norm_pool.cu", "dense.cu", "rnn.cu", "optim.cu", "pose.cu"]
+SOURCES = ["lib.cu", "conv_simt.cu", "conv_tc.cu", "conv_f16.cu", "conv_s2d.cu", "norm_pool.cu", "dense.cu", "rnn.cu", "optim.cu", "pose.cu", "scan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -54,7 +54,8 @@ def _trace_mask(run, cname, y, bnv, pre_relu, relu, res, res_mode, c_off):
     if pre_relu:
         m = y.t > 0                                       # y holds relu(conv + bias): positive <=> the ReLU passed it
     elif relu:
-        v = torch.addcmul(bnv[3], y.t, bnv[2])
+        # the kernels evaluate fmaf(scale, y, shift): a single rounding of the exact value, which fp64 holds exactly
+        v = (y.t.double() * bnv[2].double() + bnv[3].double()).float()
         if res is not None and res_mode == 1:
             if res.t is None:
                 return
@@ -366,6 +367,8 @@ def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool
         L.bn_act_pool_fwd(y.t4, ptr(y.t), ptr(bnv[2]), ptr(bnv[3]), res.t4 if res is not None else dummy,
                           ptr(res.t) if res is not None else None, bp, out.t4, ptr(out.t), ptr(out.lo), ptr(out.h2),
                           ptr(out.bound) if out.h2 is not None else None, ptr(idx), ptr(ymax), st)
+        if MASK_TRACE is not None and idx is not None:
+            MASK_TRACE[getattr(run, "trace_prefix", "") + cname + "#pool"] = idx.permute(0, 3, 1, 2).cpu()
         result = out
     if not run.record:
         return result
@@ -536,7 +539,7 @@ def se_layer(run, x, prefix, out_pad=(0, 0)):
     return out
 
 
-def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
+def max_pool(run, x, stride, ceil=False, out_pad=(0, 0), name=None):
     """MaxPool2d(3, stride, padding=1) on its own (PointSeg pools, pointseg_net.py:28,35,43,50)."""
     st = stream()
     oh, ow = pool_out(x.h, stride[0], ceil), pool_out(x.w, stride[1], ceil)
@@ -545,6 +548,8 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0)):
     idx = run.empty(x.n, oh, ow, x.c, dtype=torch.uint8) if run.record else None
     L.bn_act_pool_fwd(x.t4, ptr(x.t), None, None, x.t4, None, bp, out.t4, ptr(out.t), ptr(out.lo), None, None,
                       ptr(idx), None, st)
+    if MASK_TRACE is not None and idx is not None and name:
+        MASK_TRACE[getattr(run, "trace_prefix", "") + name] = idx.permute(0, 3, 1, 2).cpu()
     out.bound = x.bound
     if not run.record:
         return out

@@ -88,6 +88,7 @@ class GraphedTrainStep:
                 self.graphs.append(graph)
                 self.static_losses.append(loss)
             self.graph, self.static_loss = self.graphs[0], self.static_losses[0]
+            Fn._drop_counter[0] = drop0                # the capture drew its seeds; no step has run yet
         finally:
             Fn._seed_epoch[0] = prev
 

@@ -231,7 +231,7 @@ class PointSegEncoder(_Encoder):
                 elif e[0] == "S":
                     t = E.se_layer(run, t, q, out_pad=(1, 1))
                 else:
-                    t = E.max_pool(run, t, e[1], ceil=False, out_pad=(1, 1))
+                    t = E.max_pool(run, t, e[1], ceil=False, out_pad=(1, 1), name=q + "pool")
         E.global_avg(run, t, feat, ld, off)  # adaptive_avg_pool2d outside the encoder (lidar_feat_nets.py:84-85)
 
 

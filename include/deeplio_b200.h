@@ -393,6 +393,28 @@ int dlio_pair_gather(const float *frames, long long sb, long long sf, long long 
                      const int *combinations, int S, int c0, int C, dlio_tensor4 dst, float *dst_ptr, float *dst_lo,
                      int *flags, int flag_bit, void *stream);
 
+/* ------------------------------------------------------------------ LiDAR / IMU preprocessing (N4)
+ * dlio_scan_project: one velodyne frame -> range image channels, replacing LaserScan.open_scan's depth filter +
+ * do_range_projection + do_normal_projection (deeplio/common/laserscan.py:86-91,122-191,215-248) and the image assembly
+ * / mean subtraction / channel selection of KittiRawData.get_velo_image + Kitti.transform_images (deeplio/datasets/
+ * kitti.py:83-97,345-364).  points4 [n_points, 4] = (x, y, z, remission) as in the .bin files (utils.py:168-171),
+ * 16-byte aligned.  The 8 channels are (x, y, z) / max_depth, remission, normal (3), range; `channels` (HOST array)
+ * selects n_channels of them (config.yaml `channels`), mean8 (HOST, 8 floats, may be NULL) is subtracted in
+ * out_normed.  Outputs, each optional: out_org / out_normed [n_channels, H, W] planar; out_idx [H, W] = index of the
+ * winning point in points4 (-1: empty pixel).  The nearest point wins a pixel (lower index on an exact depth tie).
+ * scratch: dlio_scan_scratch_bytes(H, W) bytes (the 64-bit z-buffer), 8-byte aligned. */
+size_t dlio_scan_scratch_bytes(int H, int W);
+int dlio_scan_project(const float *points4, int n_points, int H, int W, float fov_up_deg, float fov_down_deg,
+                      float min_depth, float max_depth, const int *channels, int n_channels, const float *mean8,
+                      void *scratch, float *out_org, float *out_normed, int *out_idx, void *stream);
+/* IMU windowing, Kitti.load_imus + transform_imus (kitti.py:317-343,366-368): ts [m] (sorted, seconds, fp64) and imu
+ * [m, 6] = (ax, ay, az, wx, wy, wz) of the OXTS stream, velo_ts [n_frames] the LiDAR timestamps; window w holds the
+ * samples with velo_ts[w] <= ts < velo_ts[w+1], zero-padded / truncated to T rows, then (v - mean6) / std6 (HOST
+ * arrays, may both be NULL) applied to every row, padding included, as the reference does.  out [n_frames-1, T, 6];
+ * valid [n_frames-1] (optional): 0 where a window is empty. */
+int dlio_imu_windows(const double *ts, const float *imu, int m, const double *velo_ts, int n_frames, int T,
+                     const float *mean6, const float *std6, float *out, int *valid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

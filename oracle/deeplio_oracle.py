@@ -50,12 +50,40 @@ def _bn(sd, p, x, training):
 # convolution that feeds it (tests count ReLU-mask disagreements between the B200 path and this oracle:
 # tests/test_gpu_model.py, tests/test_gpu_fullsize.py)
 TRACE = None
+# When a dict (same keys, bool masks), the listed ReLUs apply THAT mask instead of their own input > 0: the gradient
+# tests impose the B200 path's ReLU decisions on the fp64 oracle, so that the comparison is about arithmetic and not
+# about which side of zero a 1e-7 input landed on (a parameter gradient is a sum of up to 10^8 terms of random sign:
+# one flipped decision moves it by ~1 / sqrt(terms), far above the 2e-4 parity bar)
+FORCE_MASKS = None
 
 
 def _relu(x, key):
     if TRACE is not None:
         TRACE[key] = x.detach() > 0
+    if FORCE_MASKS is not None and key in FORCE_MASKS:
+        return x * FORCE_MASKS[key].to(x.dtype)
     return F.relu(x)
+
+
+def _pool(x, stride, ceil_mode, key):
+    """MaxPool2d(3, stride, padding=1).  With TRACE: stores the window-relative arg-max (uint8, dy * 3 + dx, NCHW) under
+    ``key``; with FORCE_MASKS[key]: takes the window element THAT index names instead of the maximum (the B200
+    path's arg-max decisions imposed on the oracle, as for the ReLU masks)."""
+    if TRACE is None and (FORCE_MASKS is None or key not in FORCE_MASKS):
+        return F.max_pool2d(x, 3, stride, 1, ceil_mode=ceil_mode)
+    sh, sw = stride
+    n, c, h, w = x.shape
+    y, flat = F.max_pool2d(x, 3, stride, 1, ceil_mode=ceil_mode, return_indices=True)
+    oh, ow = y.shape[2:]
+    top = (torch.arange(oh) * sh - 1).view(1, 1, oh, 1)
+    left = (torch.arange(ow) * sw - 1).view(1, 1, 1, ow)
+    if TRACE is not None:
+        TRACE[key] = (((flat // w) - top) * 3 + ((flat % w) - left)).to(torch.uint8)
+    if FORCE_MASKS is not None and key in FORCE_MASKS:
+        r = FORCE_MASKS[key].long()
+        iy, ix = top + r // 3, left + r % 3
+        return x.flatten(2).gather(2, (iy * w + ix).flatten(2)).view(n, c, oh, ow)
+    return y
 
 
 def _conv(sd, p, x, stride=(1, 1)):
@@ -74,23 +102,23 @@ def simple1_encoder(sd, p, x, training, bypass=False):
     def blk(i, t, stride=(1, 1)):
         return _bn(sd, "%sbn%d" % (p, i), _relu(_conv(sd, "%sconv%d" % (p, i), t, stride), "%sconv%d" % (p, i)), training)
 
-    def pool(t, stride):
-        return F.max_pool2d(t, 3, stride, 1, ceil_mode=True)
+    def pool(t, stride, i):
+        return _pool(t, stride, True, "%sconv%d#pool" % (p, i))
 
-    t = pool(blk(1, x, (1, 2)), (1, 2))
-    t = pool(blk(2, t), (1, 2))
+    t = pool(blk(1, x, (1, 2)), (1, 2), 1)
+    t = pool(blk(2, t), (1, 2), 2)
     t = blk(3, t)
     ident = t
     t = blk(4, t)
     if bypass:
         t = t + ident
-    t = pool(t, (2, 2))
+    t = pool(t, (2, 2), 4)
     t = blk(5, t)
     ident = t
     t = blk(6, t)
     if bypass:
         t = t + ident
-    t = pool(t, (2, 2))
+    t = pool(t, (2, 2), 6)
     t = blk(7, t)
     return t.mean(dim=(2, 3))
 
@@ -116,7 +144,7 @@ def resnet_encoder(sd, p, x, training):
     """ResNetEncoder (resnet.py:36-108) over torchvision BasicBlock
     (torchvision/models/resnet.py:59-105, v0.26.0)."""
     t = _relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x), training), p + "conv1")
-    t = F.max_pool2d(t, 3, (1, 2), 1)
+    t = _pool(t, (1, 2), False, p + "conv1#pool")
     for lname, nblk, stride in _RESNET_LAYERS:
         for b in range(nblk):
             q = "%s%s.%d." % (p, lname, b)
@@ -156,7 +184,7 @@ _POINTSEG = [("fire_blk1", ["F", "F", "S", "P12"]), ("fire_blk2", ["F", "F", "S"
 def pointseg_encoder(sd, p, x, training, bypass="simple"):
     """PSEncoder (pointseg_net.py:18-71)."""
     t = _relu(_bn(sd, p + "conv1a.1", _conv(sd, p + "conv1a.0", x, (1, 2)), training), p + "conv1a.0")
-    t = F.max_pool2d(t, 3, (1, 2), 1)
+    t = _pool(t, (1, 2), False, p + "conv1a.0#pool")
     for bname, entries in _POINTSEG:
         for i, e in enumerate(entries):
             q = "%s%s.%d." % (p, bname, i)
@@ -167,9 +195,9 @@ def pointseg_encoder(sd, p, x, training, bypass="simple"):
             elif e == "S":
                 t = _se(sd, q, t)
             elif e == "P12":
-                t = F.max_pool2d(t, 3, (1, 2), 1)
+                t = _pool(t, (1, 2), False, q + "pool")
             else:
-                t = F.max_pool2d(t, 3, (2, 2), 1)
+                t = _pool(t, (2, 2), False, q + "pool")
     return t.mean(dim=(2, 3))  # adaptive_avg_pool2d outside the encoder (lidar_feat_nets.py:84-85)
 
 

@@ -22,7 +22,9 @@ for r in csv.DictReader(lines):
         d[r["Metric Name"]] = v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 items = list(by_id.values())
 adam = [i for i, d in enumerate(items) if "adam_kernel" in d["name"]]
-step = items[adam[0] + 1:adam[1] + 1]
+# one optimizer step = a run of consecutive adam launches (one per parameter group)
+ends = [i for k, i in enumerate(adam) if k + 1 == len(adam) or adam[k + 1] != i + 1]
+step = items[ends[0] + 1:ends[1] + 1]
 total = sum(d["ms"] for d in step)
 agg = collections.OrderedDict()
 for d in step:

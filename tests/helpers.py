@@ -74,15 +74,34 @@ def perturbed_grads(cfg, sd64, in64, draws):
 
 
 def count_relu_flips(ours, oracle, prefix="lidar_feat_net."):
-    """ReLU-mask disagreements between the B200 path (engine.MASK_TRACE: bool masks, NCHW) and the oracle
-    (oracle.TRACE, same form): {layer: (flipped elements, total elements)} for the layers both sides recorded."""
+    """Discrete decisions on which the B200 path (engine.MASK_TRACE: ReLU masks, bool NCHW; max-pool arg-max, uint8
+    NCHW under '<conv>#pool') and the oracle (oracle.TRACE, same form) disagree: {layer: (differing, total)}."""
     flips = {}
     for k, m in ours.items():
         ref = oracle.get(prefix + k)
-        if ref is None or tuple(ref.shape) != tuple(m.shape):
-            continue
+        assert ref is not None and tuple(ref.shape) == tuple(m.shape), ("decision trace mismatch", k)
         flips[k] = (int((m != ref).sum()), m.numel())
     return flips
+
+
+def forced_oracle_step(cfg, sd, inputs, decisions, dtype=torch.float64, prefix="lidar_feat_net."):
+    """One train-mode forward + backward of the oracle in ``dtype`` with the B200 path's discrete decisions (ReLU
+    masks and max-pool arg-max, engine.MASK_TRACE) imposed on it.  Returns (pos, ori, grads, the oracle's OWN
+    decisions for ``count_relu_flips``).  Why: a parameter gradient is a sum of 10^5 .. 10^8 terms of random sign, so
+    one ReLU input (or one pair of pooling candidates) within round-off of a tie, decided the other way, moves it by
+    ~1 / sqrt(terms) -- 1e-3 .. 1e-4, above the 2e-4 bar -- in ANY two fp32 implementations (the fp32 oracle against
+    the fp64 oracle included).  With the decisions imposed, what is compared is the arithmetic."""
+    def cast(t):
+        return t.to(dtype) if t.is_floating_point() else t
+    O.TRACE = {}
+    O.FORCE_MASKS = {prefix + k: v for k, v in decisions.items()}
+    try:
+        pos, ori, grads, _ = oracle_train_step(cfg, {k: cast(v) for k, v in sd.items()}, tuple(cast(t) for t in inputs))
+        own = O.TRACE
+    finally:
+        O.TRACE = None
+        O.FORCE_MASKS = None
+    return pos, ori, grads, own
 
 
 def grad_rows(grads, g64, g32=None, gperts=()):

