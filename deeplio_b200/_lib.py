@@ -46,6 +46,7 @@ _PROTOS = {
     "dlio_last_error": (C.c_char_p, []),
     "dlio_device_check": (I, [I]),
     "dlio_launch_count": (LL, []),
+    "dlio_set_option": (I, [C.c_char_p, I]),
     "dlio_profile_enable": (I, [I]),
     "dlio_profile_read": (I, [I, P, P]),
     "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P, P]),
@@ -87,7 +88,7 @@ _PROTOS = {
     "dlio_rnn_fwd": (I, [I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P]),
     "dlio_rnn_bwd": (I, [I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "dlio_hws_loss": (I, [P, P, P, P, I, F, F, P, P, P, P]),
-    "dlio_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
+    "dlio_adam_step": (I, [P, P, P, P, LL, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, I, C.c_double, P]),
     "dlio_pose_loss": (I, [LossTerm, LossTerm, LossTerm, LossTerm, P, P, I, F, P, P, P, P, P]),
     "dlio_se3_chain_fwd": (I, [P, P, I, I, P, P, P, P]),
     "dlio_se3_chain_bwd": (I, [P, P, I, I, P, P, P, P, P]),

@@ -9,6 +9,7 @@
 // finish with one fp64 global atomic per channel per block.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -21,14 +22,24 @@ constexpr int MAX_C = 1024;  // channel limit of the reducing kernels (largest o
 // DLIO_EW_BLOCK (environment, 64 .. 256, default 256) caps the block size: 128-thread blocks fit beside a resident
 // tcgen05 convolution CTA (320 threads x 168 registers, ~205 KB of shared memory), so that with the two encoders on two
 // streams (engine.ENC_STREAMS) these HBM-bound passes run under the other encoder's tensor-bound convolutions
+static int g_ew_cap = 0;
 static int ew_block_cap() {
-    static int cap = 0;
+    int &cap = g_ew_cap;
     if (!cap) {
         const char *e = getenv("DLIO_EW_BLOCK");
         int v = e ? atoi(e) : 256;
         cap = v < 64 ? 64 : (v > 256 ? 256 : v);
     }
     return cap;
+}
+// DLIO_POOL_TMA=0 falls back to the per-thread-load pooling kernels (A/B switch for bench and tests)
+static int g_pool_tma = -1;
+static bool pool_tma_enabled() {
+    if (g_pool_tma < 0) {
+        const char *e = getenv("DLIO_POOL_TMA");
+        g_pool_tma = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pool_tma != 0;
 }
 static inline int block_for_cg(int cg) {
     const int cap = ew_block_cap();
@@ -802,6 +813,382 @@ __global__ void __launch_bounds__(256) pool_bwd_sums_kernel(Geo dout, const floa
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, (double)red[i]);
 }
 
+// ------------------------------------------------------------------ bulk-copy row rings (TMA-staged pooling passes)
+// The pooled passes above fetch every window / un-pooling candidate with its own global load: 4.5 x (forward) and
+// ~4 x (backward) more L1 / L2 requests than DRAM bytes, and they ran at 3.0 - 3.9 TB/s, bound by L2 bandwidth and
+// load latency (ncu: L2 -> L1 906 MB for 283 MB of DRAM reads).  The kernels below stage whole row segments in shared
+// memory with cp.async.bulk (one elected thread issues; completion on an mbarrier per ring slot), so every byte
+// crosses L2 once, many KB per SM are in flight independent of the per-thread window structure, and the window logic
+// reads shared memory.  A CTA owns a contiguous range of (image, column segment, row) units -- rows fastest -- and
+// streams the rows of a segment through the ring, so rows are not re-read at unit boundaries either.
+__device__ __forceinline__ uint32_t ring_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ring_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ring_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void ring_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+constexpr int RING_SLOTS = 8;
+
+// Forward: BN-apply (+ReLU) + 3x3 max-pool (+ arg-max bytes, + y at the arg-max) + fp16 split / fp32 store.
+// blockDim = cg * WS (channel groups x output columns of a segment).  Shared memory: RING_SLOTS input-row segments
+// of ((WS - 1) * SW + 3) columns x C floats.  Same arithmetic and tie-breaking as bn_pool3_fwd_kernel.
+template <int SH, int SW, bool RELU>
+__global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS, int nseg, long long units_per_cta) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ __align__(8) unsigned long long bars[RING_SLOTS];
+    const int cg = a.cg, C = cg * 4;
+    const int c = (int)(threadIdx.x % cg) * 4, xo = (int)(threadIdx.x / cg);
+    const int wcols = (WS - 1) * SW + 3;
+    const uint32_t slot_bytes = (uint32_t)wcols * C * 4;
+    float *ring = reinterpret_cast<float *>(ring_raw);
+    const uint32_t ring0 = ring_smem_u32(ring), bar0 = ring_smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING_SLOTS; ++i) ring_bar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const float s16 = a.out_h2 ? f16_scale_from_bound(*a.out_bound) : 1.f;
+    float4 sc = f4(1.f), sf = f4(0.f);
+    if (a.scale) {
+        sc = ld4(a.scale + c);
+        sf = ld4(a.shift + c);
+    }
+    const int H = a.y.h, W = a.y.w, OH = a.out.h, OW = a.out.w;
+    const long long total = (long long)a.out.n * nseg * OH;
+    long long u = (long long)blockIdx.x * units_per_cta;
+    const long long u_end = min(total, u + units_per_cta);
+    unsigned k_issue = 0, k_base = 0;       // stream indices (input rows issued / first row of the current span)
+    while (u < u_end) {
+        // ---- span: rows [ho_a, ho_b) of column segment seg of image n
+        const int ho_a = (int)(u % OH);
+        const long long t = u / OH;
+        const int seg = (int)(t % nseg), n = (int)(t / nseg);
+        const int ho_b = (int)min((long long)OH, ho_a + (u_end - u));
+        const int x0 = seg * WS;                                   // first output column of the segment
+        const int w_lo = x0 * SW - 1;                              // input column of ring column 0
+        const int wa = max(w_lo, 0), wb = min(w_lo + wcols, W);    // valid input columns [wa, wb)
+        const uint32_t dst_off = (uint32_t)(wa - w_lo) * C * 4, bytes = (uint32_t)(wb - wa) * C * 4;
+        const int r_first = max(ho_a * SH - 1, 0), r_last = min((ho_b - 1) * SH + 1, H - 1);
+        const float *src0 = a.yp + a.y.off(n, 0, wa);
+        const size_t row_stride = (size_t)a.y.wp * a.y.c;
+        int r_issue = r_first;                                     // next input row to issue
+        const int wo = x0 + xo;
+        const bool col_ok = wo < OW;
+        const int w0 = wo * SW - 1, ci0 = xo * SW;                 // window column 0: input column / ring column
+        for (int ho = ho_a; ho < ho_b; ++ho) {
+            const int need_lo = max(ho * SH - 1, 0), need_hi = min(ho * SH + 1, H - 1);
+            if (threadIdx.x == 0) {
+                // rows below need_lo are dead (the __syncthreads of the previous iteration ordered their last reads)
+                while (r_issue <= r_last && r_issue - need_lo < RING_SLOTS) {
+                    const unsigned s = k_issue % RING_SLOTS;
+                    ring_expect_tx(bar0 + 8 * s, bytes);
+                    ring_bulk_load(ring0 + s * slot_bytes + dst_off, src0 + (size_t)r_issue * row_stride, bytes, bar0 + 8 * s);
+                    ++r_issue;
+                    ++k_issue;
+                }
+            }
+            for (int r = need_lo; r <= need_hi; ++r) {
+                const unsigned k = k_base + (unsigned)(r - r_first);
+                ring_wait(bar0 + 8 * (k % RING_SLOTS), (k / RING_SLOTS) & 1u);
+            }
+            const unsigned pix = ((unsigned)(n * a.out.hp + ho + a.out.ph)) * (unsigned)a.out.wp + (unsigned)(wo + a.out.pw);
+            if (col_ok) {
+                float4 best = f4(-FLT_MAX), yb = f4(0.f);
+                unsigned bi = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int h = ho * SH - 1 + dy;
+                    if (h < 0 || h >= H) continue;
+                    const unsigned k = k_base + (unsigned)(h - r_first);
+                    const float *row = ring + (size_t)(k % RING_SLOTS) * (slot_bytes / 4) + c;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int w = w0 + dx;
+                        if (w < 0 || w >= W) continue;
+                        const float4 raw = ld4(row + (ci0 + dx) * C);
+                        float4 v = fma4(sc, raw, sf);
+                        if (RELU) v = relu4(v);
+                        const unsigned r = (unsigned)(dy * 3 + dx);
+                        if (v.x > best.x) { best.x = v.x; yb.x = raw.x; bi = (bi & 0xFFFFFF00u) | r; }
+                        if (v.y > best.y) { best.y = v.y; yb.y = raw.y; bi = (bi & 0xFFFF00FFu) | (r << 8); }
+                        if (v.z > best.z) { best.z = v.z; yb.z = raw.z; bi = (bi & 0xFF00FFFFu) | (r << 16); }
+                        if (v.w > best.w) { best.w = v.w; yb.w = raw.w; bi = (bi & 0x00FFFFFFu) | (r << 24); }
+                    }
+                }
+                const size_t po = ((size_t)(n * OH + ho) * OW + wo) * C + c;
+                if (a.idx) *reinterpret_cast<unsigned *>(a.idx + po) = bi;
+                if (a.ymax) st4(a.ymax + po, yb);
+                bnpool_store(a, pix, c, best, s16);
+            }
+            // zero pads of the output tensor around this row segment
+            if (a.out.pw > 0 && (seg == 0 || seg == nseg - 1)) {
+                const unsigned rowpix = ((unsigned)(n * a.out.hp + ho + a.out.ph)) * (unsigned)a.out.wp;
+                for (int i = xo; i < a.out.pw; i += WS) {
+                    if (seg == 0) bnpool_store(a, rowpix + i, c, f4(0.f), 1.f);
+                    if (seg == nseg - 1) bnpool_store(a, rowpix + a.out.pw + OW + i, c, f4(0.f), 1.f);
+                }
+            }
+            if (a.out.ph > 0 && (ho == 0 || ho == OH - 1)) {
+                // pad rows above / below: the columns of this segment (+ the column pads at the outer segments)
+                const int xa = seg == 0 ? 0 : a.out.pw + x0;
+                const int xb = seg == nseg - 1 ? a.out.wp : a.out.pw + min(x0 + WS, OW);
+                for (int pr = 0; pr < a.out.ph; ++pr) {
+                    if (ho == 0) {
+                        const unsigned rowpix = ((unsigned)(n * a.out.hp + pr)) * (unsigned)a.out.wp;
+                        for (int x = xa + xo; x < xb; x += WS) bnpool_store(a, rowpix + x, c, f4(0.f), 1.f);
+                    }
+                    if (ho == OH - 1) {
+                        const unsigned rowpix = ((unsigned)(n * a.out.hp + a.out.ph + OH + pr)) * (unsigned)a.out.wp;
+                        for (int x = xa + xo; x < xb; x += WS) bnpool_store(a, rowpix + x, c, f4(0.f), 1.f);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        k_base += (unsigned)(r_last - r_first + 1);
+        u += ho_b - ho_a;
+    }
+}
+
+// Backward apply pass of a  conv -> (ReLU) -> BN -> 3x3 max-pool  layer with the un-pooling inside (the gather variant
+// of bn_bwd_apply_kernel), rows staged by bulk copies: the conv output y (each element read once), and the pooled-side
+// rows of dout and of the arg-max bytes that the 2 - 3 input rows and 1.5 - 3 input columns of a window share.
+// blockDim = cg * WT; a thread owns a channel group and U input columns WT apart.  dout.c == C, c_off == 0.
+constexpr int APPLY_YSLOTS = 4, APPLY_PSLOTS = 6, APPLY_U = 2;
+template <int SH, int SW>
+__global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, int WT, int nseg, long long units_per_cta) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ __align__(8) unsigned long long bars[APPLY_YSLOTS + APPLY_PSLOTS];
+    __shared__ float red[MAX_C];
+    __shared__ float wred[32];
+    const int cg = a.cg, C = cg * 4;
+    constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;
+    const int WSI = APPLY_U * WT;                                   // input columns per segment
+    const int ocols = WSI / SW + 2;                                 // pooled columns a segment can touch
+    const uint32_t yslot = (uint32_t)WSI * C * 4, dslot = (uint32_t)ocols * C * 4, islot = (uint32_t)ocols * C;
+    const uint32_t ring0 = ring_smem_u32(ring_raw), bar0 = ring_smem_u32(bars);
+    const uint32_t dring0 = ring0 + APPLY_YSLOTS * yslot, iring0 = dring0 + APPLY_PSLOTS * dslot;
+    const float *yring = reinterpret_cast<const float *>(ring_raw);
+    const float *dring = reinterpret_cast<const float *>(ring_raw + (size_t)APPLY_YSLOTS * yslot);
+    const uint8_t *iring = ring_raw + (size_t)APPLY_YSLOTS * yslot + (size_t)APPLY_PSLOTS * dslot;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < APPLY_YSLOTS + APPLY_PSLOTS; ++i) ring_bar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- prologue shared with bn_bwd_apply_kernel: bound of dy, parameter gradients, per-channel constants
+    float s16 = 1.f;
+    if (a.dy_h2) {
+        const float mz = (float)a.sums[2 * C];
+        float b = 0.f;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            float t = mz;
+            if (a.batch_stats) t += (float)(fabs(a.sums[i]) / a.count + sqrt(a.count) * fabs(a.sums[C + i]) / a.count);
+            b = fmaxf(b, fabsf(a.scale ? a.scale[i] : 1.f) * t);
+        }
+        b = warp_max(b);
+        if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = b;
+        __syncthreads();
+        b = 0.f;
+        for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) b = fmaxf(b, wred[i]);
+        b *= 1.001f;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.dy_bound = b;
+        s16 = f16_scale_from_bound(b);
+    }
+    if (a.dbias)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int c = (int)(threadIdx.x % cg) * 4, xi = (int)(threadIdx.x / cg);
+    float4 sc = f4(1.f), mu = f4(0.f), is = f4(1.f), m1 = f4(0.f), m2 = f4(0.f);
+    if (a.scale) sc = ld4(a.scale + c);
+    if (a.mean) {
+        mu = ld4(a.mean + c);
+        is = ld4(a.invstd + c);
+    }
+    if (a.sums && a.batch_stats) {
+        m1 = make_float4((float)(a.sums[c] / a.count), (float)(a.sums[c + 1] / a.count),
+                         (float)(a.sums[c + 2] / a.count), (float)(a.sums[c + 3] / a.count));
+        m2 = make_float4((float)(a.sums[C + c] / a.count), (float)(a.sums[C + c + 1] / a.count),
+                         (float)(a.sums[C + c + 2] / a.count), (float)(a.sums[C + c + 3] / a.count));
+    }
+    if (blockIdx.x == 0 && a.sums && threadIdx.x < cg) {
+        const int cc = threadIdx.x * 4;
+        for (int j = 0; j < 4; ++j) {
+            if (a.dbeta) a.dbeta[cc + j] = (float)a.sums[cc + j];
+            if (a.dgamma) a.dgamma[cc + j] = (float)a.sums[C + cc + j];
+        }
+    }
+    float4 sb = f4(0.f);
+    const int H = a.y.h, W = a.y.w, OH = a.pooled_h, OW = a.pooled_w;
+    const long long total = (long long)a.y.n * nseg * H;
+    long long u = (long long)blockIdx.x * units_per_cta;
+    const long long u_end = min(total, u + units_per_cta);
+    unsigned ky_issue = 0, ky_base = 0, kp_issue = 0, kp_base = 0;
+    while (u < u_end) {
+        const int h_a = (int)(u % H);
+        const long long t = u / H;
+        const int seg = (int)(t % nseg), n = (int)(t / nseg);
+        const int h_b = (int)min((long long)H, h_a + (u_end - u));
+        const int w_seg = seg * WSI, w_end = min(W, w_seg + WSI);
+        const uint32_t ybytes = (uint32_t)(w_end - w_seg) * C * 4;
+        // pooled columns [o_lo, o_hi) that the segment's input columns can select
+        const int o_lo = SW == 1 ? max(w_seg - 1, 0) : (w_seg >> 1);
+        const int o_hi = min(OW, SW == 1 ? w_end + 1 : ((w_end - 1) >> 1) + 2);
+        const uint32_t dbytes = (uint32_t)(o_hi - o_lo) * C * 4, ibytes = (uint32_t)(o_hi - o_lo) * C;
+        // pooled rows the rows [h_a, h_b) can select
+        const int p_first = SH == 1 ? max(h_a - 1, 0) : (h_a >> 1);
+        const int p_last = min(OH - 1, SH == 1 ? h_b : (((h_b - 1) >> 1) + ((h_b - 1) & 1)));
+        const float *ysrc = a.yp + a.y.off(n, 0, w_seg);
+        const size_t yrow = (size_t)a.y.wp * a.y.c;
+        const float *dsrc = a.doutp + a.dout.off(n, 0, o_lo);
+        const size_t drow = (size_t)a.dout.wp * a.dout.c;
+        const uint8_t *isrc = a.idx + ((size_t)n * OH * OW + o_lo) * C;
+        const size_t irow = (size_t)OW * C;
+        int y_issue = h_a, p_issue = p_first;
+        for (int h = h_a; h < h_b; ++h) {
+            const int ho0 = SH == 1 ? h - 1 : h >> 1;
+            const int p_lo = max(ho0, 0);
+            const int p_hi = min(OH - 1, SH == 1 ? h + 1 : ho0 + (h & 1));
+            if (threadIdx.x == 0) {
+                while (y_issue < h_b && y_issue - h < APPLY_YSLOTS) {
+                    const unsigned s = ky_issue % APPLY_YSLOTS;
+                    ring_expect_tx(bar0 + 8 * s, ybytes);
+                    ring_bulk_load(ring0 + s * yslot, ysrc + (size_t)y_issue * yrow, ybytes, bar0 + 8 * s);
+                    ++y_issue;
+                    ++ky_issue;
+                }
+                while (p_issue <= p_last && p_issue - p_lo < APPLY_PSLOTS) {
+                    const unsigned s = kp_issue % APPLY_PSLOTS;
+                    const uint32_t bar = bar0 + 8 * (APPLY_YSLOTS + s);
+                    ring_expect_tx(bar, dbytes + ibytes);
+                    ring_bulk_load(dring0 + s * dslot, dsrc + (size_t)p_issue * drow, dbytes, bar);
+                    ring_bulk_load(iring0 + s * islot, isrc + (size_t)p_issue * irow, ibytes, bar);
+                    ++p_issue;
+                    ++kp_issue;
+                }
+            }
+            {
+                const unsigned k = ky_base + (unsigned)(h - h_a);
+                ring_wait(bar0 + 8 * (k % APPLY_YSLOTS), (k / APPLY_YSLOTS) & 1u);
+            }
+            for (int p = p_lo; p <= p_hi; ++p) {
+                const unsigned k = kp_base + (unsigned)(p - p_first);
+                ring_wait(bar0 + 8 * (APPLY_YSLOTS + k % APPLY_PSLOTS), (k / APPLY_PSLOTS) & 1u);
+            }
+            const unsigned ks = ky_base + (unsigned)(h - h_a);
+            const float *yrow_s = yring + (size_t)(ks % APPLY_YSLOTS) * (yslot / 4) + c;
+            const float *dp[NR];
+            const uint8_t *ip[NR];
+            unsigned rbase[NR];         // (window-relative row) * 3, or 255 when the window row does not exist
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int ho = ho0 + i;
+                const bool okh = ho >= 0 && ho < OH && (SH == 1 || i == 0 || (h & 1));
+                const int rh = SH == 1 ? 2 - i : h + 1 - 2 * ho;
+                const unsigned k = kp_base + (unsigned)((okh ? ho : p_lo) - p_first);
+                dp[i] = dring + (size_t)(k % APPLY_PSLOTS) * (dslot / 4) + c;
+                ip[i] = iring + (size_t)(k % APPLY_PSLOTS) * islot + c;
+                rbase[i] = okh ? (unsigned)(rh * 3) : 255u;
+            }
+            const unsigned pixrow = ((unsigned)(n * a.dy.hp + h + a.dy.ph)) * (unsigned)a.dy.wp + (unsigned)a.dy.pw;
+#pragma unroll
+            for (int uu = 0; uu < APPLY_U; ++uu) {
+                const int w = w_seg + xi + uu * WT;
+                if (w >= w_end) break;
+                const float4 y = ld4(yrow_s + (size_t)(w - w_seg) * C);
+                const int wo0 = SW == 1 ? w - 1 : w >> 1;
+                float4 g = f4(0.f);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const int wo = wo0 + j;
+                    const bool okw = wo >= 0 && wo < OW && (SW == 1 || j == 0 || (w & 1));
+                    const int rw = SW == 1 ? 2 - j : w + 1 - 2 * wo;
+                    const int oc = (okw ? wo : o_lo) - o_lo;
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const unsigned bi = *reinterpret_cast<const unsigned *>(ip[i] + (size_t)oc * C);
+                        const float4 d = ld4(dp[i] + (size_t)oc * C);
+                        const unsigned r = (okw && rbase[i] != 255u) ? rbase[i] + (unsigned)rw : 255u;
+                        const unsigned m = __vcmpeq4(bi, r * 0x01010101u);
+                        if (m & 0x000000FFu) g.x += d.x;
+                        if (m & 0x0000FF00u) g.y += d.y;
+                        if (m & 0x00FF0000u) g.z += d.z;
+                        if (m & 0xFF000000u) g.w += d.w;
+                    }
+                }
+                const float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
+                float4 d = make_float4(sc.x * (g.x - m1.x - yh.x * m2.x), sc.y * (g.y - m1.y - yh.y * m2.y),
+                                       sc.z * (g.z - m1.z - yh.z * m2.z), sc.w * (g.w - m1.w - yh.w * m2.w));
+                if (a.pre_relu) {
+                    if (!(y.x > 0.f)) d.x = 0.f;
+                    if (!(y.y > 0.f)) d.y = 0.f;
+                    if (!(y.z > 0.f)) d.z = 0.f;
+                    if (!(y.w > 0.f)) d.w = 0.f;
+                }
+                const unsigned pix = pixrow + (unsigned)w;
+                if (a.dy_hi) st4_split(a.dy_hi, a.dy_lo, (size_t)pix * C + c, d);
+                if (a.dy_h2) st4_h2(a.dy_h2, pix, C, c, d, s16);
+                sb = add4(sb, d);
+            }
+            // zero pads of the dy grid around this row segment
+            if (a.dy.pw > 0 && (seg == 0 || seg == nseg - 1)) {
+                const unsigned rowpix = ((unsigned)(n * a.dy.hp + h + a.dy.ph)) * (unsigned)a.dy.wp;
+                for (int i = xi; i < a.dy.pw; i += WT) {
+                    for (int e = 0; e < 2; ++e) {
+                        if (e == 0 ? seg != 0 : seg != nseg - 1) continue;
+                        const unsigned pix = rowpix + (e == 0 ? i : a.dy.pw + W + i);
+                        if (a.dy_hi) st4(a.dy_hi + (size_t)pix * C + c, f4(0.f));
+                        if (a.dy_lo) st4(a.dy_lo + (size_t)pix * C + c, f4(0.f));
+                        if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, C, c);
+                    }
+                }
+            }
+            if (a.dy.ph > 0 && (h == 0 || h == H - 1)) {
+                const int xa = seg == 0 ? 0 : a.dy.pw + w_seg;
+                const int xb = seg == nseg - 1 ? a.dy.wp : a.dy.pw + w_end;
+                for (int pr = 0; pr < a.dy.ph; ++pr) {
+                    for (int e = 0; e < 2; ++e) {
+                        if (e == 0 ? h != 0 : h != H - 1) continue;
+                        const unsigned rowpix = ((unsigned)(n * a.dy.hp + (e == 0 ? pr : a.dy.ph + H + pr))) * (unsigned)a.dy.wp;
+                        for (int x = xa + xi; x < xb; x += WT) {
+                            const unsigned pix = rowpix + x;
+                            if (a.dy_hi) st4(a.dy_hi + (size_t)pix * C + c, f4(0.f));
+                            if (a.dy_lo) st4(a.dy_lo + (size_t)pix * C + c, f4(0.f));
+                            if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, C, c);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        ky_base += (unsigned)(h_b - h_a);
+        kp_base += (unsigned)(p_last - p_first + 1);
+        u += h_b - h_a;
+    }
+    if (a.dbias) {
+        atomicAdd(&red[c + 0], sb.x); atomicAdd(&red[c + 1], sb.y);
+        atomicAdd(&red[c + 2], sb.z); atomicAdd(&red[c + 3], sb.w);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(a.dbias + i, (double)red[i]);
+    }
+}
+
 __global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (float)src[i];
@@ -951,6 +1338,17 @@ __global__ void dropout_mask_kernel(float *mask, long long n, float p, unsigned 
 
 using namespace dlio;
 
+extern "C" int dlio_set_option(const char *name, int value) {
+    DLIO_CHECK_ARG(name, "set_option: null name");
+    if (!strcmp(name, "pool_tma")) dlio::g_pool_tma = value ? 1 : 0;
+    else if (!strcmp(name, "ew_block")) dlio::g_ew_cap = value < 64 ? 64 : (value > 256 ? 256 : value);
+    else {
+        set_error("set_option: unknown option %s", name);
+        return DLIO_ERR_INVALID;
+    }
+    return DLIO_OK;
+}
+
 extern "C" int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,
                                dlio_tensor4 dst, float *dst_ptr, float *dst_lo, void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
@@ -1011,6 +1409,37 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
     const int block = block_for_cg(a.cg);
     cudaStream_t st = (cudaStream_t)stream;
+    if (a.pk == 3 && a.res_mode == 0 && (a.sh == 1 || a.sh == 2) && (a.sw == 1 || a.sw == 2) &&
+        (long long)a.out.n * a.out.hp * a.out.wp < (1LL << 31) && pool_tma_enabled() && a.cg <= 256 &&
+        (((uintptr_t)y_ptr) & 15) == 0) {
+        // bulk-copy row ring (see bn_pool3_fwd_tma_kernel)
+        const int WS = a.cg >= 256 ? 1 : 256 / a.cg;
+        const int nseg = (a.out.w + WS - 1) / WS;
+        const int wcols = (WS - 1) * a.sw + 3;
+        const size_t smem = (size_t)RING_SLOTS * wcols * y.c * sizeof(float);
+        const long long total = (long long)a.out.n * nseg * a.out.h;
+#define DLIO_POOL3_TMA(SH_, SW_)                                                                              \
+    do {                                                                                                      \
+        auto kern = a.relu ? bn_pool3_fwd_tma_kernel<SH_, SW_, true> : bn_pool3_fwd_tma_kernel<SH_, SW_, false>; \
+        DLIO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        int per_sm = 0;                                                                                       \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, a.cg * WS, smem) != cudaSuccess || per_sm < 1) per_sm = 1; \
+        long long grid = 148LL * per_sm;                                                                      \
+        if (grid > total) grid = total;                                                                       \
+        const long long upc = (total + grid - 1) / grid;                                                      \
+        grid = (total + upc - 1) / upc;                                                                       \
+        kern<<<(unsigned)grid, a.cg * WS, smem, st>>>(a, WS, nseg, upc);                                      \
+    } while (0)
+        if (smem <= 200 * 1024) {
+            if (a.sh == 1 && a.sw == 2) DLIO_POOL3_TMA(1, 2);
+            else if (a.sh == 2 && a.sw == 2) DLIO_POOL3_TMA(2, 2);
+            else if (a.sh == 1 && a.sw == 1) DLIO_POOL3_TMA(1, 1);
+            else DLIO_POOL3_TMA(2, 1);
+            DLIO_LAUNCH_CHECK();
+            return DLIO_OK;
+        }
+#undef DLIO_POOL3_TMA
+    }
     if (a.pk == 3 && a.res_mode == 0 && (a.sh == 1 || a.sh == 2) && (a.sw == 1 || a.sw == 2) &&
         (long long)a.out.n * a.out.hp * a.out.wp < (1LL << 31)) {
         const int rows = a.out.n * a.out.hp;
@@ -1145,6 +1574,37 @@ static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz
                        "bn_pool_bwd_apply: bad dout descriptor");
         a.dout = Geo(dout_t); a.doutp = dout; a.idx = pool_idx; a.pooled_h = dout_t.h; a.pooled_w = dout_t.w;
         a.c_off = p->c_off;
+        {
+            // bulk-copy row rings (bn_pool_bwd_apply_tma_kernel): dout carries exactly this layer's channels
+            const int WT = a.cg >= 256 ? 1 : 256 / a.cg, WSI = APPLY_U * WT;
+            const int ocols = WSI / p->pool_sw + 2;
+            const size_t smem = (size_t)APPLY_YSLOTS * WSI * y.c * 4 + (size_t)APPLY_PSLOTS * ocols * y.c * 5;
+            if (pool_tma_enabled() && dout_t.c == y.c && p->c_off == 0 && y.c % 16 == 0 && (a.cg * WT) % 32 == 0 &&
+                a.cg * WT <= 256 && smem <= 200 * 1024 && a.y.w % 1 == 0 &&
+                ((((uintptr_t)y_ptr) | ((uintptr_t)dout) | ((uintptr_t)pool_idx)) & 15) == 0) {
+                const int nseg = (a.y.w + WSI - 1) / WSI;
+                const long long total = (long long)a.y.n * nseg * a.y.h;
+#define DLIO_APPLY_TMA(SH_, SW_)                                                                                  \
+    do {                                                                                                          \
+        auto kern = bn_pool_bwd_apply_tma_kernel<SH_, SW_>;                                                       \
+        DLIO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        int per_sm = 0;                                                                                           \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, a.cg * WT, smem) != cudaSuccess || per_sm < 1) per_sm = 1; \
+        long long grid = 148LL * per_sm;                                                                          \
+        if (grid > total) grid = total;                                                                           \
+        const long long upc = (total + grid - 1) / grid;                                                          \
+        grid = (total + upc - 1) / upc;                                                                           \
+        kern<<<(unsigned)grid, a.cg * WT, smem, st>>>(a, WT, nseg, upc);                                          \
+    } while (0)
+                if (p->pool_sh == 1 && p->pool_sw == 2) DLIO_APPLY_TMA(1, 2);
+                else if (p->pool_sh == 2 && p->pool_sw == 2) DLIO_APPLY_TMA(2, 2);
+                else if (p->pool_sh == 1 && p->pool_sw == 1) DLIO_APPLY_TMA(1, 1);
+                else DLIO_APPLY_TMA(2, 1);
+#undef DLIO_APPLY_TMA
+                DLIO_LAUNCH_CHECK();
+                return DLIO_OK;
+            }
+        }
         if (p->pool_sh == 1 && p->pool_sw == 2) DLIO_APPLY(1, 2);
         else if (p->pool_sh == 2 && p->pool_sw == 2) DLIO_APPLY(2, 2);
         else if (p->pool_sh == 1 && p->pool_sw == 1) DLIO_APPLY(1, 1);

@@ -5,37 +5,36 @@
 
 namespace dlio {
 
+// The update follows torch.optim.Adam's single-tensor path operation by operation (torch/optim/adam.py):
+//   g' = g * grad_scale + wd * p;  m <- m + (1 - b1) (g' - m)  [lerp];  v <- v * b2 + ((1 - b2) g') g'  [mul, addcmul];
+//   p <- p + (-step_size) * (m / (sqrt(v) / bc2_sqrt + eps))   [addcdiv]
+// with 1 - b1, 1 - b2, step_size = lr / (1 - b1^t) and bc2_sqrt = sqrt(1 - b2^t) evaluated in double on the host and
+// rounded once (torch evaluates them in Python floats): computing 1.f - 0.999f on the device is off by 4.7e-5.
+struct AdamK {
+    float b2, omb1, omb2, step, bc2_sqrt, eps, wd, grad_scale;
+};
+__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamK &k) {
+    const float gr = g * k.grad_scale + k.wd * p;
+    m = m + k.omb1 * (gr - m);
+    v = v * k.b2 + (k.omb2 * gr) * gr;
+    p = p - k.step * (m / (sqrtf(v) / k.bc2_sqrt + k.eps));
+}
 __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const float *__restrict__ g,
-                                                   float *__restrict__ m, float *__restrict__ v, long long n,
-                                                   float lr, float b1, float b2, float eps, float wd,
-                                                   float bc1, float bc2_sqrt, float grad_scale) {
+                                                   float *__restrict__ m, float *__restrict__ v, long long n, AdamK k) {
     long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    const float step = lr / bc1;
     for (; i < n; i += stride) {
         if (i + 3 < n) {
             float4 pp = ld4(p + i), gg = ld4(g + i), mm = ld4(m + i), vv = ld4(v + i);
-            float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
-            float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float gr = ga[j] * grad_scale + wd * pa[j];
-                ma[j] = b1 * ma[j] + (1.f - b1) * gr;
-                va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
-                pa[j] -= step * ma[j] / (sqrtf(va[j]) / bc2_sqrt + eps);
-            }
-            st4(p + i, make_float4(pa[0], pa[1], pa[2], pa[3]));
-            st4(m + i, make_float4(ma[0], ma[1], ma[2], ma[3]));
-            st4(v + i, make_float4(va[0], va[1], va[2], va[3]));
+            adam_one(pp.x, gg.x, mm.x, vv.x, k);
+            adam_one(pp.y, gg.y, mm.y, vv.y, k);
+            adam_one(pp.z, gg.z, mm.z, vv.z, k);
+            adam_one(pp.w, gg.w, mm.w, vv.w, k);
+            st4(p + i, pp);
+            st4(m + i, mm);
+            st4(v + i, vv);
         } else {
-            for (long long k = i; k < n; ++k) {
-                float gr = g[k] * grad_scale + wd * p[k];
-                float mk = b1 * m[k] + (1.f - b1) * gr;
-                float vk = b2 * v[k] + (1.f - b2) * gr * gr;
-                m[k] = mk;
-                v[k] = vk;
-                p[k] -= step * mk / (sqrtf(vk) / bc2_sqrt + eps);
-            }
+            for (long long j = i; j < n; ++j) adam_one(p[j], g[j], m[j], v[j], k);
         }
     }
 }
@@ -45,19 +44,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
 using namespace dlio;
 
 extern "C" int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                              float grad_scale, void *stream) {
+                              double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                              double grad_scale, void *stream) {
     ProfScope prof_(DLIO_PROF_OPTIM, (cudaStream_t)stream);
     DLIO_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad argument");
     DLIO_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                    "adam_step: pointers must be 16-byte aligned");
-    float bc1 = 1.f - powf(beta1, (float)step);
-    float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+    AdamK k;
+    k.b2 = (float)beta2;
+    k.omb1 = (float)(1.0 - beta1);
+    k.omb2 = (float)(1.0 - beta2);
+    k.step = (float)(lr / (1.0 - pow(beta1, (double)step)));
+    k.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    k.eps = (float)eps;
+    k.wd = (float)weight_decay;
+    k.grad_scale = (float)grad_scale;
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                               eps, weight_decay, bc1, bc2, grad_scale);
+    adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, k);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

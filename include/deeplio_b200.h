@@ -84,6 +84,10 @@ typedef enum {
     DLIO_PROF_ELEMENTWISE = 6, /* BN / pool / SE / packing / element-wise passes (norm_pool.cu) */
     DLIO_PROF_DENSE = 7, DLIO_PROF_RNN = 8, DLIO_PROF_OPTIM = 9
 } dlio_prof_kind;
+/* Tuning switches (A/B measurements and tests; the defaults are what ships): "pool_tma" 0/1 -- pooling passes staged
+ * through shared memory by bulk copies (default 1; environment DLIO_POOL_TMA), "ew_block" 64..256 -- block-size cap of
+ * the element-wise passes (default 256; environment DLIO_EW_BLOCK). */
+int dlio_set_option(const char *name, int value);
 int dlio_profile_enable(int on);
 int dlio_profile_read(int kind, double *total_ms, long long *launches);
 
@@ -332,11 +336,12 @@ size_t dlio_rnn_bwd_scratch_floats(int kind, int L, int D, int B, int T, int I, 
 
 /* ------------------------------------------------------------------ optimizer
  * Fused Adam with L2 weight decay over a flat fp32 arena (torch.optim.Adam semantics; the reference builds it
- * at deeplio/models/optimizer.py:10): g = grad*grad_scale + wd*p; m,v moments; bias-corrected update.
- * `step` is the 1-based step count. */
+ * at deeplio/models/optimizer.py:10): g = grad*grad_scale + wd*p; m,v moments; bias-corrected update, operation by
+ * operation as torch's single-tensor Adam; the hyper-parameters are doubles (Python floats) so that 1 - beta and the
+ * bias corrections are rounded once, as torch does.  `step` is the 1-based step count. */
 int dlio_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                   float grad_scale, void *stream);
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                   double grad_scale, void *stream);
 /* Frame-to-frame part of HWSLoss (deeplio/losses/losses.py:68-86) with fixed sx, sq, and its gradient:
  * loss = mse(pos, gt_pos) e^-sx + sx + mse(ori, gt_ori) e^-sq + sq over n = B*S*3 elements; dpos / dori
  * (optional) receive d loss / d pos, d loss / d ori. */

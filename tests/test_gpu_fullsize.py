@@ -198,8 +198,7 @@ def test_reference_default_resolution_57x720(kw):
     widths -- ceil-mode pools with overhanging windows, H-stride-2 layers over an odd number of rows, W-strided
     layers whose input width is odd (no pixel-pair view: they take the CUDA-core path).  Train-mode forward at 2e-5
     and every parameter gradient against an fp64 run of the oracle with the B200 path's discrete decisions imposed
-    (tests.helpers.forced_oracle_step), bar max(2e-4 of the tensor's largest entry, 4 x the fp32 oracle's own distance
-    from the fp64 one under the same decisions)."""
+    (tests.helpers.forced_oracle_step), every tensor at the plain bar: 2e-4 of its largest entry."""
     from deeplio_b200 import engine as E
     h, w, B, S, T = 57, 720, 2, 2, 15
     cfg = make_cfg(height=h, width=w, seq=S, odom_hidden=64, **kw)
@@ -219,7 +218,6 @@ def test_reference_default_resolution_57x720(kw):
     assert rel_err(pos.detach().cpu(), opos) < 2e-5
     assert rel_err(ori.detach().cpu(), oori) < 2e-5
     _, _, g64, own = forced_oracle_step(cfg, sd, inputs, mtrace)
-    g32 = forced_oracle_step(cfg, sd, inputs, mtrace, dtype=torch.float32)[2]
     flips = count_relu_flips(mtrace, own)
     n_flips, n_dec = sum(f for f, _ in flips.values()), sum(t for _, t in flips.values())
     params = dict(model.named_parameters())
@@ -227,19 +225,9 @@ def test_reference_default_resolution_57x720(kw):
     for k, p in params.items():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
         ours[k] = p.grad.cpu()
-    rows = grad_rows(ours, g64, g32)
+    rows = grad_rows(ours, g64)
     gmax = max(s_ for _, _, s_, _, _ in rows)
-    n_tight = n_ref_tight = n_both = 0
-    over = []
-    for k, e, scale, e_ref, _ in rows:
-        tight, ref_tight = e <= 2e-4 * scale + 1e-5 * gmax, e_ref <= 2e-4 * scale + 1e-5 * gmax
-        n_tight, n_ref_tight, n_both = n_tight + tight, n_ref_tight + ref_tight, n_both + (tight and ref_tight)
-        if e > max(2e-4 * scale, 4 * e_ref) + 1e-5 * gmax:
-            over.append((k, e / (scale + 1e-30), e_ref / (scale + 1e-30)))
-    diag({"test": "57x720", "case": kw["lidar"], "tensors": len(rows), "n_tight": int(n_tight), "n_ref_tight": int(n_ref_tight),
-          "n_both": int(n_both), "flips": n_flips, "decisions": n_dec, "over": over[:12]})
-    # the discrete decisions are imposed, so what is left is arithmetic: a tensor may exceed 2e-4 only where the fp32
-    # oracle itself is that far from fp64 (deep layers: BatchNorm over a few hundred samples), and then by at most 4x
+    over = [(k, e / (scale + 1e-30)) for k, e, scale, _, _ in rows if e > 2e-4 * scale + 1e-5 * gmax]
+    diag({"test": "57x720", "case": kw["lidar"], "tensors": len(rows), "flips": n_flips, "decisions": n_dec, "over": over[:12]})
     assert n_flips <= 2e-5 * n_dec + 2, (n_flips, n_dec)
     assert not over, over
-    assert n_both >= 0.95 * n_ref_tight, (n_both, n_ref_tight, n_tight, len(rows))

@@ -57,57 +57,33 @@ def test_model_matches_oracle_and_golden(name):
     opos, oori, ograds, osd = oracle_train_step(cfg, sd, inputs)
     assert rel_err(pos.detach().cpu(), opos) < FWD_TOL
     assert rel_err(ori.detach().cpu(), oori) < FWD_TOL
-    # gradients: every parameter, against an fp64 evaluation of the oracle WITH THE B200 PATH'S DISCRETE DECISIONS
-    # IMPOSED (ReLU masks, max-pool arg-max: tests.helpers.forced_oracle_step) -- a ReLU input within round-off of
-    # zero that lands on the other side moves a gradient by far more than any arithmetic error, in any two fp32
-    # implementations; the number of such differing decisions is recorded and bounded instead.  What is left is
-    # arithmetic plus smooth conditioning: in these small fixtures BatchNorm runs over as few as 32 samples, so a
-    # near-constant channel multiplies round-off by 1/sqrt(var + eps) (one such channel of PointSeg's fire_blk5 turns
-    # a 1e-6 input change into a 30 % change of its weight gradient).  That is MEASURED per tensor, with the same
-    # decisions imposed: sens = max(distance of the fp32 oracle from the fp64 one, largest change of the fp64
-    # gradient under four 2e-6 .. 4e-6 relative perturbations of every weight and input).  Bars: every tensor within
-    # max(GRAD_TOL, 4 sens); every tensor whose fp32-oracle error meets GRAD_TOL must meet GRAD_TOL here too, up to
-    # 5 % of them (the sensitivity estimate is itself a four-sample maximum).
+    # gradients: EVERY parameter at the plain bar GRAD_TOL (2e-4 of the tensor's largest entry; tensors whose exact
+    # gradient is zero -- a convolution bias in front of a train-mode BatchNorm -- are held to 1e-5 of the model's
+    # largest entry), against an fp64 evaluation of the oracle WITH THE B200 PATH'S DISCRETE DECISIONS IMPOSED (ReLU
+    # masks, max-pool arg-max: tests.helpers.forced_oracle_step).  A ReLU input within round-off of zero that lands on
+    # the other side moves a gradient -- a sum of thousands to 10^8 terms of random sign -- by ~1 / sqrt(terms), far
+    # more than any arithmetic error, in any two fp32 implementations (round 1 needed sensitivity-scaled bars for
+    # that); the differing decisions are counted and bounded instead (measured: 0 .. 12 of 2 .. 6 million).
     _, _, g64, own = forced_oracle_step(cfg, sd, inputs, mtrace)
     flips = count_relu_flips(mtrace, own)
     n_flips, n_dec = sum(f for f, _ in flips.values()), sum(t for _, t in flips.values())
     assert n_flips <= 2e-5 * n_dec + 2, (n_flips, n_dec)
-    g32 = forced_oracle_step(cfg, sd, inputs, mtrace, dtype=torch.float32)[2]
-    gperts = []
-    for seed, amp in ((99, 2e-6), (100, 2e-6), (101, 4e-6), (102, 4e-6)):
-        gen = torch.Generator().manual_seed(seed)
-
-        def jitter(t):
-            return t * (1.0 + amp * torch.randn(t.shape, generator=gen, dtype=torch.float64)) if t.is_floating_point() else t
-        gperts.append(forced_oracle_step(cfg, {k: jitter(v.double() if v.is_floating_point() else v) for k, v in sd.items()},
-                                         tuple(jitter(t.double()) for t in inputs), mtrace)[2])
     gmax = max(float(n) for n, _ in rec["grads"].values())
     params = dict(model.named_parameters())
     assert set(params) == set(ograds)
     ours = {k: (p.grad.cpu() if p.grad is not None else torch.zeros_like(ograds[k])) for k, p in params.items()}
-    rows = grad_rows(ours, g64, g32, gperts)
-    n_tight = n_ref_tight = n_both = 0
-    worst = (None, 0.0)
-    for k, e_ours, scale, e_ref, e_pert in rows:
-        sens = max(e_ref, e_pert)
-        tight = e_ours <= GRAD_TOL * scale + 1e-5 * gmax
-        ref_tight = e_ref <= GRAD_TOL * scale + 1e-5 * gmax
-        n_tight += tight
-        n_ref_tight += ref_tight
-        n_both += tight and ref_tight
-        if scale > 1e-3 * gmax and e_ours / scale > worst[1]:
-            worst = (k, e_ours / scale)
-        assert e_ours <= max(GRAD_TOL * scale, 4 * sens) + 1e-5 * gmax, (k, e_ours, e_ref, e_pert, scale)
-        # the reference-generated golden norms (natural decisions on both sides): flips included in the bar
+    rows = grad_rows(ours, g64)
+    worst = max((r for r in rows if r[2] > 1e-3 * gmax), key=lambda r: r[1] / r[2])
+    diag({"test": "golden", "case": name, "tensors": len(rows), "flips": n_flips, "decisions": n_dec,
+          "worst": (worst[0], worst[1] / worst[2])})
+    for k, e_ours, scale, _, _ in rows:
+        assert e_ours <= GRAD_TOL * scale + 1e-5 * gmax, (k, e_ours / (scale + 1e-30), scale, gmax)
+        # the reference-generated golden norms (each side with its own decisions): the oracle's own distance from the
+        # imposed-decision gradients bounds what the flips may move
         e_nat = (ograds[k].double() - g64[k]).abs().max().item()
         norm, head = rec["grads"][k]
-        bar = GRAD_TOL + 4 * max(sens, e_nat) / (scale + 1e-30)
+        bar = GRAD_TOL + 4 * e_nat / (scale + 1e-30)
         assert abs(ours[k].double().norm().item() - float(norm)) <= bar * float(norm) + 1e-5 * gmax, k
-    diag({"test": "golden", "case": name, "tensors": len(rows), "n_tight": int(n_tight), "n_ref_tight": int(n_ref_tight),
-          "n_both": int(n_both), "flips": n_flips, "decisions": n_dec, "worst": worst,
-          "over": [(k, e / (s_ + 1e-30), er / (s_ + 1e-30), ep / (s_ + 1e-30)) for k, e, s_, er, ep in rows
-                   if e > GRAD_TOL * s_ + 1e-5 * gmax][:12]})
-    assert n_both >= 0.95 * n_ref_tight, (n_both, n_ref_tight, n_tight, len(params))
     # dead-direction RNN parameters still get (zero) gradient tensors, so Adam + L2 decay updates them
     for k, p in params.items():
         if "_l1_reverse" in k:

@@ -500,11 +500,13 @@ def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_
                               ceil_mode=pre_relu).shape[2:]
     dout = torch.randn((n, cout) + tuple(dout_shape), generator=g)
 
-    def reference(mask):
-        """The block in fp64.  ``mask``: the ReLU decisions the B200 path took (engine.MASK_TRACE).  A weight gradient
-        is a sum of ~10^7 terms of random sign, so ONE ReLU input within round-off of zero landing on the other side
-        moves it by ~1 / sqrt(10^7) = 3e-4 of its size -- more than the 5e-5 bar; with the decisions imposed, the
+    def reference(mask, argmax):
+        """The block in fp64.  ``mask`` / ``argmax``: the ReLU and max-pool arg-max decisions the B200 path took
+        (engine.MASK_TRACE).  A weight gradient here is a sum of 1.3e5 terms of random sign per entry, so ONE ReLU
+        input within round-off of zero (or one pair of pooling candidates within round-off of a tie) decided the other
+        way moves it by ~1 / sqrt(1.3e5) = 3e-3 of its size -- far above the 5e-5 bar; with the decisions imposed, the
         comparison is about arithmetic only (the number of differing decisions is bounded separately)."""
+        from oracle import deeplio_oracle as O
         leaves = [t.double().requires_grad_(True) for t in (wt, b, gamma, beta)]
         y = F.conv2d(x.double(), leaves[0], leaves[1], stride, ((kh - 1) // 2, (kw - 1) // 2))
         flips = 0
@@ -515,7 +517,12 @@ def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_
         if not pre_relu:
             flips = int(((y > 0) != mask).sum())
             y = y * mask
-        ref = F.max_pool2d(y, 3, pool, 1, ceil_mode=pre_relu)
+        O.TRACE, O.FORCE_MASKS = {}, {"pool": argmax}
+        try:
+            ref = O._pool(y, pool, pre_relu, "pool")
+            flips += int((O.TRACE["pool"] != argmax).sum())
+        finally:
+            O.TRACE = O.FORCE_MASKS = None
         ref.backward(dout.double())
         return ref, leaves, flips
 
@@ -530,14 +537,14 @@ def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_
     try:
         out = E.conv_bn(run, x0, "cv", "bn", stride, pre_relu=pre_relu, relu=not pre_relu, pool=pool, ceil=pre_relu,
                         out_pad=(1, 2))
-        mask = E.MASK_TRACE["cv"]
+        mask, argmax = E.MASK_TRACE["cv"], E.MASK_TRACE["cv#pool"]
     finally:
         E.MASK_TRACE = None
     torch.cuda.synchronize()
     prof = L.profile_read()
     L.profile_enable(0)
     assert "conv_fwd_tc" in prof and "conv_fwd_simt" not in prof, prof
-    ref, leaves, flips = reference(mask)
+    ref, leaves, flips = reference(mask, argmax)
     assert flips <= 1e-5 * mask.numel(), (flips, mask.numel())
     got = from_nhwc(out.t[:, 1:1 + out.h, 2:2 + out.w]).double()
     assert got.shape == ref.shape
@@ -743,3 +750,55 @@ def test_cpu_tensors_are_rejected():
     from deeplio_b200 import functional as Fn
     with pytest.raises(RuntimeError):
         Fn.linear(torch.randn(2, 4), torch.randn(3, 4))
+
+
+@pytest.mark.parametrize("c,h,w,n,pool,ceil,pre_relu,group", [
+    (64, 64, 1024, 2, (1, 2), True, True, 1),       # Simple-1 conv1 block: output width 513 (odd), 33 column segments
+    (128, 64, 513, 2, (1, 2), True, True, 1),       # conv2 block: odd input width, overhanging last window
+    (256, 64, 257, 1, (2, 2), True, True, 1),       # conv4 block: both strides, 33 x 129 output
+    (512, 33, 129, 1, (2, 2), True, True, 1),       # conv6 block: odd height
+    (64, 64, 2048, 1, (1, 2), False, False, 2),     # ResNet conv1 block: BN -> ReLU -> pool, pixel-pair planes, even pads
+    (64, 5, 7, 3, (1, 1), False, False, 1),         # tiny: fewer rows than ring slots, stride-1 pool
+    (192, 9, 11, 2, (2, 1), True, True, 1),         # 240-thread blocks (cg = 48), stride (2, 1)
+])
+def test_pooled_passes_bulk_copy_rings_equal_per_thread_loads(c, h, w, n, pool, ceil, pre_relu, group):
+    """The pooling passes staged through shared memory by cp.async.bulk row rings (forward: BN + ReLU + max-pool +
+    arg-max + y-at-arg-max + fp16 split; backward: un-pooling BN apply) against the per-thread-load kernels they
+    replace: every output bit-identical (same arithmetic, same tie-breaking), bias-gradient sums to round-off."""
+    from deeplio_b200 import engine as E
+    L = _lib()
+    g = torch.Generator().manual_seed(c + h + w)
+    cin = 32
+    x = torch.randn(n, cin, h, w, generator=g)
+    x[:, :, :, : w // 3] = x[:, :, :1, : w // 3]           # constant columns: ties inside pooling windows
+    wt = torch.randn(c, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    params = {"cv.weight": wt.to(DEV), "cv.bias": (torch.randn(c, generator=g) * 0.1).to(DEV),
+              "bn.weight": (torch.rand(c, generator=g) + 0.5).to(DEV), "bn.bias": (torch.randn(c, generator=g) * 0.1).to(DEV)}
+    xd = to_padded_nhwc(x, 1, 1)
+    results = []
+    for tma in (0, 1):
+        L.set_option(b"pool_tma", tma)
+        try:
+            bufs = {"bn.running_mean": torch.zeros(c, device=DEV), "bn.running_var": torch.ones(c, device=DEV)}
+            run = E.Run(dict(params), bufs, torch.device(DEV), True, True)
+            xa = E.Act(n, h, w, cin, 1, 1, t=xd.clone())
+            L.profile_enable(1)
+            out = E.conv_bn(run, xa, "cv", "bn", (1, 1), pre_relu=pre_relu, relu=not pre_relu, pool=pool, ceil=ceil,
+                            out_pad=(1, 2), out_group=group)
+            gd = torch.Generator().manual_seed(7)
+            run.agrad[id(out)] = to_padded_nhwc(torch.randn(n, c, out.h, out.w, generator=gd), 0, 0)
+            run.backward()
+            torch.cuda.synchronize()
+            L.profile_enable(0)
+            results.append(dict(t=out.t.clone() if out.t is not None else None, h2=out.h2.clone(), bound=out.bound.clone(),
+                                dx=run.agrad[id(xa)].clone(), dw=run.pgrad["cv.weight"].clone(), db=run.pgrad["cv.bias"].clone(),
+                                dg=run.pgrad["bn.weight"].clone(), dbeta=run.pgrad["bn.bias"].clone()))
+        finally:
+            L.set_option(b"pool_tma", 1)
+    a, b = results
+    assert torch.equal(a["h2"].view(torch.int16), b["h2"].view(torch.int16)) and torch.equal(a["bound"], b["bound"])
+    if a["t"] is not None:
+        assert torch.equal(a["t"], b["t"])
+    assert torch.equal(a["dg"], b["dg"]) and torch.equal(a["dbeta"], b["dbeta"])
+    for k in ("dx", "dw", "db"):                     # downstream of fp32 / fp64 atomics whose order differs
+        assert relerr(a[k], b[k]) < 2e-5, k
