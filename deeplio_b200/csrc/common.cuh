@@ -130,16 +130,22 @@ __device__ __forceinline__ __half *h2_addr(__half *base, size_t row, int C, int 
     return group == 2 ? base + (row >> 1) * (size_t)(4 * C) + (row & 1) * (size_t)C + c
                       : base + row * (size_t)(2 * C) + c;
 }
+// (packed conversions: cvt.rn.f16x2.f32 handles two channels per instruction; same round-to-nearest results as the
+// scalar f16_split)
 __device__ __forceinline__ void st4_h2(__half *base, size_t row, int C, int c, const float4 &v, float s, int group = 1) {
-    __align__(8) __half h[4];
-    __align__(8) __half l[4];
-    f16_split(v.x * s, h[0], l[0]);
-    f16_split(v.y * s, h[1], l[1]);
-    f16_split(v.z * s, h[2], l[2]);
-    f16_split(v.w * s, h[3], l[3]);
+    const float x0 = v.x * s, x1 = v.y * s, x2 = v.z * s, x3 = v.w * s;
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((x0 - b01.x) * 2048.f, (x1 - b01.y) * 2048.f);
+    const __half2 l23 = __floats2half2_rn((x2 - b23.x) * 2048.f, (x3 - b23.y) * 2048.f);
     __half *p = h2_addr(base, row, C, c, group);
-    *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(h);
-    *reinterpret_cast<uint2 *>(p + (group == 2 ? 2 * C : C)) = *reinterpret_cast<const uint2 *>(l);
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const unsigned *>(&h01);
+    hi.y = *reinterpret_cast<const unsigned *>(&h23);
+    lo.x = *reinterpret_cast<const unsigned *>(&l01);
+    lo.y = *reinterpret_cast<const unsigned *>(&l23);
+    *reinterpret_cast<uint2 *>(p) = hi;
+    *reinterpret_cast<uint2 *>(p + (group == 2 ? 2 * C : C)) = lo;
 }
 __device__ __forceinline__ void st4_h2_zero(__half *base, size_t row, int C, int c, int group = 1) {
     __half *p = h2_addr(base, row, C, c, group);

@@ -845,6 +845,10 @@ __device__ __forceinline__ void ring_bulk_load(uint32_t dst, const void *src, ui
 }
 
 constexpr int RING_SLOTS = 8;
+struct PoolRowMax {
+    float4 v, raw;      // best value over the row's window columns, and the conv output y it came from
+    unsigned dx;        // its window column (0 .. 2), one byte per channel
+};
 
 // Forward: BN-apply (+ReLU) + 3x3 max-pool (+ arg-max bytes, + y at the arg-max) + fp16 split / fp32 store.
 // blockDim = cg * WS (channel groups x output columns of a segment).  Shared memory: RING_SLOTS input-row segments
@@ -888,10 +892,34 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS,
         const int r_first = max(ho_a * SH - 1, 0), r_last = min((ho_b - 1) * SH + 1, H - 1);
         const float *src0 = a.yp + a.y.off(n, 0, wa);
         const size_t row_stride = (size_t)a.y.wp * a.y.c;
-        int r_issue = r_first;                                     // next input row to issue
+        int r_issue = r_first, r_waited = r_first - 1;             // next input row to issue / last row waited for
         const int wo = x0 + xo;
         const bool col_ok = wo < OW;
         const int w0 = wo * SW - 1, ci0 = xo * SW;                 // window column 0: input column / ring column
+        const bool okx0 = w0 >= 0, okx1 = w0 + 1 < W, okx2 = w0 + 2 < W;    // (w0 + 1 >= 0 always; ceil-mode windows may overhang)
+        PoolRowMax rm[3];
+        // horizontal maximum of input row h over the window's three columns: first maximum wins (strict >)
+        auto hrow = [&](int h) {
+            PoolRowMax r;
+            r.v = f4(-FLT_MAX);
+            r.raw = f4(0.f);
+            r.dx = 0u;
+            if (h < 0 || h >= H) return r;
+            const unsigned k = k_base + (unsigned)(h - r_first);
+            const float *row = ring + (size_t)(k % RING_SLOTS) * (slot_bytes / 4) + c + ci0 * C;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                if ((dx == 0 && !okx0) || (dx == 1 && !okx1) || (dx == 2 && !okx2)) continue;
+                const float4 raw = ld4(row + dx * C);
+                float4 v = fma4(sc, raw, sf);
+                if (RELU) v = relu4(v);
+                if (v.x > r.v.x) { r.v.x = v.x; r.raw.x = raw.x; r.dx = (r.dx & 0xFFFFFF00u) | (unsigned)dx; }
+                if (v.y > r.v.y) { r.v.y = v.y; r.raw.y = raw.y; r.dx = (r.dx & 0xFFFF00FFu) | ((unsigned)dx << 8); }
+                if (v.z > r.v.z) { r.v.z = v.z; r.raw.z = raw.z; r.dx = (r.dx & 0xFF00FFFFu) | ((unsigned)dx << 16); }
+                if (v.w > r.v.w) { r.v.w = v.w; r.raw.w = raw.w; r.dx = (r.dx & 0x00FFFFFFu) | ((unsigned)dx << 24); }
+            }
+            return r;
+        };
         for (int ho = ho_a; ho < ho_b; ++ho) {
             const int need_lo = max(ho * SH - 1, 0), need_hi = min(ho * SH + 1, H - 1);
             if (threadIdx.x == 0) {
@@ -904,33 +932,42 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS,
                     ++k_issue;
                 }
             }
-            for (int r = need_lo; r <= need_hi; ++r) {
+            for (int r = max(need_lo, r_waited + 1); r <= need_hi; ++r) {   // rows waited for earlier stay complete
                 const unsigned k = k_base + (unsigned)(r - r_first);
                 ring_wait(bar0 + 8 * (k % RING_SLOTS), (k / RING_SLOTS) & 1u);
             }
+            r_waited = max(r_waited, need_hi);
             const unsigned pix = ((unsigned)(n * a.out.hp + ho + a.out.ph)) * (unsigned)a.out.wp + (unsigned)(wo + a.out.pw);
             if (col_ok) {
-                float4 best = f4(-FLT_MAX), yb = f4(0.f);
-                unsigned bi = 0;
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int h = ho * SH - 1 + dy;
-                    if (h < 0 || h >= H) continue;
-                    const unsigned k = k_base + (unsigned)(h - r_first);
-                    const float *row = ring + (size_t)(k % RING_SLOTS) * (slot_bytes / 4) + c;
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int w = w0 + dx;
-                        if (w < 0 || w >= W) continue;
-                        const float4 raw = ld4(row + (ci0 + dx) * C);
-                        float4 v = fma4(sc, raw, sf);
-                        if (RELU) v = relu4(v);
-                        const unsigned r = (unsigned)(dy * 3 + dx);
-                        if (v.x > best.x) { best.x = v.x; yb.x = raw.x; bi = (bi & 0xFFFFFF00u) | r; }
-                        if (v.y > best.y) { best.y = v.y; yb.y = raw.y; bi = (bi & 0xFFFF00FFu) | (r << 8); }
-                        if (v.z > best.z) { best.z = v.z; yb.z = raw.z; bi = (bi & 0xFF00FFFFu) | (r << 16); }
-                        if (v.w > best.w) { best.w = v.w; yb.w = raw.w; bi = (bi & 0x00FFFFFFu) | (r << 24); }
+                // separable, rolling: the horizontal (value, raw y, dx) maximum of an input row is computed once and
+                // reused by every output row whose window contains it (3 with SH = 1, up to 2 with SH = 2); the kernel
+                // is bound by instruction issue, not by memory (ncu: 66 % issue slots busy at 35 % of DRAM bandwidth)
+                if (SH == 1) {
+                    if (ho == ho_a) {
+                        rm[0] = hrow(ho - 1);
+                        rm[1] = hrow(ho);
                     }
+                    rm[2] = hrow(ho + 1);
+                } else {
+                    if (ho == ho_a) rm[0] = hrow(2 * ho - 1);
+                    rm[1] = hrow(2 * ho);
+                    rm[2] = hrow(2 * ho + 1);
+                }
+                float4 best = rm[0].v, yb = rm[0].raw;
+                unsigned bi = rm[0].dx;
+#pragma unroll
+                for (int dy = 1; dy < 3; ++dy) {
+                    const unsigned code = rm[dy].dx + 0x01010101u * (unsigned)(3 * dy);
+                    if (rm[dy].v.x > best.x) { best.x = rm[dy].v.x; yb.x = rm[dy].raw.x; bi = (bi & 0xFFFFFF00u) | (code & 0x000000FFu); }
+                    if (rm[dy].v.y > best.y) { best.y = rm[dy].v.y; yb.y = rm[dy].raw.y; bi = (bi & 0xFFFF00FFu) | (code & 0x0000FF00u); }
+                    if (rm[dy].v.z > best.z) { best.z = rm[dy].v.z; yb.z = rm[dy].raw.z; bi = (bi & 0xFF00FFFFu) | (code & 0x00FF0000u); }
+                    if (rm[dy].v.w > best.w) { best.w = rm[dy].v.w; yb.w = rm[dy].raw.w; bi = (bi & 0x00FFFFFFu) | (code & 0xFF000000u); }
+                }
+                if (SH == 1) {
+                    rm[0] = rm[1];
+                    rm[1] = rm[2];
+                } else {
+                    rm[0] = rm[2];
                 }
                 const size_t po = ((size_t)(n * OH + ho) * OW + wo) * C + c;
                 if (a.idx) *reinterpret_cast<unsigned *>(a.idx + po) = bi;
@@ -1034,6 +1071,10 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, i
             if (a.dgamma) a.dgamma[cc + j] = (float)a.sums[C + cc + j];
         }
     }
+    // dy = sc * (dz - m1 - (y - mu) * is * m2) = sc * dz + cA + cB * y
+    const float4 cB = make_float4(-sc.x * is.x * m2.x, -sc.y * is.y * m2.y, -sc.z * is.z * m2.z, -sc.w * is.w * m2.w);
+    const float4 cA = make_float4(-sc.x * m1.x - cB.x * mu.x, -sc.y * m1.y - cB.y * mu.y, -sc.z * m1.z - cB.z * mu.z,
+                                  -sc.w * m1.w - cB.w * mu.w);
     float4 sb = f4(0.f);
     const int H = a.y.h, W = a.y.w, OH = a.pooled_h, OW = a.pooled_w;
     const long long total = (long long)a.y.n * nseg * H;
@@ -1060,7 +1101,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, i
         const size_t drow = (size_t)a.dout.wp * a.dout.c;
         const uint8_t *isrc = a.idx + ((size_t)n * OH * OW + o_lo) * C;
         const size_t irow = (size_t)OW * C;
-        int y_issue = h_a, p_issue = p_first;
+        int y_issue = h_a, p_issue = p_first, p_waited = p_first - 1;
         for (int h = h_a; h < h_b; ++h) {
             const int ho0 = SH == 1 ? h - 1 : h >> 1;
             const int p_lo = max(ho0, 0);
@@ -1087,54 +1128,33 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, i
                 const unsigned k = ky_base + (unsigned)(h - h_a);
                 ring_wait(bar0 + 8 * (k % APPLY_YSLOTS), (k / APPLY_YSLOTS) & 1u);
             }
-            for (int p = p_lo; p <= p_hi; ++p) {
+            for (int p = max(p_lo, p_waited + 1); p <= p_hi; ++p) {      // rows waited for by an earlier h stay complete
                 const unsigned k = kp_base + (unsigned)(p - p_first);
                 ring_wait(bar0 + 8 * (APPLY_YSLOTS + k % APPLY_PSLOTS), (k / APPLY_PSLOTS) & 1u);
             }
+            p_waited = max(p_waited, p_hi);
             const unsigned ks = ky_base + (unsigned)(h - h_a);
-            const float *yrow_s = yring + (size_t)(ks % APPLY_YSLOTS) * (yslot / 4) + c;
+            const float *yrow_s = yring + (ks % APPLY_YSLOTS) * (yslot / 4) + c;
+            // candidate pooled rows of this input row (block-uniform): ring rows and (window-relative row) * 3
+            const int nr = SH == 1 ? 3 : 1 + (h & 1);
             const float *dp[NR];
             const uint8_t *ip[NR];
-            unsigned rbase[NR];         // (window-relative row) * 3, or 255 when the window row does not exist
+            unsigned rbase[NR];
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 const int ho = ho0 + i;
-                const bool okh = ho >= 0 && ho < OH && (SH == 1 || i == 0 || (h & 1));
+                const bool okh = i < nr && ho >= 0 && ho < OH;
                 const int rh = SH == 1 ? 2 - i : h + 1 - 2 * ho;
                 const unsigned k = kp_base + (unsigned)((okh ? ho : p_lo) - p_first);
-                dp[i] = dring + (size_t)(k % APPLY_PSLOTS) * (dslot / 4) + c;
-                ip[i] = iring + (size_t)(k % APPLY_PSLOTS) * islot + c;
-                rbase[i] = okh ? (unsigned)(rh * 3) : 255u;
+                dp[i] = dring + (k % APPLY_PSLOTS) * (dslot / 4) + c;
+                ip[i] = iring + (k % APPLY_PSLOTS) * islot + c;
+                rbase[i] = okh ? (unsigned)(rh * 3) : 64u;      // 64 + rw never equals an arg-max byte (0 .. 8)
             }
             const unsigned pixrow = ((unsigned)(n * a.dy.hp + h + a.dy.ph)) * (unsigned)a.dy.wp + (unsigned)a.dy.pw;
-#pragma unroll
-            for (int uu = 0; uu < APPLY_U; ++uu) {
-                const int w = w_seg + xi + uu * WT;
-                if (w >= w_end) break;
-                const float4 y = ld4(yrow_s + (size_t)(w - w_seg) * C);
-                const int wo0 = SW == 1 ? w - 1 : w >> 1;
-                float4 g = f4(0.f);
-#pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    const int wo = wo0 + j;
-                    const bool okw = wo >= 0 && wo < OW && (SW == 1 || j == 0 || (w & 1));
-                    const int rw = SW == 1 ? 2 - j : w + 1 - 2 * wo;
-                    const int oc = (okw ? wo : o_lo) - o_lo;
-#pragma unroll
-                    for (int i = 0; i < NR; ++i) {
-                        const unsigned bi = *reinterpret_cast<const unsigned *>(ip[i] + (size_t)oc * C);
-                        const float4 d = ld4(dp[i] + (size_t)oc * C);
-                        const unsigned r = (okw && rbase[i] != 255u) ? rbase[i] + (unsigned)rw : 255u;
-                        const unsigned m = __vcmpeq4(bi, r * 0x01010101u);
-                        if (m & 0x000000FFu) g.x += d.x;
-                        if (m & 0x0000FF00u) g.y += d.y;
-                        if (m & 0x00FF0000u) g.z += d.z;
-                        if (m & 0xFF000000u) g.w += d.w;
-                    }
-                }
-                const float4 yh = make_float4((y.x - mu.x) * is.x, (y.y - mu.y) * is.y, (y.z - mu.z) * is.z, (y.w - mu.w) * is.w);
-                float4 d = make_float4(sc.x * (g.x - m1.x - yh.x * m2.x), sc.y * (g.y - m1.y - yh.y * m2.y),
-                                       sc.z * (g.z - m1.z - yh.z * m2.z), sc.w * (g.w - m1.w - yh.w * m2.w));
+            // dy = scale * (dz - mean(dz) - yhat * mean(dz * yhat)) = scale * dz + (cA + cB * y), constants per channel
+            auto finish = [&](int w, const float4 &y, const float4 &g) {
+                float4 d = make_float4(fmaf(sc.x, g.x, fmaf(cB.x, y.x, cA.x)), fmaf(sc.y, g.y, fmaf(cB.y, y.y, cA.y)),
+                                       fmaf(sc.z, g.z, fmaf(cB.z, y.z, cA.z)), fmaf(sc.w, g.w, fmaf(cB.w, y.w, cA.w)));
                 if (a.pre_relu) {
                     if (!(y.x > 0.f)) d.x = 0.f;
                     if (!(y.y > 0.f)) d.y = 0.f;
@@ -1145,6 +1165,75 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, i
                 if (a.dy_hi) st4_split(a.dy_hi, a.dy_lo, (size_t)pix * C + c, d);
                 if (a.dy_h2) st4_h2(a.dy_h2, pix, C, c, d, s16);
                 sb = add4(sb, d);
+            };
+            if (SW == 2) {
+                // a thread owns the pixel pair (2 wo, 2 wo + 1): both can be the arg-max of window column wo (window
+                // columns 1 and 2), the odd one also of window column wo + 1 (window column 0) -- the candidate loads
+                // of column wo are shared, and the arg-max bytes are unpacked once per load
+                const int oc = xi;                                  // ring column of pooled column wo = o_lo + xi
+                const int w_e = w_seg + 2 * xi;
+                if (w_e < w_end) {
+                    const bool odd_ok = w_e + 1 < w_end;
+                    const bool okA = o_lo + oc < OW, okB = o_lo + oc + 1 < OW;
+                    float4 ge = f4(0.f), go = f4(0.f);
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        if (i >= nr) break;
+                        {
+                            const unsigned bi = okA ? *reinterpret_cast<const unsigned *>(ip[i] + oc * C) : 0xFFFFFFFFu;
+                            const float4 d = ld4(dp[i] + oc * C);
+                            const unsigned r1 = rbase[i] + 1u, r2 = rbase[i] + 2u;
+                            const unsigned b0 = bi & 0xFFu, b1 = (bi >> 8) & 0xFFu, b2 = (bi >> 16) & 0xFFu, b3 = bi >> 24;
+                            if (b0 == r1) ge.x += d.x;
+                            if (b1 == r1) ge.y += d.y;
+                            if (b2 == r1) ge.z += d.z;
+                            if (b3 == r1) ge.w += d.w;
+                            if (b0 == r2) go.x += d.x;
+                            if (b1 == r2) go.y += d.y;
+                            if (b2 == r2) go.z += d.z;
+                            if (b3 == r2) go.w += d.w;
+                        }
+                        {
+                            const unsigned bi = okB ? *reinterpret_cast<const unsigned *>(ip[i] + (oc + 1) * C) : 0xFFFFFFFFu;
+                            const float4 d = ld4(dp[i] + (oc + 1) * C);
+                            const unsigned r0 = rbase[i];
+                            if ((bi & 0xFFu) == r0) go.x += d.x;
+                            if (((bi >> 8) & 0xFFu) == r0) go.y += d.y;
+                            if (((bi >> 16) & 0xFFu) == r0) go.z += d.z;
+                            if ((bi >> 24) == r0) go.w += d.w;
+                        }
+                    }
+                    const float *yp2 = yrow_s + (w_e - w_seg) * C;
+                    finish(w_e, ld4(yp2), ge);
+                    if (odd_ok) finish(w_e + 1, ld4(yp2 + C), go);
+                }
+            } else {
+#pragma unroll
+                for (int uu = 0; uu < APPLY_U; ++uu) {
+                    const int w = w_seg + xi + uu * WT;
+                    if (w >= w_end) break;
+                    const int wo0 = w - 1;
+                    float4 g = f4(0.f);
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        const int wo = wo0 + j;
+                        const bool okw = wo >= 0 && wo < OW;
+                        const unsigned rw = (unsigned)(2 - j);
+                        const int oc = (okw ? wo : o_lo) - o_lo;
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            if (i >= nr) break;
+                            const unsigned bi = okw ? *reinterpret_cast<const unsigned *>(ip[i] + oc * C) : 0xFFFFFFFFu;
+                            const float4 d = ld4(dp[i] + oc * C);
+                            const unsigned r = rbase[i] + rw;
+                            if ((bi & 0xFFu) == r) g.x += d.x;
+                            if (((bi >> 8) & 0xFFu) == r) g.y += d.y;
+                            if (((bi >> 16) & 0xFFu) == r) g.z += d.z;
+                            if ((bi >> 24) == r) g.w += d.w;
+                        }
+                    }
+                    finish(w, ld4(yrow_s + (w - w_seg) * C), g);
+                }
             }
             // zero pads of the dy grid around this row segment
             if (a.dy.pw > 0 && (seg == 0 || seg == nseg - 1)) {

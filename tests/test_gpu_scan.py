@@ -51,7 +51,8 @@ def test_scan_projection_full_size_against_oracle():
     # 99.9 % of the well-defined normals within 1e-4, all within 1e-2
     err = np.abs(got[3:6] - ref_org[3:6]).max(axis=0)[well]
     assert (err < 1e-4).mean() > 0.999 and err.max() < 1e-2, ((err < 1e-4).mean(), err.max())
-    assert np.abs(normed.cpu().numpy() - ref_norm)[:, same].max() < 1e-2
+    assert np.abs(normed.cpu().numpy() - ref_norm)[:, well].max() < 1e-2
+    assert np.abs(normed.cpu().numpy()[0:3] - ref_norm[0:3])[:, same].max() == 0.0
     # an empty cloud gives the empty image (zeros minus the mean)
     org0, norm0 = scan.project_scan(torch.zeros(0, 4, device=DEV), 16, 64, channels=channels, mean_image=MEAN)
     assert float(org0.abs().max()) == 0.0
