@@ -25,6 +25,7 @@
 // registers (round-to-nearest adds) every 8 K stages and keeps the small lo*hi + hi*lo corrections in a separate
 // accumulator (see the kernel); wgrad spreads the hi*hi products round-robin over three accumulators.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv.cuh"
@@ -464,6 +465,329 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     }
 }
 
+// ==================================================================== CTA-pair variant (cta_group::2)
+// The single-CTA kernel above is bound by shared-memory bandwidth, not by the tensor pipe: per 32-byte K step the
+// three MMAs read 20 KB of operands (A_lo, B_hi | A_hi, B_lo | B_hi; A_hi reused through the collector) and TMA
+// writes 16 KB, 36 KB per 192 tensor-pipe clocks = 187 B/clk against the SM's 128 B/clk -- the measured 67 - 75 %
+// tensor-pipe activity IS that ratio.  Here two CTAs on the two SMs of a TPC run ONE tcgen05.mma.cta_group::2 with
+// M = 256 (128 rows of A per CTA) and N = bn: each CTA stages only HALF of the B tile (bn / 2 weight rows) and the
+// tensor cores of both SMs read both halves, so per CTA and K step the MMAs read 14 KB and TMA writes 12 KB:
+// 135 B/clk.  Structure, accumulator scheme and epilogue are those of conv_tc_kernel; what changes is the barrier
+// protocol across the pair:
+//   * rank 0 (leader) issues every MMA; both CTAs run a TMA producer for their own A rows and B half, and both
+//     signal the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address mapped to rank 0),
+//     on which the leader posts the byte count of both CTAs;
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster arrives on the empty / mfull / cfull barriers of BOTH CTAs;
+//   * the epilogue warps of both CTAs drain their own TMEM (rows r * 128 ..) and arrive on the leader's mempty /
+//     cempty barriers (count 16), remotely for rank 1.
+__device__ __forceinline__ uint32_t cluster_ctarank_() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+#define DLIO_UMMA2_ASM(COLL)                                                                                   \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                            \
+                 "tcgen05.mma.cta_group::2.kind::f16" COLL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),      \
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)                                                  \
+                 : "memory")
+template <int COLL>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (COLL == 0) DLIO_UMMA2_ASM("");
+    else if (COLL == 1) DLIO_UMMA2_ASM(".collector::a::fill");
+    else DLIO_UMMA2_ASM(".collector::a::lastuse");
+}
+// arrives (when the MMAs issued so far retire) on the barrier at this shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_FWD_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * 8 + 8];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank_();
+    const bool leader = rank == 0;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int bk = TC_BK16;                               // halves per 128-byte K chunk
+    const int bnh = a.bn / 2;                                 // weight rows staged by this CTA
+    const uint32_t a_bytes = TC_BM * 128;                     // 16 KB per plane
+    const uint32_t b_bytes = (uint32_t)bnh * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int S = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+    const uint32_t mfull0 = smem_u32(&bars[16]), mempty0 = smem_u32(&bars[18]);
+    const uint32_t cfull0 = smem_u32(&bars[20]), cempty0 = smem_u32(&bars[22]);
+    const int cchunks = a.cin / bk;
+    const int iters = a.kh * a.kw * cchunks;
+    const int SEG = a.seg;
+    const long long tiles = a.mtiles * a.ntiles;              // mtiles counts 256-row tiles here
+    const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(mfull0 + 8 * i, 1);
+            mbar_init(mempty0 + 8 * i, 2 * TC_EPI_WARPS);
+            mbar_init(cfull0 + 8 * i, 1);
+            mbar_init(cempty0 + 8 * i, 2 * TC_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();            // the peer's barriers are initialised before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer of this CTA's A rows and B half; completion on the leader's full barrier =====
+        uint32_t s = 0, ph = 0;
+        for (long long tile = pair; tile < tiles; tile += npairs) {
+            const long long q0 = (tile / a.ntiles) * (2 * TC_BM) + (long long)rank * TC_BM;
+            const int n0 = (int)(tile % a.ntiles) * a.bn + (int)rank * bnh;
+            int dy = 0, dx = 0, cc = 0, wcol = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                if (elect_one()) {
+                    const int row = (int)(q0 + (long long)(dy - a.ph) * a.x.wp + (dx - a.pw));
+                    const uint32_t sa = smem_u32(smem) + s * stage_bytes;
+                    const uint32_t fb = map_to_rank(full0 + 8 * s, 0);
+                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * stage_bytes);
+                    tma_load_2d_pair(sa, &tm_xhi, fb, cc * bk, row);
+                    tma_load_2d_pair(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
+                    tma_load_2d_pair(sa + 2 * a_bytes, &tm_whi, fb, wcol, n0);
+                    tma_load_2d_pair(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, wcol, n0);
+                }
+                __syncwarp();
+                wcol += bk;
+                if (++cc == cchunks) {
+                    cc = 0;
+                    if (++dx == a.kw) { dx = 0; ++dy; }
+                }
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer of the pair =====
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+            const uint32_t sa0 = smem_u32(smem);
+            const uint64_t dA_hi = make_kmajor_desc(sa0), dA_lo = make_kmajor_desc(sa0 + a_bytes);
+            const uint64_t dB_hi = make_kmajor_desc(sa0 + 2 * a_bytes), dB_lo = make_kmajor_desc(sa0 + 2 * a_bytes + b_bytes);
+            const uint32_t stage16 = stage_bytes >> 4;
+            uint32_t s = 0, ph = 0, seg = 0, tcount = 0;
+            for (long long tile = pair; tile < tiles; tile += npairs, ++tcount) {
+                const uint32_t p = tcount & 1u;
+                mbar_wait(cempty0 + 8 * p, ((tcount >> 1) & 1u) ^ 1u);
+                const uint32_t t_corr = tmem_base + (2 + p) * a.bn;
+                uint32_t t_main = 0;
+                int si = 0;
+                for (int it = 0; it < iters; ++it) {
+                    if (si == 0) {
+                        mbar_wait(mempty0 + 8 * (seg & 1u), ((seg >> 1) & 1u) ^ 1u);
+                        t_main = tmem_base + (seg & 1u) * a.bn;
+                    }
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const bool seg_end = si == SEG - 1 || it == iters - 1;
+                    if (elect_one()) {
+                        const uint64_t so = (uint64_t)(s * stage16);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = so + (uint64_t)(k * 2);
+                            umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                            umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                            umma2<2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
+                        }
+                        umma2_commit_both(empty0 + 8 * s);
+                        if (seg_end) umma2_commit_both(mfull0 + 8 * (seg & 1u));
+                        if (it == iters - 1) umma2_commit_both(cfull0 + 8 * p);
+                    }
+                    __syncwarp();
+                    if (seg_end) { ++seg; si = 0; } else ++si;
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: as in conv_tc_kernel, on this CTA's 128 rows of the 256-row tile =====
+        const int quad = warp & 3, ew = warp - 2, half = ew >> 2;
+        const int cw = a.bn >= 64 ? a.bn / 2 : a.bn;
+        const bool active = half == 0 || a.bn >= 64;
+        const int cb = half * cw;
+        double *red = reinterpret_cast<double *>(smem + (size_t)S * stage_bytes) + (size_t)ew * 2 * 64;
+        for (int i = lane; i < 2 * 64; i += 32) red[i] = 0.0;
+        const float inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.wb));
+        const float corr = 1.f / 2048.f;
+        const int nseg = (iters + SEG - 1) / SEG;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const uint32_t mempty_l = map_to_rank(mempty0, 0), cempty_l = map_to_rank(cempty0, 0);
+        uint32_t seg = 0, tcount = 0;
+        int red_n0 = -1;
+        auto flush_stats = [&](int n0) {
+            __syncwarp();
+            for (int c = lane; c < cw; c += 32) {
+                atomicAdd(a.stats + n0 + cb + c, red[c]);
+                atomicAdd(a.stats + a.cout + n0 + cb + c, red[64 + c]);
+                red[c] = 0.0;
+                red[64 + c] = 0.0;
+            }
+            __syncwarp();
+        };
+        for (long long tile = pair; tile < tiles; tile += npairs, ++tcount) {
+            const long long q = (tile / a.ntiles) * (2 * TC_BM) + (long long)rank * TC_BM + quad * 32 + lane;
+            const int n0 = (int)(tile % a.ntiles) * a.bn;
+            bool valid = q < a.rows;
+            size_t obase = 0;
+            if (valid) {
+                int xx = (int)(q % a.x.wp);
+                long long t = q / a.x.wp;
+                int yy = (int)(t % a.x.hp);
+                int n = (int)(t / a.x.hp);
+                int h = yy - a.x.ph, w = xx - a.x.pw;
+                valid = h >= 0 && h < a.x.h && w >= 0 && w < a.x.w;
+                if (a.hdec == 2) {
+                    valid = valid && !(h & 1);
+                    h >>= 1;
+                }
+                if (valid) obase = a.o.off(n, h, w) + n0 + cb;
+            }
+            if (a.stats && active && red_n0 != n0) {
+                if (red_n0 >= 0) flush_stats(red_n0);
+                red_n0 = n0;
+            }
+            float acc[2][32];
+            for (int sg = 0; sg < nseg; ++sg, ++seg) {
+                const uint32_t b = seg & 1u;
+                mbar_wait(mfull0 + 8 * b, (seg >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (active) {
+                    const uint32_t t_main = tmem_base + lane_off + b * a.bn + cb;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c * 32 < cw) {
+                            uint32_t v[32];
+                            tmem_ld32_nowait(t_main + c * 32, v);
+                            tmem_ld_wait();
+                            if (sg == 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) acc[c][j] = __uint_as_float(v[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) acc[c][j] += __uint_as_float(v[j]);
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mempty_l + 8 * b);
+            }
+            const uint32_t p = tcount & 1u;
+            mbar_wait(cfull0 + 8 * p, (tcount >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float rinv = valid ? inv : 0.f;
+            if (active) {
+                const uint32_t t_corr = tmem_base + lane_off + (2 + p) * a.bn + cb;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c * 32 < cw) {
+                        uint32_t u[32];
+                        tmem_ld32_nowait(t_corr + c * 32, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c][j] = fmaf(__uint_as_float(u[j]), corr, acc[c][j]) * rinv;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cempty_l + 8 * p);
+            if (!active) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int c0 = c * 32;
+                if (c0 < cw) {
+                    const int ncol = min(32, cw - c0);
+                    if (a.bias) {
+                        const float bmask = valid ? 1.f : 0.f;
+                        const float *bp = a.bias + n0 + cb + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j < ncol) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + j));
+                                acc[c][j] = fmaf(b4.x, bmask, acc[c][j]);
+                                acc[c][j + 1] = fmaf(b4.y, bmask, acc[c][j + 1]);
+                                acc[c][j + 2] = fmaf(b4.z, bmask, acc[c][j + 2]);
+                                acc[c][j + 3] = fmaf(b4.w, bmask, acc[c][j + 3]);
+                            }
+                        }
+                    }
+                    if (a.act == DLIO_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c][j] = fmaxf(acc[c][j], 0.f);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < ncol)
+                                st4(a.out + obase + c0 + j, make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]));
+                    }
+                    if (a.stats) {
+                        float sq[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sq[j] = acc[c][j] * acc[c][j];
+                        const float s1 = warp_colsum32(acc[c], lane), s2 = warp_colsum32(sq, lane);
+                        if (lane < ncol) {
+                            red[c0 + lane] += (double)s1;
+                            red[64 + c0 + lane] += (double)s2;
+                        }
+                    }
+                }
+            }
+        }
+        if (a.stats && active && red_n0 >= 0) flush_stats(red_n0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();            // neither CTA leaves (or frees TMEM) while the other may still signal / read it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -520,6 +844,15 @@ static int make_map_pair(CUtensorMap *hi, CUtensorMap *lo, const float *p_hi, co
     return make_map(lo, p_lo, false, rows, cols, cols, box_rows, swizzle);
 }
 
+// CTA-pair convolution kernel (conv_tc2_kernel): off unless DLIO_CONV_CG2=1 / dlio_set_option("conv_cg2", 1)
+int g_conv_cg2 = -1;
+static bool conv_cg2_enabled() {
+    if (g_conv_cg2 < 0) {
+        const char *e = getenv("DLIO_CONV_CG2");
+        g_conv_cg2 = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_conv_cg2 != 0;
+}
 static int pick_bn(int cout) {
     for (int bn : {128, 64, 32, 16})   // four accumulators of bn columns must fit the 512 TMEM columns
         if (cout % bn == 0) return bn;
@@ -578,6 +911,28 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     }
     ProfScope prof(prof_kind, st);
     if (a.o.ph > 0 || a.o.pw > 0) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
+    if (f16 && bn == 128 && conv_cg2_enabled()) {
+        // CTA pairs (conv_tc2_kernel): 256-row tiles, each CTA stages half of the weight tile
+        CUtensorMap mwh2, mwl2;
+        if ((rc = make_map_pair(&mwh2, &mwl2, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn / 2))) return rc;
+        const int stage2 = 2 * TC_BM * 128 + 2 * (bn / 2) * 128;
+        int stages2 = (TC_SMEM_LIMIT - TC_EPI_SMEM) / stage2;
+        if (stages2 > 6) stages2 = 6;
+        t.stages = stages2;
+        t.mtiles = (rows + 2 * TC_BM - 1) / (2 * TC_BM);
+        static bool attr2 = false;
+        if (!attr2) {
+            DLIO_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+            attr2 = true;
+        }
+        const long long tiles2 = t.mtiles * t.ntiles;
+        long long pairs = tiles2 < n_sm / 2 ? tiles2 : n_sm / 2;
+        if (pairs > t.ntiles) pairs -= pairs % t.ntiles;
+        const size_t smem2 = (size_t)stages2 * stage2 + TC_EPI_SMEM + 1024;
+        conv_tc2_kernel<<<(unsigned)(2 * pairs), TC_FWD_THREADS, smem2, st>>>(mxh, mxl, mwh2, mwl2, t);
+        DLIO_LAUNCH_CHECK();
+        return 1;
+    }
     const long long tiles = t.mtiles * t.ntiles;
     // one persistent CTA per SM; keep the grid a multiple of ntiles so that a CTA stays on one N tile (its BN
     // statistics then accumulate in shared memory over all its tiles)

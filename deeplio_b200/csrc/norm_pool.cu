@@ -33,6 +33,7 @@ static int ew_block_cap() {
     return cap;
 }
 // DLIO_POOL_TMA=0 falls back to the per-thread-load pooling kernels (A/B switch for bench and tests)
+extern int g_conv_cg2;      // conv_tc.cu
 static int g_pool_tma = -1;
 static bool pool_tma_enabled() {
     if (g_pool_tma < 0) {
@@ -844,7 +845,6 @@ __device__ __forceinline__ void ring_bulk_load(uint32_t dst, const void *src, ui
                  : "memory");
 }
 
-constexpr int RING_SLOTS = 8;
 struct PoolRowMax {
     float4 v, raw;      // best value over the row's window columns, and the conv output y it came from
     unsigned dx;        // its window column (0 .. 2), one byte per channel
@@ -855,6 +855,8 @@ struct PoolRowMax {
 // of ((WS - 1) * SW + 3) columns x C floats.  Same arithmetic and tie-breaking as bn_pool3_fwd_kernel.
 template <int SH, int SW, bool RELU>
 __global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS, int nseg, long long units_per_cta) {
+    // an output row keeps 3 input rows alive and consumes SH new ones: 3 + 3 rows of look-ahead (SH = 1), 3 + 5 (SH = 2)
+    constexpr int RING_SLOTS = SH == 1 ? 6 : 8;
     extern __shared__ __align__(128) unsigned char ring_raw[];
     __shared__ __align__(8) unsigned long long bars[RING_SLOTS];
     const int cg = a.cg, C = cg * 4;
@@ -1010,7 +1012,7 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS,
 // blockDim = cg * WT; a thread owns a channel group and U input columns WT apart.  dout.c == C, c_off == 0.
 constexpr int APPLY_YSLOTS = 4, APPLY_PSLOTS = 6, APPLY_U = 2;
 template <int SH, int SW>
-__global__ void __launch_bounds__(256) bn_pool_bwd_apply_tma_kernel(BnApply a, int WT, int nseg, long long units_per_cta) {
+__global__ void __launch_bounds__(256, 3) bn_pool_bwd_apply_tma_kernel(BnApply a, int WT, int nseg, long long units_per_cta) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
     __shared__ __align__(8) unsigned long long bars[APPLY_YSLOTS + APPLY_PSLOTS];
     __shared__ float red[MAX_C];
@@ -1431,6 +1433,7 @@ extern "C" int dlio_set_option(const char *name, int value) {
     DLIO_CHECK_ARG(name, "set_option: null name");
     if (!strcmp(name, "pool_tma")) dlio::g_pool_tma = value ? 1 : 0;
     else if (!strcmp(name, "ew_block")) dlio::g_ew_cap = value < 64 ? 64 : (value > 256 ? 256 : value);
+    else if (!strcmp(name, "conv_cg2")) dlio::g_conv_cg2 = value ? 1 : 0;
     else {
         set_error("set_option: unknown option %s", name);
         return DLIO_ERR_INVALID;
@@ -1505,7 +1508,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
         const int WS = a.cg >= 256 ? 1 : 256 / a.cg;
         const int nseg = (a.out.w + WS - 1) / WS;
         const int wcols = (WS - 1) * a.sw + 3;
-        const size_t smem = (size_t)RING_SLOTS * wcols * y.c * sizeof(float);
+        const size_t smem = (size_t)(a.sh == 1 ? 6 : 8) * wcols * y.c * sizeof(float);
         const long long total = (long long)a.out.n * nseg * a.out.h;
 #define DLIO_POOL3_TMA(SH_, SW_)                                                                              \
     do {                                                                                                      \

@@ -79,8 +79,8 @@ extern "C" int dlio_scan_project(const float *points4, int n_points, int H, int 
                                  const float *mean8, void *scratch, float *out_org, float *out_normed, int *out_idx,
                                  void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(points4 && n_points >= 0 && H > 0 && W > 0 && scratch && (out_org || out_normed || out_idx) &&
-                       (((uintptr_t)points4) & 15) == 0 && (((uintptr_t)scratch) & 7) == 0,
+    DLIO_CHECK_ARG((points4 || n_points == 0) && n_points >= 0 && H > 0 && W > 0 && scratch &&
+                       (out_org || out_normed || out_idx) && (((uintptr_t)points4) & 15) == 0 && (((uintptr_t)scratch) & 7) == 0,
                    "scan_project: bad argument");
     DLIO_CHECK_ARG(n_channels >= 0 && n_channels <= 8 && (n_channels == 0 || channels), "scan_project: 0 .. 8 channels");
     DLIO_CHECK_ARG(max_depth > 0.f && min_depth >= 0.f, "scan_project: bad depth range");

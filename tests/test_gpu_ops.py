@@ -799,5 +799,7 @@ def test_pooled_passes_bulk_copy_rings_equal_per_thread_loads(c, h, w, n, pool, 
     assert torch.equal(a["h2"].view(torch.int16), b["h2"].view(torch.int16)) and torch.equal(a["bound"], b["bound"])
     if a["t"] is not None:
         assert torch.equal(a["t"], b["t"])
-    for k in ("dg", "dbeta", "dx", "dw", "db"):      # downstream of fp32 / fp64 atomics whose order differs
+    for k in ("dg", "dbeta", "dx", "dw"):            # downstream of fp32 / fp64 atomics whose order differs
         assert relerr(a[k], b[k]) < 2e-5, k
+    # the bias of a convolution in front of a train-mode BatchNorm has zero gradient in exact arithmetic: noise only
+    assert (a["db"] - b["db"]).abs().max().item() < 1e-5 * a["dw"].abs().max().item()
