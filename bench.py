@@ -209,7 +209,17 @@ def run_b200(args):
     # trainer.py:56-58: two parameter groups, the model's and the criterion's
     opt = FlatAdam([{"params": model.parameters()}, {"params": criterion.parameters()}], lr=LR, weight_decay=WD)
     n_params = sum(p.numel() for p in model.parameters()) + sum(p.numel() for p in criterion.parameters())
-    reducer = parallel.OverlappedGradReducer(model, opt) if world > 1 else None
+    # N > 1: the backward pass is cut at the encoders' feature vector; the gradients of everything downstream (78 % of
+    # the bytes: odometry LSTM, fusion, heads, IMU net, fc1, sx / sq) are all-reduced while the encoders' backward runs
+    lidar_net = getattr(model, "lidar_feat_net", None)
+    split = world > 1 and lidar_net is not None and os.environ.get("DLIO_SPLIT_BWD", "1") != "0"
+    reducer = None
+    if world > 1:
+        late = [criterion] + ([model.imu_feat_net, lidar_net.fc1] if split else [])
+        reducer = parallel.OverlappedGradReducer(model, opt, extra_late=[m for m in late if m is not None])
+        if split:
+            lidar_net.split_backward = True
+            model.on_head_grads_ready = None       # fired explicitly after loss.backward()
 
     host = {k: v.pin_memory() for k, v in synthetic_host_batch(B, S, T, seed=100 + rank).items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
@@ -229,6 +239,9 @@ def run_b200(args):
         opt.zero_grad()
         loss = fwd_loss(d)
         loss.backward()
+        if split:
+            reducer.fire()
+            lidar_net.backward_encoders()
         scale = reducer.finish() if reducer is not None else 1.0
         opt.step(scale)
         return loss.detach()      # no reference to the autograd graph survives the step (deeplio_b200.graph)
@@ -236,8 +249,9 @@ def run_b200(args):
     gstep = [None]
 
     def graph_step(d):
-        loss = gstep[0](d)                       # forward + loss + backward: graph launches
-        opt.step(parallel.allreduce_grads(opt.flat_grad))
+        # forward + loss + backward: graph launches (two per step when the backward pass is split)
+        loss = gstep[0](d, between=reducer.fire if split else None)
+        opt.step(reducer.finish() if reducer is not None else 1.0)
         return loss
 
     def train_step(d):
@@ -290,17 +304,18 @@ def run_b200(args):
         try:
             from deeplio_b200.graph import GraphedTrainStep
             if reducer is not None:
-                model.on_head_grads_ready = None
-                reducer = None
+                model.on_head_grads_ready = None       # under the graph nothing fires from a hook
             E.ENC_STREAMS = enc_streams
-            gstep[0] = GraphedTrainStep(fwd_loss, resident, opt.zero_grad, model=model)
+            gstep[0] = GraphedTrainStep(fwd_loss, resident, opt.zero_grad, model=model,
+                                        second_backward=lidar_net.backward_encoders if split else None)
             state["resident"] = gstep[0].input_slots[0]     # the graph's own input buffers: resident steps copy nothing
             for _ in range(args.warmup):
                 train_step(state["resident"])
             n0 = _lib.launch_count()
             ms_total = timed(resident_steps, args.steps)
             launches = _lib.launch_count() - n0 + gstep[0].captured_launches * args.steps
-            launch_mode = "cuda-graph (forward + loss + backward: %d library kernels per replay; all-reduce and Adam eager)" % gstep[0].captured_launches
+            launch_mode = "cuda-graph (forward + loss + backward: %d library kernels per replay%s; all-reduce and Adam eager)" % (
+                gstep[0].captured_launches, ", split at the encoder features with the downstream all-reduce under the encoders' backward" if split else "")
         except Exception as e:      # capture is an optimisation: report the eager numbers and say why
             gstep[0] = None
             launch_mode = "eager (CUDA graph capture failed: %s)" % str(e).splitlines()[0][:160]

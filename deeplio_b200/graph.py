@@ -35,7 +35,7 @@ class GraphedTrainStep:
     then happens on the current stream.  When the current stream is the default stream, a side stream is used and no
     eager step may have run before."""
 
-    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None, slots=2):
+    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None, slots=2, second_backward=None):
         """``model`` (optional): its buffers (BatchNorm running statistics and ``num_batches_tracked``) and the dropout
         call counter are snapshotted before the warm-up passes and restored before the capture, so that building the
         graph leaves the training state exactly as an eager run would find it.
@@ -43,7 +43,13 @@ class GraphedTrainStep:
         ``slots``: number of static input sets, one captured graph each (``input_slots``).  An input pipeline that
         writes batch i + 1 into one set while the step on batch i reads the other (pipeline.DevicePrefetcher with
         ``buffers=step.input_slots``) then feeds the graphs without a device-to-device copy of the inputs.  The
-        graphs share one memory pool (they are replayed one at a time, on one stream), so the activations exist once."""
+        graphs share one memory pool (they are replayed one at a time, on one stream), so the activations exist once.
+
+        ``second_backward`` (optional callable): the step is captured as TWO graphs per slot -- (A) zero_grad, forward,
+        loss, ``loss.backward()`` and (B) ``second_backward()`` -- for a model whose autograd graph is cut in two
+        (``LidarFeatNet.split_backward``: (B) is the encoders' backward).  ``step(inputs, between=f)`` calls ``f()``
+        between the two replays: a data-parallel step launches the all-reduce of the gradients (A) completed there,
+        so that it runs under (B)."""
         dev = next(iter(example.values())).device
         self.input_slots = [{k: torch.empty_like(v) for k, v in example.items()} for _ in range(max(1, slots))]
         for slot in self.input_slots:
@@ -51,7 +57,7 @@ class GraphedTrainStep:
                 slot[k].copy_(v)
         self.static_in = self.input_slots[0]
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.graphs, self.static_losses = [], []
+        self.graphs, self.graphs_b, self.static_losses = [], [], []
         self._next = 0
         gc.collect()       # drop autograd graphs of earlier eager steps that are only kept alive by reference cycles
         prev = Fn._seed_epoch[0]
@@ -66,6 +72,8 @@ class GraphedTrainStep:
                 for _ in range(warmup):
                     zero_grad()
                     fwd_loss(self.static_in).backward()
+                    if second_backward is not None:
+                        second_backward()
                 with torch.no_grad():
                     for b, v in saved:
                         b.copy_(v)
@@ -83,8 +91,13 @@ class GraphedTrainStep:
                     zero_grad()
                     loss = fwd_loss(slot)
                     loss.backward()
-                self.captured_launches = L.launch_count() - n0     # library kernels every replay launches
                 pool = graph.pool()
+                if second_backward is not None:
+                    graph_b = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph_b, stream=side, pool=pool):
+                        second_backward()
+                    self.graphs_b.append(graph_b)
+                self.captured_launches = L.launch_count() - n0     # library kernels every replay launches
                 self.graphs.append(graph)
                 self.static_losses.append(loss)
             self.graph, self.static_loss = self.graphs[0], self.static_losses[0]
@@ -92,9 +105,9 @@ class GraphedTrainStep:
         finally:
             Fn._seed_epoch[0] = prev
 
-    def __call__(self, inputs):
+    def __call__(self, inputs, between=None):
         """``inputs``: one of ``input_slots`` (replayed in place) or any dict of tensors with the captured shapes
-        (copied into the next slot first)."""
+        (copied into the next slot first).  ``between``: called between the two graphs of a split step."""
         k = next((i for i, s in enumerate(self.input_slots) if inputs is s), None)
         if k is None:
             k = self._next
@@ -103,4 +116,8 @@ class GraphedTrainStep:
                 if v.data_ptr() != self.input_slots[k][name].data_ptr():
                     self.input_slots[k][name].copy_(v, non_blocking=True)
         self.graphs[k].replay()
+        if self.graphs_b:
+            if between is not None:
+                between()
+            self.graphs_b[k].replay()
         return self.static_losses[k].detach()

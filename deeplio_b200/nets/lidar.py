@@ -339,6 +339,8 @@ class BaseLidarFeatNet(BaseNet):
         self.timestamps = self.cfg_container.timestamps
         self.combinations = self.cfg_container.combinations
         self.input_shape = input_shape
+        self.split_backward = False
+        self._cut = None
 
     def _finish(self, width):
         self.fc1 = nn.Linear(width * (2 if self.fusion == "cat" else 1), 128)
@@ -360,8 +362,24 @@ class BaseLidarFeatNet(BaseNet):
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         views = [v if isinstance(v, PairedFrames) else as5(v) for v in (imgs_xyz, imgs_normals)]
         y = _EncoderPair.apply(self, record, views[0], views[1], *params)
+        if self.split_backward and y.requires_grad:
+            # cut the autograd graph at the encoders' feature vector: ``loss.backward()`` then stops here with the
+            # gradients of everything downstream complete, and ``backward_encoders()`` runs the encoders' backward as
+            # a second step -- the seam where a data-parallel step starts reducing the downstream gradients
+            # (deeplio_b200.graph.GraphedTrainStep, deeplio_b200.parallel.OverlappedGradReducer)
+            cut = y.detach().requires_grad_(True)
+            self._cut = (y, cut)
+            y = cut
         y = self._tail(y)
         return y.view(b, s, -1)
+
+    def backward_encoders(self):
+        """Second half of a split backward pass (``split_backward = True``): the encoders' backward from the gradient
+        that ``loss.backward()`` left at the cut."""
+        y, cut = self._cut
+        self._cut = None
+        if cut.grad is not None:
+            y.backward(cut.grad)
 
     def _tail(self, y):
         if self.tail == "drop_then_leaky":      # Simple-1 (lidar_feat_nets.py:230-233)

@@ -59,13 +59,18 @@ class OverlappedGradReducer:
     all-reduced asynchronously on NCCL's stream while the encoder backward runs, and ``finish()`` reduces the rest
     (feature-net gradients) after ``backward()`` and joins.  Same sums as one all-reduce of the whole arena."""
 
-    def __init__(self, model, opt):
+    def __init__(self, model, opt, extra_late=()):
+        """``extra_late``: further modules / parameters whose gradients are complete at the same moment (the loss
+        module's sx / sq; with a split backward pass -- ``lidar_feat_net.split_backward`` -- also the IMU net and the
+        LiDAR net's fc1, i.e. everything but the two encoders)."""
         self.flat_grad = opt.flat_grad
         late = set()
-        for name in ("fusion_net", "odom_feat_net", "fc_pos", "fc_ori"):
-            m = getattr(model, name, None)
+        mods = [getattr(model, name, None) for name in ("fusion_net", "odom_feat_net", "fc_pos", "fc_ori")] + list(extra_late)
+        for m in mods:
             if isinstance(m, torch.nn.Module):
                 late.update(id(p) for p in m.parameters())
+            elif isinstance(m, torch.nn.Parameter):
+                late.add(id(m))
         self.late_ranges, self.early_ranges = [], []
         ends = opt.offsets[1:] + [opt.numel]
         for p, a, b in zip(opt.params, opt.offsets, ends):
@@ -76,6 +81,10 @@ class OverlappedGradReducer:
                 rs.append([a, b])
         self.work, self.fired = [], False
         model.on_head_grads_ready = self._fire
+
+    def fire(self):
+        """The downstream gradients are complete: start reducing them (asynchronously, on NCCL's stream)."""
+        self._fire()
 
     def _fire(self):
         if world_size() > 1 and not self.fired:

@@ -87,7 +87,7 @@ typedef enum {
 /* Tuning switches (A/B measurements and tests; the defaults are what ships): "pool_tma" 0/1 -- pooling passes staged
  * through shared memory by bulk copies (default 1; environment DLIO_POOL_TMA), "ew_block" 64..256 -- block-size cap of
  * the element-wise passes (default 256; environment DLIO_EW_BLOCK), "conv_cg2" 0/1 -- stride-1 fp16 convolutions with 128-
- * channel output tiles on CTA pairs (tcgen05 cta_group::2; environment DLIO_CONV_CG2). */
+ * channel output tiles on CTA pairs (tcgen05 cta_group::2; default 1; environment DLIO_CONV_CG2). */
 int dlio_set_option(const char *name, int value);
 int dlio_profile_enable(int on);
 int dlio_profile_read(int kind, double *total_ms, long long *launches);

@@ -1,6 +1,5 @@
 """CTA-pair convolution kernel (tcgen05 cta_group::2, csrc/conv_tc.cu conv_tc2_kernel) against the single-CTA kernel
-and against F.conv2d in fp64.  Kept in its own file: the kernel is opt-in (dlio_set_option("conv_cg2", 1)) and its
-barrier protocol spans two CTAs, so scripts run this file under its own timeout."""
+and against F.conv2d in fp64 (dlio_set_option("conv_cg2", 0 / 1) switches between them; the pair kernel is the default)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -50,7 +49,7 @@ def test_conv_cta_pair_equals_single_cta(case):
                              b.to(DEV).data_ptr() if bias else None, cv, act, yt4, y.data_ptr(), stats.data_ptr(), _st())
             torch.cuda.synchronize()
         finally:
-            L.set_option(b"conv_cg2", 0)
+            L.set_option(b"conv_cg2", 1)
         outs.append((y, stats))
     (y0, s0), (y1, s1) = outs
     assert relerr(from_nhwc(y1).double(), ref) < 1e-5
