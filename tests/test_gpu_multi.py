@@ -86,3 +86,76 @@ def test_nccl_world2_overlapped_exchange_matches_plain_allreduce_and_oracle_mean
         # two backward passes of the same step differ by fp64-atomics order only (1e-6-level), the exchange adds nothing
         assert d_plain < 2e-5, d_plain
         assert d_oracle < 1e-3, d_oracle       # largest entry of the arena; per-tensor bars: tests/test_gpu_model.py
+
+
+def _worker_split(rank, world, port, out):
+    """The bench's N > 1 step: backward cut at the encoder features, two CUDA graphs per step, the downstream
+    gradients all-reduced between them (under the encoders' backward), the encoders' afterwards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from deeplio_b200 import data, losses, nets, parallel, pose
+    from deeplio_b200.config import build_config_container
+    from deeplio_b200.graph import GraphedTrainStep
+    from deeplio_b200.optim import FlatAdam
+    from deeplio_b200.workloads import synthetic_gts
+    from oracle import deeplio_oracle as O
+    from oracle.configs import make_cfg
+    parallel.init_from_env()
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(rank)
+    with torch.cuda.stream(torch.cuda.Stream(dev)):
+        B, S, H, W, T = 2, 2, 16, 128, 6
+        cfg = make_cfg(lidar="lidar-feat-simple-1", imu="imu-feat-rnn", odom="odom-feat-rnn", seq=S, height=H, width=W,
+                       odom_hidden=64)
+        combos = cfg["datasets"]["combinations"]
+        build_config_container(cfg, argparse.Namespace(device=str(dev), batch_size=B))
+        model = nets.get_model((3, H, W), cfg, str(dev))
+        model.load_state_dict(O.synthetic_state(cfg, seed=3))
+        model.train()
+        crit = losses.get_loss_function(cfg, str(dev))
+        opt = FlatAdam([{"params": model.parameters()}, {"params": crit.parameters()}], lr=1e-3)
+        lidar = model.lidar_feat_net
+        lidar.split_backward = True
+        red = parallel.OverlappedGradReducer(model, opt, extra_late=[crit, model.imu_feat_net, lidar.fc1])
+        model.on_head_grads_ready = None
+        g = torch.Generator().manual_seed(50 + rank)
+        d = {"frames": torch.randn(B, S + 1, 6, H, W, generator=g).to(dev), "imus": torch.randn(B, S, T, 6, generator=g).to(dev),
+             "gts": synthetic_gts(B, S + 1, seed=rank).to(dev)}
+
+        def fwd_loss(t):
+            f2f, f2g = data.ground_truth(t["gts"], combos)
+            pos, ori = model([[data.PairedFrames(t["frames"], combos, 0, 3), data.PairedFrames(t["frames"], combos, 3, 3)],
+                              t["imus"]])
+            p, q = pose.se3_to_SE3(pos, ori, check=False)
+            return crit(pos, ori, p[:, 1:3], q[:, 1:3], f2f[:, :, 0:3], f2f[:, :, 3:], f2g[:, 1:3, 0:3], f2g[:, 1:3, 3:7])
+        step = GraphedTrainStep(fwd_loss, d, opt.zero_grad, model=model, second_backward=lidar.backward_encoders)
+        loss_g = step(step.input_slots[0], between=red.fire)
+        fired = red.fired
+        scale = red.finish()
+        torch.cuda.synchronize()
+        reduced = opt.flat_grad.clone()
+        n_late = sum(b - a for a, b in red.late_ranges)
+        # the same step eagerly, unsplit, one all-reduce of the whole arena
+        lidar.split_backward = False
+        opt.zero_grad()
+        loss_e = fwd_loss(d)
+        loss_e.backward()
+        plain = opt.flat_grad.clone()
+        dist.all_reduce(plain)
+        torch.cuda.synchronize()
+        gmax = plain.abs().max().item()
+        out[rank] = (fired, scale, n_late / opt.numel, abs(float(loss_g) - float(loss_e)) / abs(float(loss_e)),
+                     (reduced - plain).abs().max().item() / gmax, pose.raise_for_status(dev))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_nccl_world2_split_backward_graphs_overlap_the_exchange():
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_worker_split, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        fired, scale, late_frac, d_loss, d_grad, status = out[rank]
+        assert fired and scale == 0.5 and status == 0
+        assert late_frac > 0.5            # the odometry LSTM, fusion, heads, IMU net, fc1, sx / sq
+        assert d_loss < 1e-6 and d_grad < 2e-5, (d_loss, d_grad)
