@@ -1171,6 +1171,154 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
     }
 }
 
+// CTA-pair variant of wgrad_tc_kernel (fp16 operands, Cin % 128 == 0, Cout % 256 == 0, no operand swap): one
+// tcgen05.mma.cta_group::2 computes a 256 x 128 tile of dw for one tap -- each CTA stages its own 128 dy channels (A)
+// and only HALF of the x tile (64 of the 128 input channels, B), halving the B traffic through shared memory.  Barrier
+// protocol as in conv_tc2_kernel: both producers complete on the leader's full barrier, the leader's commits arrive on
+// the empty / tfull barriers of both CTAs; there is one tile per pair, so no accumulator hand-back.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_constant__ CUtensorMap tm_dylo,
+                 const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * 8 + 1];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank_();
+    const bool leader = rank == 0;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int krows = 64, bc = 64;                      // pixel rows (K) per stage, channels per TMA box
+    constexpr uint32_t box_bytes = (uint32_t)krows * 128;
+    const uint32_t a_bytes = 2 * box_bytes;                 // dy: 64 rows x 128 channels (two boxes)
+    const uint32_t b_bytes = box_bytes;                     // x:  64 rows x 64 channels (this CTA's half of the 128)
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int S = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
+
+    const int nblk = a.cin / 128;
+    const int pairx = blockIdx.x >> 1;                      // (tap, 128-channel block of Cin)
+    const int tap = pairx / nblk;
+    const int ci0 = (pairx - tap * nblk) * 128;
+    const int co0 = blockIdx.z * 256 + (int)rank * 128;
+    const int dy_ = tap / a.kw, dx_ = tap - dy_ * a.kw;
+    const long long shift = (long long)(dy_ - a.ph) * a.wp + (dx_ - a.pw);
+    const long long k_begin = (long long)blockIdx.y * a.rows_per_split;
+    long long k_end = k_begin + a.rows_per_split;
+    if (k_end > a.rows) k_end = a.rows;
+    const int iters = k_end > k_begin ? (int)((k_end - k_begin + krows - 1) / krows) : 0;
+    const int nmain = iters < 3 ? iters : 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (iters > 0) {            // uniform for the pair
+        if (warp == 0) {
+            uint32_t s = 0, ph = 0;
+            int q = (int)k_begin;
+            const int qs = (int)shift;
+            for (int it = 0; it < iters; ++it, q += krows) {
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem) + s * stage_bytes;
+                    const uint32_t fb = map_to_rank(full0 + 8 * s, 0);
+                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * stage_bytes);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        tma_load_2d_pair(sa + j * box_bytes, &tm_dyhi, fb, co0 + bc * j, q);
+                        tma_load_2d_pair(sa + a_bytes + j * box_bytes, &tm_dylo, fb, co0 + bc * j, q);
+                    }
+                    tma_load_2d_pair(sa + 2 * a_bytes, &tm_xhi, fb, ci0 + (int)rank * bc, q + qs);
+                    tma_load_2d_pair(sa + 2 * a_bytes + b_bytes, &tm_xlo, fb, ci0 + (int)rank * bc, q + qs);
+                }
+                __syncwarp();
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+        } else if (warp == 1) {
+            if (leader) {
+                // fp32 accumulate, f16 operands, both MN-major, M = 256, N = 128
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24) | (1u << 15) | (1u << 16);
+                constexpr uint64_t kstep = (uint64_t)(2048 >> 4);
+                const uint32_t sa0 = smem_u32(smem);
+                const uint64_t dA_hi = make_mnmajor_desc(sa0, true), dA_lo = make_mnmajor_desc(sa0 + a_bytes, true);
+                const uint64_t dB_hi = make_mnmajor_desc(sa0 + 2 * a_bytes, true), dB_lo = make_mnmajor_desc(sa0 + 2 * a_bytes + b_bytes, true);
+                const uint32_t stage16 = stage_bytes >> 4;
+                const uint32_t t_corr = tmem_base + 3 * 128;
+                uint32_t s = 0, ph = 0, m = 0;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t so = (uint64_t)(s * stage16);
+                        const uint32_t t_main = tmem_base + m * 128;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = so + (uint64_t)k * kstep;
+                            umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                            umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                            umma2<2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
+                        }
+                        umma2_commit_both(empty0 + 8 * s);
+                        if (it == iters - 1) umma2_commit_both(tfull);
+                    }
+                    __syncwarp();
+                    if (++m == 3) m = 0;
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+                }
+            }
+        } else {
+            const int quad = warp & 3;
+            const int co = co0 + quad * 32 + lane;
+            const int taps = a.kh * a.kw;
+            float *orow = a.dw + ((size_t)co * taps + tap) * a.cin + ci0;
+            const float inv = (1.f / f16_scale_from_bound(*a.xb)) * (1.f / f16_scale_from_bound(*a.yb));
+            const float corr = 1.f / 2048.f;
+            mbar_wait(tfull, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32], u[32];
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+                tmem_ld32(trow, v);
+                for (int m = 1; m < nmain; ++m) {
+                    tmem_ld32(trow + m * 128, u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                }
+                tmem_ld32(trow + 3 * 128, u);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    atomicAdd(reinterpret_cast<float4 *>(orow + c0 + j),
+                              make_float4(fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv,
+                                          fmaf(__uint_as_float(u[j + 1]), corr, __uint_as_float(v[j + 1])) * inv,
+                                          fmaf(__uint_as_float(u[j + 2]), corr, __uint_as_float(v[j + 2])) * inv,
+                                          fmaf(__uint_as_float(u[j + 3]), corr, __uint_as_float(v[j + 3])) * inv));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     // a.x: padded input (x_hi / x_lo); a.y: dy geometry (w_hi / w_lo carry dy); a.out = dw [cout][kh][kw][cin]
     // f16 mode: x_h2 / w_h2 are the packed planes of x / dy, x_bound / w_bound their bounds
@@ -1240,6 +1388,38 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     }
     ProfScope prof(DLIO_PROF_CONV_WGRAD_TC, st);
     DLIO_CUDA(cudaMemsetAsync(a.out, 0, (size_t)a.cout * taps * a.cin * sizeof(float), st));
+    static const bool wgrad_pairs = [] { const char *e = getenv("DLIO_WGRAD_CG2"); return !(e && e[0] == '0'); }();
+    if (f16 && !swap && bn == 128 && a.cout % 256 == 0 && wgrad_pairs && conv_cg2_enabled()) {
+        // CTA pairs (wgrad_tc2_kernel): 256 x 128 tiles; K splits sized for whole waves of 74 pairs
+        const int tiles2 = taps * (a.cin / 128) * (a.cout / 256);
+        int splits2 = 1;
+        double best2 = 0.0;
+        for (int waves = 2; waves <= 4; ++waves) {
+            int s2 = waves * 74 / tiles2;
+            if (s2 > max_splits) s2 = (int)max_splits;
+            if (s2 < 1) s2 = 1;
+            const long long ctas = (long long)s2 * tiles2;
+            const double fill = (double)ctas / (double)(((ctas + 73) / 74) * 74);
+            if (fill > best2 + 1e-9) { best2 = fill; splits2 = s2; }
+        }
+        long long rps2 = (rows + splits2 - 1) / splits2;
+        rps2 = (rps2 + krows - 1) / krows * krows;
+        if ((rows + rps2 - 1) / rps2 < splits2) splits2 = (int)((rows + rps2 - 1) / rps2);
+        t.rows_per_split = rps2;
+        const int stage2 = 2 * (2 * 64 * 128) + 2 * (64 * 128);       // dy hi|lo (128 ch) + x hi|lo (64 ch)
+        int stages2 = TC_SMEM_LIMIT / stage2;
+        if (stages2 > 6) stages2 = 6;
+        t.stages = stages2;
+        static bool attr2 = false;
+        if (!attr2) {
+            DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
+            attr2 = true;
+        }
+        dim3 grid2((unsigned)(2 * taps * (a.cin / 128)), (unsigned)splits2, (unsigned)(a.cout / 256));
+        wgrad_tc2_kernel<<<grid2, TC_THREADS, (size_t)stages2 * stage2 + 1024, st>>>(mdh, mdl, mxh, mxl, t);
+        DLIO_LAUNCH_CHECK();
+        return 1;
+    }
     dim3 grid((unsigned)(swap ? (taps + tpg - 1) / tpg : taps * (a.cin / bn)), (unsigned)splits, (unsigned)mblocks);
     if (f16 && swap) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mdh, mdl, t);   // x as A, dy as B
     else if (f16) wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mdh, mdl, mxh, mxl, t);

@@ -56,3 +56,46 @@ def test_conv_cta_pair_equals_single_cta(case):
     assert torch.equal(y0, y1)                              # same K order, same accumulator segments per output
     assert torch.allclose(s0, s1, rtol=1e-12, atol=1e-9)    # fp64 atomics: order only
     assert torch.allclose(s1.cpu()[:cout], ref.sum((0, 2, 3)), rtol=5e-5, atol=1e-4)
+
+
+WGRAD_CASES = [
+    # n, cin, cout, h, w, (kh, kw): Cin % 128 == 0 and Cout % 256 == 0 take the pair kernel
+    (2, 128, 256, 6, 11, (3, 3)),                  # fewer K chunks than pipeline stages
+    (1, 128, 256, 64, 257, (3, 3)),                # Simple-1 conv4 (one image)
+    (3, 512, 512, 17, 65, (3, 3)),                 # conv7
+    (1, 256, 512, 33, 129, (3, 3)),                # conv6
+    (2, 256, 256, 9, 20, (1, 1)),                  # one tap
+    (1, 128, 256, 1, 3, (3, 3)),                   # a handful of pixels: most K splits are empty
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_cta_pair_equals_single_cta(case):
+    """wgrad_tc2_kernel (256 x 128 tiles of dw per CTA pair) against wgrad_tc_kernel and torch fp64.  The K split
+    differs between the two (74 pairs against 148 CTAs per wave), so the fp32 atomics combine other partial sums:
+    equal to accumulation round-off, not bitwise."""
+    L = _lib()
+    n, cin, cout, h, w, (kh, kw) = case
+    g = torch.Generator().manual_seed(cin + 5 * cout + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    dy = torch.randn(n, cout, h, w, generator=g)
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    wr = torch.zeros(cout, cin, kh, kw, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wr, None, 1, (ph, pw)).backward(dy.double())
+    x_h2, x_b, _ = pack_f16(L, x, ph, pw)
+    dy_h2, dy_b, _ = pack_f16(L, dy, ph, pw)
+    xt4, dyt4 = L.Tensor4(n, h, w, cin, ph, pw), L.Tensor4(n, h, w, cout, ph, pw)
+    cv = L.Conv(kh, kw, 1, 1, ph, pw)
+    outs = []
+    for pair in (0, 1):
+        L.set_option(b"conv_cg2", pair)
+        try:
+            dw = torch.full((cout, kh, kw, cin), float("nan"), device=DEV)
+            L.conv2d_bwd_weight_f16(xt4, x_h2.data_ptr(), x_b.data_ptr(), dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), cv,
+                                    dw.data_ptr(), _st())
+            torch.cuda.synchronize()
+        finally:
+            L.set_option(b"conv_cg2", 1)
+        outs.append(dw.permute(0, 3, 1, 2).cpu().double())
+    assert relerr(outs[1], wr.grad) < 1e-5
+    assert relerr(outs[1], outs[0]) < 2e-6
