@@ -47,6 +47,7 @@ _PROTOS = {
     "dlio_device_check": (I, [I]),
     "dlio_launch_count": (LL, []),
     "dlio_set_option": (I, [C.c_char_p, I]),
+    "dlio_workspace_bytes": (SZ, [C.c_char_p, C.POINTER(C.c_longlong), I]),
     "dlio_profile_enable": (I, [I]),
     "dlio_profile_read": (I, [I, P, P]),
     "dlio_pack_input": (I, [P, LL, LL, LL, I, I, Tensor4, P, P, P]),
@@ -138,6 +139,15 @@ scan_scratch_bytes = _lib.dlio_scan_scratch_bytes
 rnn_reserve_floats = _lib.dlio_rnn_reserve_floats
 rnn_bwd_scratch_floats = _lib.dlio_rnn_bwd_scratch_floats
 abi_version = _lib.dlio_abi_version
+
+
+def workspace_bytes(op, *dims):
+    """dlio_workspace_bytes: caller-owned scratch of one call of `op` (see the header for the dims of each op)."""
+    arr = (C.c_longlong * max(1, len(dims)))(*dims)
+    n = _lib.dlio_workspace_bytes(op.encode(), arr, len(dims))
+    if n == C.c_size_t(-1).value:
+        raise DlioError("dlio_workspace_bytes failed: %s" % last_error())
+    return n
 
 
 PROF_KINDS = ("conv_fwd_simt", "conv_dgrad_simt", "conv_wgrad_simt", "conv_fwd_tc", "conv_dgrad_tc", "conv_wgrad_tc",

@@ -5,9 +5,24 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace dlio {
+
+int g_nvtx = -1;   // NVTX ranges (kernel class names) around every profiled launch group; DLIO_NVTX=1 / "nvtx" option
+static bool nvtx_on() {
+    if (g_nvtx < 0) {
+        const char *e = getenv("DLIO_NVTX");
+        g_nvtx = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_nvtx != 0;
+}
+static const char *const kProfNames[] = {"dlio/conv_fwd_simt", "dlio/conv_dgrad_simt", "dlio/conv_wgrad_simt",
+                                         "dlio/conv_fwd_tc",   "dlio/conv_dgrad_tc",   "dlio/conv_wgrad_tc",
+                                         "dlio/elementwise",   "dlio/dense",           "dlio/rnn",
+                                         "dlio/optim"};
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -30,6 +45,7 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 
 int prof_begin(int kind, cudaStream_t st) {
+    if (nvtx_on()) nvtxRangePushA(kind >= 0 && kind < 10 ? kProfNames[kind] : "dlio");
     if (!g_prof_on.load(std::memory_order_relaxed)) return -1;
     ProfRec r;
     r.kind = kind;
@@ -40,6 +56,7 @@ int prof_begin(int kind, cudaStream_t st) {
     return (int)g_prof.size() - 1;
 }
 void prof_end(int idx, cudaStream_t st) {
+    if (g_nvtx > 0) nvtxRangePop();
     if (idx < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].b, st);

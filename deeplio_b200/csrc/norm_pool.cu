@@ -34,6 +34,7 @@ static int ew_block_cap() {
 }
 // DLIO_POOL_TMA=0 falls back to the per-thread-load pooling kernels (A/B switch for bench and tests)
 extern int g_conv_cg2;      // conv_tc.cu
+extern int g_nvtx;          // lib.cu
 static int g_pool_tma = -1;
 static bool pool_tma_enabled() {
     if (g_pool_tma < 0) {
@@ -1434,11 +1435,37 @@ extern "C" int dlio_set_option(const char *name, int value) {
     if (!strcmp(name, "pool_tma")) dlio::g_pool_tma = value ? 1 : 0;
     else if (!strcmp(name, "ew_block")) dlio::g_ew_cap = value < 64 ? 64 : (value > 256 ? 256 : value);
     else if (!strcmp(name, "conv_cg2")) dlio::g_conv_cg2 = value ? 1 : 0;
+    else if (!strcmp(name, "nvtx")) dlio::g_nvtx = value ? 1 : 0;
     else {
         set_error("set_option: unknown option %s", name);
         return DLIO_ERR_INVALID;
     }
     return DLIO_OK;
+}
+
+extern "C" size_t dlio_workspace_bytes(const char *op, const long long *dims, int ndims) {
+    const size_t bad = (size_t)-1;
+    if (!op || (ndims > 0 && !dims)) {
+        set_error("workspace_bytes: null argument");
+        return bad;
+    }
+    auto need = [&](int n) {
+        if (ndims == n) return true;
+        set_error("workspace_bytes: %s takes %d dims, got %d", op, n, ndims);
+        return false;
+    };
+    if (!strcmp(op, "conv2d_fwd")) return need(1) ? (size_t)(2 * dims[0]) * sizeof(double) : bad;
+    if (!strcmp(op, "bn_bwd")) return need(1) ? (size_t)(2 * dims[0] + 1) * sizeof(double) : bad;
+    if (!strcmp(op, "rnn_fwd") || !strcmp(op, "rnn_bwd")) {
+        if (!need(7)) return bad;
+        const int d[7] = {(int)dims[0], (int)dims[1], (int)dims[2], (int)dims[3], (int)dims[4], (int)dims[5], (int)dims[6]};
+        const size_t f = op[4] == 'f' ? dlio_rnn_reserve_floats(d[0], d[1], d[2], d[3], d[4], d[5], d[6])
+                                      : dlio_rnn_bwd_scratch_floats(d[0], d[1], d[2], d[3], d[4], d[5], d[6]);
+        return f * sizeof(float);
+    }
+    if (!strcmp(op, "scan_project")) return need(2) ? dlio_scan_scratch_bytes((int)dims[0], (int)dims[1]) : bad;
+    set_error("workspace_bytes: unknown op %s", op);
+    return bad;
 }
 
 extern "C" int dlio_pack_input(const float *src, long long sn, long long st, long long sc, int T, int C,

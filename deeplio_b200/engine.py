@@ -48,6 +48,9 @@ FLOPS = None
 # test aid: when a dict, every conv_bn forward stores the ReLU mask of its layer (bool, NCHW) under
 # Run.trace_prefix + conv name, so that tests can count mask disagreements with the oracle (oracle.TRACE)
 MASK_TRACE = None
+# profiling aid (DLIO_NVTX=1, the same switch as the library's dlio/<kernel class> ranges): an NVTX range per layer,
+# "<encoder>.<conv name>" around its forward launches and "<...>/bwd" around its backward ones
+NVTX = os.environ.get("DLIO_NVTX", "0") == "1"
 
 
 def _trace_mask(run, cname, y, bnv, pre_relu, relu, res, res_mode, c_off):
@@ -240,7 +243,31 @@ def pack_input(run, view, c_pad, ph, pw):
     return x
 
 
-def conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
+def conv_bn(run, x, cname, *args, **kwargs):
+    if not NVTX:
+        return _conv_bn(run, x, cname, *args, **kwargs)
+    label = getattr(run, "trace_prefix", "") + cname
+    n_tape = len(run.tape)
+    torch.cuda.nvtx.range_push(label)
+    try:
+        return _conv_bn(run, x, cname, *args, **kwargs)
+    finally:
+        torch.cuda.nvtx.range_pop()
+        for i in range(n_tape, len(run.tape)):
+            run.tape[i] = _nvtx_wrapped(run.tape[i], label + "/bwd")
+
+
+def _nvtx_wrapped(fn, label):
+    def call():
+        torch.cuda.nvtx.range_push(label)
+        try:
+            fn()
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return call
+
+
+def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, pool=None, ceil=False, res=None,
             res_mode=0, out=None, c_off=0, out_c=None, out_pad=(0, 0), feat=None, feat_ld=0, feat_off=0,
             out_f32=True, out_group=1, out_c_pad=None):
     """conv(+bias)(+ReLU if pre_relu) -> BatchNorm (batch statistics when run.training) -> (+res)(ReLU)(+res)

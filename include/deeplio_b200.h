@@ -87,8 +87,19 @@ typedef enum {
 /* Tuning switches (A/B measurements and tests; the defaults are what ships): "pool_tma" 0/1 -- pooling passes staged
  * through shared memory by bulk copies (default 1; environment DLIO_POOL_TMA), "ew_block" 64..256 -- block-size cap of
  * the element-wise passes (default 256; environment DLIO_EW_BLOCK), "conv_cg2" 0/1 -- stride-1 fp16 convolutions with 128-
- * channel output tiles on CTA pairs (tcgen05 cta_group::2; default 1; environment DLIO_CONV_CG2). */
+ * channel output tiles on CTA pairs (tcgen05 cta_group::2; default 1; environment DLIO_CONV_CG2), "nvtx" 0/1 -- an NVTX
+ * range named dlio/<kernel class> around the launches of every entry point (default 0; environment DLIO_NVTX; the
+ * Python engine adds a range per layer, e.g. encoder1.conv3, when it is on). */
 int dlio_set_option(const char *name, int value);
+/* Caller-owned scratch of one call, in bytes -- the library never allocates device memory.  One
+ * query for every entry point that takes scratch:
+ *   "conv2d_fwd"   {Cout}                  the fp64 `stats` buffer (sum | sum of squares per channel; zeroed by the caller)
+ *   "bn_bwd"       {C}                     the fp64 `sums` buffer of dlio_bn_act_pool_bwd_reduce / dlio_pool_bwd_sums
+ *   "rnn_fwd"      {kind,L,D,B,T,I,H}      `reserve` of dlio_rnn_fwd (= 4 * dlio_rnn_reserve_floats)
+ *   "rnn_bwd"      {kind,L,D,B,T,I,H}      `scratch` of dlio_rnn_bwd
+ *   "scan_project" {H,W}                   `scratch` of dlio_scan_project
+ * Returns (size_t)-1 and sets dlio_last_error for an unknown op or a wrong number of dims. */
+size_t dlio_workspace_bytes(const char *op, const long long *dims, int ndims);
 int dlio_profile_enable(int on);
 int dlio_profile_read(int kind, double *total_ms, long long *launches);
 

@@ -38,6 +38,20 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.abi_version() == lib.ABI_VERSION == int(re.search(r"#define DLIO_ABI_VERSION (\d+)", header).group(1))
 
 
+def test_workspace_bytes_is_the_scratch_the_entry_points_take(lib):
+    """Host-only query (no device call): the sizes the engine allocates for each op's scratch."""
+    assert lib.workspace_bytes("conv2d_fwd", 128) == 2 * 128 * 8
+    assert lib.workspace_bytes("bn_bwd", 64) == (2 * 64 + 1) * 8
+    dims = (0, 2, 2, 8, 15, 6, 128)           # kind, layers, directions, B, T, I, H
+    assert lib.workspace_bytes("rnn_fwd", *dims) == 4 * lib.rnn_reserve_floats(*dims) > 0
+    assert lib.workspace_bytes("rnn_bwd", *dims) == 4 * lib.rnn_bwd_scratch_floats(*dims) > 0
+    assert lib.workspace_bytes("scan_project", 64, 2048) == lib.scan_scratch_bytes(64, 2048) > 0
+    with pytest.raises(lib.DlioError, match="unknown op"):
+        lib.workspace_bytes("fire", 1)
+    with pytest.raises(lib.DlioError, match="takes 2 dims"):
+        lib.workspace_bytes("scan_project", 64)
+
+
 def test_library_is_sm100a_with_no_other_arch(lib):
     out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
