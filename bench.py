@@ -196,6 +196,10 @@ def run_b200(args):
     # the whole train loop runs on ONE dedicated stream: the CUDA-graph capture below needs every autograd node that
     # outlives a step to belong to the capturing stream, never to the legacy default stream (deeplio_b200/graph.py)
     torch.cuda.set_stream(torch.cuda.Stream(dev))
+    # measurement-only switch (never the default): dgrad / wgrad with the hi*hi product alone
+    single_bwd = os.environ.get("DLIO_BWD_SINGLE", "0") == "1"
+    if single_bwd:
+        _lib.set_option(b"bwd_single_pass", 1)
     workload = args.workload or WORKLOAD
     cfg, B, S, T = workload_config(workload, H, W)
     B = args.batch or (B if workload == WORKLOAD else max(1, B // 8))      # per-GPU batch (weak scaling)
@@ -408,6 +412,8 @@ def run_b200(args):
         cfgd = workload_dict(workload, B, S, T, world, n_params)
         cfgd.update({"parallelism": "dp%d" % world, "launch": launch_mode, "eager_ms_per_step": ms_eager / args.steps,
                      "encoder_streams": 2 if E.ENC_STREAMS else 1,
+                     **({"ab": "bwd_single_pass: dgrad / wgrad at plain fp16 operand accuracy -- NOT the parity-tested "
+                               "path, not a bench value"} if single_bwd else {}),
                      "l2": "working set per step (%.1f GB peak, activations) exceeds the 126 MB L2; no explicit flush" % peak_gb})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -58,6 +58,8 @@ struct TcArgs {
     int f16;           // 0: 3xTF32 on fp32 planes; 1: 3xF16 on packed half planes (K chunk = 64 halves)
     int hdec;          // 2: H-stride-2 convolution computed over the whole grid, only even rows are stored / counted
     const float *xb, *wb;   // f16: device bounds of the two operands (-> power-of-two scales)
+    int single;        // A/B switch "bwd_single_pass": hi*hi products only (the correction accumulator is initialised
+                       // by one lo*hi MMA per tile and otherwise left alone) -- fp16 / TF32 accuracy at 1/3 of the MMAs
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -299,8 +301,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                // 128-byte rows / 32 bytes per MMA K step
                         const uint64_t ko = so + (uint64_t)(k * 2);
-                        umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                        umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                        if (!a.single || !(it | k)) umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                        if (!a.single) umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
                         umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
                     }
                     umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
@@ -627,8 +629,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ko = so + (uint64_t)(k * 2);
-                            umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                            umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                            if (!a.single || !(it | k)) umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                            if (!a.single) umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
                             umma2<2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
                         }
                         umma2_commit_both(empty0 + 8 * s);
@@ -847,6 +849,7 @@ static int make_map_pair(CUtensorMap *hi, CUtensorMap *lo, const float *p_hi, co
 // CTA-pair convolution kernel (conv_tc2_kernel): on unless DLIO_CONV_CG2=0 / dlio_set_option("conv_cg2", 0)
 // (measured on the headline step: forward class 4.26 -> 3.94 ms, dgrad 3.61 -> 3.13 ms, outputs bit-identical)
 int g_conv_cg2 = -1;
+int g_bwd_single = 0;   // option "bwd_single_pass" (A/B measurement only; never the default)
 static bool conv_cg2_enabled() {
     if (g_conv_cg2 < 0) {
         const char *e = getenv("DLIO_CONV_CG2");
@@ -879,6 +882,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     TcArgs t;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.wb = a.w_bound;
     t.hdec = a.hdec;
+    t.single = (prof_kind == DLIO_PROF_CONV_DGRAD_TC && g_bwd_single) ? 1 : 0;
     t.x = a.x; t.o = a.o;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw;
     t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.act = a.act;
@@ -965,6 +969,7 @@ struct TcWgradArgs {
     float *dw;
     int f16;
     const float *xb, *yb;   // f16: device bounds of x and dy
+    int single;             // see TcArgs::single
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, bool f16) {
@@ -1105,8 +1110,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t ko = so + (uint64_t)k * kstep;
-                    umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                    umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                    if (!a.single || !(it | k)) umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                    if (!a.single) umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
                     umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
@@ -1270,8 +1275,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_const
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ko = so + (uint64_t)k * kstep;
-                            umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                            umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                            if (!a.single || !(it | k)) umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                            if (!a.single) umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
                             umma2<2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                         }
                         umma2_commit_both(empty0 + 8 * s);
@@ -1369,6 +1374,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     t.cin = a.cin; t.cout = a.cout; t.bn = bn; t.swap = swap ? 1 : 0;
     t.rows = rows; t.rows_per_split = rps; t.dw = a.out;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.yb = a.w_bound;
+    t.single = g_bwd_single ? 1 : 0;
     const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
     int stages = TC_SMEM_LIMIT / stage_bytes;
     if (stages > 6) stages = 6;

@@ -35,6 +35,7 @@ static int ew_block_cap() {
 // DLIO_POOL_TMA=0 falls back to the per-thread-load pooling kernels (A/B switch for bench and tests)
 extern int g_conv_cg2;      // conv_tc.cu
 extern int g_nvtx;          // lib.cu
+extern int g_bwd_single;    // conv_tc.cu
 static int g_pool_tma = -1;
 static bool pool_tma_enabled() {
     if (g_pool_tma < 0) {
@@ -1436,6 +1437,7 @@ extern "C" int dlio_set_option(const char *name, int value) {
     else if (!strcmp(name, "ew_block")) dlio::g_ew_cap = value < 64 ? 64 : (value > 256 ? 256 : value);
     else if (!strcmp(name, "conv_cg2")) dlio::g_conv_cg2 = value ? 1 : 0;
     else if (!strcmp(name, "nvtx")) dlio::g_nvtx = value ? 1 : 0;
+    else if (!strcmp(name, "bwd_single_pass")) dlio::g_bwd_single = value ? 1 : 0;
     else {
         set_error("set_option: unknown option %s", name);
         return DLIO_ERR_INVALID;

@@ -89,7 +89,9 @@ typedef enum {
  * the element-wise passes (default 256; environment DLIO_EW_BLOCK), "conv_cg2" 0/1 -- stride-1 fp16 convolutions with 128-
  * channel output tiles on CTA pairs (tcgen05 cta_group::2; default 1; environment DLIO_CONV_CG2), "nvtx" 0/1 -- an NVTX
  * range named dlio/<kernel class> around the launches of every entry point (default 0; environment DLIO_NVTX; the
- * Python engine adds a range per layer, e.g. encoder1.conv3, when it is on). */
+ * Python engine adds a range per layer, e.g. encoder1.conv3, when it is on), "bwd_single_pass" 0/1 -- MEASUREMENT ONLY:
+ * dgrad and wgrad issue the hi*hi product alone (plain fp16 / TF32 operand accuracy, the reference's own cudnn.allow_tf32
+ * level) instead of the three products of the split scheme; default 0, the gradient parity tests fail with it on. */
 int dlio_set_option(const char *name, int value);
 /* Caller-owned scratch of one call, in bytes -- the library never allocates device memory.  One
  * query for every entry point that takes scratch:
