@@ -212,7 +212,10 @@ class PointSegEncoder(_Encoder):
         # the squeeze output (16 .. 80 channels) is allocated with a multiple of 64 channels, zeros beyond the real
         # ones, so that both expand convolutions run on the fp16 tensor-core kernels
         sq = run.params[q + "squeeze.weight"].shape[0]
-        s = E.conv_bn(run, x, q + "squeeze", q + "squeeze_bn", out_pad=(1, 1), out_c_pad=(sq + 63) // 64 * 64)
+        # ... and its only consumers are those two convolutions, so no fp32 copy of it is written
+        c_pad = (sq + 63) // 64 * 64
+        s = E.conv_bn(run, x, q + "squeeze", q + "squeeze_bn", out_pad=(1, 1), out_c_pad=c_pad,
+                      out_f32=not E.consumer_reads_f16_only(c_pad, ex, 3, (1, 1), x.w, x.h))
         res = x if (bypass and x.c == 2 * ex) else None
         out = E.conv_bn(run, s, q + "expand1x1", q + "expand1x1_bn", res=res, res_mode=2, c_off=0, out_c=2 * ex,
                         out_pad=(1, 1))
