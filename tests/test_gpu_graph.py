@@ -77,3 +77,36 @@ def test_graph_replays_draw_fresh_dropout_masks():
         torch.cuda.synchronize()
     # BN running statistics do not enter a train-mode forward, so only the dropout masks can change the loss
     assert len({round(v, 9) for v in losses}) == 3, losses
+
+
+def test_split_backward_two_graphs_equal_the_unsplit_step():
+    """The N > 1 step of bench.py on one GPU: the backward pass cut at the encoders' feature vectors
+    (``split_backward``), graph A = forward + loss + backward of everything downstream, graph B = the encoders'
+    backward, a callback in between (where the downstream all-reduce is fired).  Same gradients as the eager,
+    unsplit step; both input slots work."""
+    from deeplio_b200.graph import GraphedTrainStep
+    model, opt, batches, fwd_loss = _setup(no_dropout=True)
+    eager = []
+    for d in batches:
+        opt.zero_grad()
+        loss = fwd_loss(d)
+        loss.backward()
+        eager.append((float(loss), opt.flat_grad.clone()))
+    del loss
+    lidar = model.lidar_feat_net
+    lidar.split_backward = True
+    try:
+        step = GraphedTrainStep(fwd_loss, batches[0], opt.zero_grad, model=model, second_backward=lidar.backward_encoders)
+        assert len(step.graphs_b) == len(step.graphs) == 2
+        calls = []
+        for rep in range(2):
+            for d, (eloss, egrad) in zip(batches, eager):
+                loss = step(d, between=lambda: calls.append(opt.flat_grad.abs().sum().item()))
+                torch.cuda.synchronize()
+                assert abs(float(loss) - eloss) <= 1e-5 * max(1.0, abs(eloss))
+                assert (opt.flat_grad - egrad).abs().max().item() <= 2e-5 * egrad.abs().max().item()
+        # the callback ran between the two graphs: the encoders' gradients were still zero there
+        enc = [p for k, p in model.named_parameters() if ".encoder" in k]
+        assert len(calls) == 4 and all(c > 0 for c in calls) and all(p.grad.abs().max().item() > 0 for p in enc[:2])
+    finally:
+        lidar.split_backward = False
