@@ -22,7 +22,7 @@ class Conv(C.Structure):
 
 
 class BnPool(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("relu", "res_mode", "pool_k", "pool_sh", "pool_sw", "c_off", "out_group")]
+    _fields_ = [(k, C.c_int) for k in ("relu", "res_mode", "pool_k", "pool_sh", "pool_sw", "c_off", "out_group", "zero_tail")]
 
 
 class LossTerm(C.Structure):
@@ -62,6 +62,11 @@ _PROTOS = {
     "dlio_weight_flip_transpose": (I, [P, I, I, I, I, P, P, P]),
     "dlio_weight_pack_f16": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "dlio_pack_f16": (I, [P, LL, I, P, P, P]),
+    "dlio_absmax": (I, [P, LL, P, P]),
+    "dlio_weight_to_s2d_f16": (I, [P, I, I, I, I, I, P, P, P]),
+    "dlio_weight_grad_from_s2d_f16": (I, [P, I, I, I, I, I, P, P]),
+    "dlio_conv2d_fwd_f16_folded": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
+    "dlio_conv2d_bwd_weight_f16_folded": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
     "dlio_weight_pack_pair_f16": (I, [P, I, I, I, I, I, I, P, P, P]),
     "dlio_weight_grad_from_pair": (I, [P, I, I, I, I, P, P]),
     "dlio_conv2d_fwd_f16": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
@@ -95,7 +100,7 @@ _PROTOS = {
     "dlio_se3_chain_bwd": (I, [P, P, I, I, P, P, P, P, P]),
     "dlio_gt_relative": (I, [P, I, I, P, I, P, P, P, P]),
     "dlio_finite_check": (I, [P, P, I, P, P]),
-    "dlio_pair_gather": (I, [P, LL, LL, LL, I, I, P, I, I, I, Tensor4, P, P, P, I, P]),
+    "dlio_pair_gather": (I, [P, LL, LL, LL, I, I, P, I, I, I, Tensor4, P, P, P, P, P, I, P]),
     "dlio_scan_scratch_bytes": (SZ, [I, I]),
     "dlio_scan_project": (I, [P, I, I, I, F, F, F, F, P, I, P, P, P, P, P, P]),
     "dlio_imu_windows": (I, [P, P, I, P, I, I, P, P, P, P, P]),
@@ -107,7 +112,7 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 if _lib.dlio_abi_version() != ABI_VERSION:
     raise ImportError("deeplio_b200: ABI version mismatch (library %d, binding %d)" % (_lib.dlio_abi_version(), ABI_VERSION))
 

@@ -136,6 +136,62 @@ extern "C" int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float
     return DLIO_OK;
 }
 
+// First layer, "folded split" operands (conv_s2d.cu): x is the [n, h, w/4, 64] view of the packed 8-channel input
+// planes (per pixel [8 hi | 8 lo]; pads ph, 1), y the [n, h, w/4, R * cout] view of the fp32 output.
+extern "C" int dlio_conv2d_fwd_f16_folded(dlio_tensor4 x, const void *x_h2, const float *x_bound, const void *w4_h2,
+                                          const float *w_bound, const float *bias, dlio_conv cv, int act,
+                                          dlio_tensor4 y, float *y_ptr, double *stats, void *stream) {
+    int rc = same_conv_check(x, y, cv, "conv2d_fwd_f16_folded");
+    if (rc) return rc;
+    DLIO_CHECK_ARG(x_h2 && x_bound && w4_h2 && w_bound && y_ptr && x.c == 64, "conv2d_fwd_f16_folded: bad argument");
+    ConvArgs a;
+    a.x = Geo(x); a.y = Geo(y); a.o = Geo(y);
+    a.kh = cv.kh; a.kw = cv.kw; a.sh = 1; a.sw = 1; a.ph = cv.ph; a.pw = cv.pw;
+    a.cin = x.c; a.cout = y.c; a.act = act;
+    a.x_hi = a.x_lo = a.w_hi = a.w_lo = nullptr;
+    a.x_h2 = (const __half *)x_h2; a.w_h2 = (const __half *)w4_h2; a.x_bound = x_bound; a.w_bound = w_bound;
+    a.bias = bias; a.out = y_ptr; a.stats = stats; a.p_chunk = 0; a.fold = 1;
+    rc = conv_tc_fwd(a, DLIO_PROF_CONV_FWD_TC, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    DLIO_CHECK_ARG(rc == 1, "conv2d_fwd_f16_folded: shape not supported (cout %d %% 16, input pads %d,%d >= %d,%d)", y.c,
+                   x.ph, x.pw, cv.ph, cv.pw);
+    return DLIO_OK;
+}
+
+// dw64 [dy.c][kh][kw][64] (fp32, K index k = p * 16 + part * 8 + c: dlio_weight_grad_from_s2d_f16 folds it to OIHW).
+// dy: the [n, h, w/4, R * 64] view (pads as x) of dy planes stored per OUTPUT pixel as [64 hi | 64 lo].
+extern "C" int dlio_conv2d_bwd_weight_f16_folded(dlio_tensor4 x, const void *x_h2, const float *x_bound, dlio_tensor4 dy,
+                                                 const void *dy_h2, const float *dy_bound, dlio_conv cv, float *dw64,
+                                                 void *stream) {
+    int rc = same_conv_check(x, dy, cv, "conv2d_bwd_weight_f16_folded");
+    if (rc) return rc;
+    DLIO_CHECK_ARG(x_h2 && x_bound && dy_h2 && dy_bound && dw64 && x.c == 64 && dy.c % 128 == 0,
+                   "conv2d_bwd_weight_f16_folded: bad argument (x.c == 64, dy.c a multiple of 128)");
+    ConvArgs a;
+    a.x = Geo(x); a.y = Geo(dy); a.o = Geo(dy);
+    a.kh = cv.kh; a.kw = cv.kw; a.sh = 1; a.sw = 1; a.ph = cv.ph; a.pw = cv.pw;
+    a.cin = x.c; a.cout = dy.c; a.act = 0;
+    a.x_hi = a.x_lo = a.w_hi = a.w_lo = nullptr;
+    a.x_h2 = (const __half *)x_h2; a.w_h2 = (const __half *)dy_h2; a.x_bound = x_bound; a.w_bound = dy_bound;
+    a.bias = nullptr; a.out = dw64; a.stats = nullptr; a.p_chunk = 0; a.fold = 1;
+    rc = conv_tc_wgrad(a, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    DLIO_CHECK_ARG(rc == 1, "conv2d_bwd_weight_f16_folded: shape not supported (shared padded grid)");
+    return DLIO_OK;
+}
+
+// max |x| over n floats -> *bound (one float in device memory; the scale of packed fp16 planes derives from it)
+extern "C" int dlio_absmax(const float *x, long long n, float *bound, void *stream) {
+    DLIO_CHECK_ARG(x && bound && n > 0, "absmax: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, st);
+    DLIO_CUDA(cudaMemsetAsync(bound, 0, sizeof(float), st));
+    long long grid = (n + 256 * 16 - 1) / (256 * 16);
+    absmax_kernel<<<(unsigned)(grid > 2368 ? 2368 : grid), 256, 0, st>>>(x, n, bound);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
 extern "C" int dlio_conv2d_bwd_data_f16(dlio_tensor4 dy, const void *dy_h2, const float *dy_bound, const void *wt_h2,
                                         const float *w_bound, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr,
                                         void *stream) {

@@ -59,6 +59,67 @@ __global__ void weight_grad_from_s2d_kernel(const float *__restrict__ dw4, int c
     dw[i] = s;
 }
 
+// "Folded split" operands of the first layer (fp16 tensor-core path without a 64-byte-swizzle kernel).  The input
+// planes hold, per pixel, [8 hi | 8 lo] halves (common.cuh, fp16 operand split), so a group of four pixels is ONE
+// 128-byte row of 64 halves, K index k = p * 16 + part * 8 + c (part 0 = hi, 1 = lo).  With the weight planes
+//     B_main[k] = part == 0 ? w_hi : 0          B_corr[k] = part == 0 ? w_lo : w_hi
+// the kernel's "hi" product x . B_main is x_hi * w_hi and its "hi x lo" product x . B_corr is x_hi * w_lo + x_lo * w_hi:
+// the two accumulators of the split scheme from TWO products over a K of 64 instead of three over a K of 32, and no
+// second plane of x.  Rows: (r, co), columns: (dy, t, k); layout [R * cout][2][kh * 3 * 64] as every packed weight.
+__global__ void __launch_bounds__(256) weight_to_s2d_f16_kernel(const float *__restrict__ w, int cout, int cin, int kh,
+                                                                int kw, int sw, const float *bound,
+                                                                __half *__restrict__ out) {
+    const int R = 4 / sw, pw = (kw - 1) / 2;
+    const long long K = (long long)kh * 3 * 64;
+    const long long total = (long long)R * cout * K;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float s = f16_scale_from_bound(*bound);
+    const int k = (int)(i % 64);
+    long long t1 = i / 64;
+    const int t = (int)(t1 % 3);
+    t1 /= 3;
+    const int dy = (int)(t1 % kh);
+    const int rco = (int)(t1 / kh);
+    const int p = k >> 4, part = (k >> 3) & 1, c = k & 7;
+    const int r = rco / cout, co = rco - r * cout;
+    const int dx = 4 * (t - 1) + p - sw * r + pw;
+    float v = 0.f;
+    if (c < cin && dx >= 0 && dx < kw) v = w[(((size_t)co * cin + c) * kh + dy) * kw + dx];   // OIHW
+    __half h, l;
+    f16_split(v * s, h, l);
+    const size_t col = (size_t)(i % K);
+    out[(size_t)rco * 2 * K + col] = part == 0 ? h : __float2half(0.f);
+    out[(size_t)rco * 2 * K + K + col] = part == 0 ? l : h;
+}
+
+// dw[co][c][dy][dx] (OIHW) = sum over (r, t, p) that map to dx, and over both parts, of dw64[(r, co)][dy][t][k]
+__global__ void weight_grad_from_s2d_f16_kernel(const float *__restrict__ dw64, int cout, int cin, int kh, int kw,
+                                                int sw, float *__restrict__ dw) {
+    const int R = 4 / sw, pw = (kw - 1) / 2;
+    const long long total = (long long)cout * cin * kh * kw;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int dx = (int)(i % kw);
+    long long t1 = i / kw;
+    int dy = (int)(t1 % kh);
+    t1 /= kh;
+    int c = (int)(t1 % cin);
+    int co = (int)(t1 / cin);
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) {
+        int off = dx + sw * r - pw;          // = 4 t' + p
+        int tq = (off + 8) / 4 - 2;          // floor(off / 4) for off >= -8
+        int p = off - 4 * tq;
+        int t = tq + 1;
+        if (t >= 0 && t < 3) {
+            const float *g = dw64 + ((((size_t)(r * cout + co)) * kh + dy) * 3 + t) * 64 + p * 16 + c;
+            s += g[0] + g[8];
+        }
+    }
+    dw[i] = s;
+}
+
 // out[j*c + k] = sum_r in[j*R*c + r*c + k]   (j = 0: sums, j = 1: sums of squares)
 __global__ void fold_stats_kernel(const double *__restrict__ in, int R, int c, double *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,6 +251,36 @@ extern "C" int dlio_weight_grad_from_s2d(const float *dw4, int cout, int cin, in
                    "weight_grad_from_s2d: bad argument");
     long long total = (long long)cout * cin * kh * kw;
     weight_grad_from_s2d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(dw4, cout, cin, kh, kw, sw, dw_oihw);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_weight_to_s2d_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int sw, float *w_bound,
+                                      void *w4_h2, void *stream) {
+    DLIO_CHECK_ARG(w_oihw && w_bound && w4_h2 && cout > 0 && cin > 0 && cin <= 8 && (sw == 1 || sw == 2) && kw >= 1 &&
+                       kw <= 7 && (kw & 1),
+                   "weight_to_s2d_f16: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, st);
+    const long long n = (long long)cout * cin * kh * kw;
+    DLIO_CUDA(cudaMemsetAsync(w_bound, 0, sizeof(float), st));
+    int grid = ceil_div(n, 256 * 8);
+    absmax_plain_kernel<<<grid > 592 ? 592 : grid, 256, 0, st>>>(w_oihw, n, w_bound);
+    DLIO_LAUNCH_CHECK();
+    const long long total = (long long)(4 / sw) * cout * kh * 3 * 64;
+    weight_to_s2d_f16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w_oihw, cout, cin, kh, kw, sw, w_bound, (__half *)w4_h2);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+
+extern "C" int dlio_weight_grad_from_s2d_f16(const float *dw64, int cout, int cin, int kh, int kw, int sw,
+                                             float *dw_oihw, void *stream) {
+    DLIO_CHECK_ARG(dw64 && dw_oihw && cout > 0 && cin > 0 && cin <= 8 && (sw == 1 || sw == 2) && kw <= 7 && (kw & 1),
+                   "weight_grad_from_s2d_f16: bad argument");
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
+    long long total = (long long)cout * cin * kh * kw;
+    weight_grad_from_s2d_f16_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(dw64, cout, cin, kh, kw, sw,
+                                                                                           dw_oihw);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

@@ -60,6 +60,8 @@ struct TcArgs {
     const float *xb, *wb;   // f16: device bounds of the two operands (-> power-of-two scales)
     int single;        // A/B switch "bwd_single_pass": hi*hi products only (the correction accumulator is initialised
                        // by one lo*hi MMA per tile and otherwise left alone) -- fp16 / TF32 accuracy at 1/3 of the MMAs
+    int fold;          // "folded split" (first layer, conv_s2d.cu): every 128-byte row of x holds hi AND lo halves of
+                       // 32 channels, the weight planes are [w_hi | 0] and [w_lo | w_hi]: no x_lo plane, two products
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -259,9 +261,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                     const int row = (int)(q0 + (long long)(dy - a.ph) * a.x.wp + (dx - a.pw));
                     const uint32_t sa = smem_u32(smem) + s * stage_bytes;
                     const uint32_t fb = full0 + 8 * s;
-                    mbar_expect_tx(fb, stage_bytes);
+                    mbar_expect_tx(fb, a.fold ? stage_bytes - a_bytes : stage_bytes);
                     tma_load_2d(sa, &tm_xhi, fb, cc * bk, row);
-                    tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
+                    if (!a.fold) tma_load_2d(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
                     tma_load_2d(sa + 2 * a_bytes, &tm_whi, fb, wcol, n0);
                     tma_load_2d(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, wcol, n0);
                 }
@@ -301,8 +303,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                // 128-byte rows / 32 bytes per MMA K step
                         const uint64_t ko = so + (uint64_t)(k * 2);
-                        if (!a.single || !(it | k)) umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                        if (!a.single) umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                        if (!a.fold && (!a.single || !(it | k)))
+                            umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                        if (!a.single) umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, (a.fold && !(it | k)) ? 0u : 1u);
                         umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
                     }
                     umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
@@ -586,9 +589,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constan
                     const int row = (int)(q0 + (long long)(dy - a.ph) * a.x.wp + (dx - a.pw));
                     const uint32_t sa = smem_u32(smem) + s * stage_bytes;
                     const uint32_t fb = map_to_rank(full0 + 8 * s, 0);
-                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * stage_bytes);
+                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (a.fold ? stage_bytes - a_bytes : stage_bytes));
                     tma_load_2d_pair(sa, &tm_xhi, fb, cc * bk, row);
-                    tma_load_2d_pair(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
+                    if (!a.fold) tma_load_2d_pair(sa + a_bytes, &tm_xlo, fb, cc * bk, row);
                     tma_load_2d_pair(sa + 2 * a_bytes, &tm_whi, fb, wcol, n0);
                     tma_load_2d_pair(sa + 2 * a_bytes + b_bytes, &tm_wlo, fb, wcol, n0);
                 }
@@ -629,8 +632,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ko = so + (uint64_t)(k * 2);
-                            if (!a.single || !(it | k)) umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                            if (!a.single) umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                            if (!a.fold && (!a.single || !(it | k)))
+                                umma2<0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                            if (!a.single) umma2<1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, (a.fold && !(it | k)) ? 0u : 1u);
                             umma2<2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (si | k) ? 1u : 0u);
                         }
                         umma2_commit_both(empty0 + 8 * s);
@@ -879,9 +883,11 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     if ((((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo | (uintptr_t)a.out |
           (uintptr_t)a.x_h2 | (uintptr_t)a.w_h2) & 15) != 0) return 0;
 
+    if (a.fold && !(f16 && a.cin == TC_BK16 && a.hdec == 1)) return 0;
     TcArgs t;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.wb = a.w_bound;
     t.hdec = a.hdec;
+    t.fold = a.fold;
     t.single = (prof_kind == DLIO_PROF_CONV_DGRAD_TC && g_bwd_single) ? 1 : 0;
     t.x = a.x; t.o = a.o;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw;
@@ -898,7 +904,12 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     CUtensorMap mxh, mxl, mwh, mwl;
     const long long K = (long long)a.kh * a.kw * a.cin;
     int rc;
-    if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, TC_BM))) return rc;
+    if (a.fold) {       // one plane, rows of 64 halves
+        if ((rc = make_map(&mxh, a.x_h2, true, rows, a.cin, a.cin, TC_BM))) return rc;
+        mxl = mxh;
+    } else if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, TC_BM))) {
+        return rc;
+    }
     if ((rc = make_map_pair(&mwh, &mwl, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn))) return rc;
     t.mtiles = (rows + TC_BM - 1) / TC_BM;
     t.ntiles = a.cout / bn;
@@ -970,6 +981,8 @@ struct TcWgradArgs {
     int f16;
     const float *xb, *yb;   // f16: device bounds of x and dy
     int single;             // see TcArgs::single
+    int fold;               // see TcArgs::fold (swap mode only); fold_cs: halves between the dy boxes of consecutive
+    int fold_cs;            // 64-channel groups (dy rows are [64 hi | 64 lo] per output pixel: 128)
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, bool f16) {
@@ -1061,7 +1074,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
             if (elect_one()) {
                 const uint32_t sa = smem_u32(smem) + s * stage_bytes;
                 const uint32_t fb = full0 + 8 * s;
-                mbar_expect_tx(fb, stage_bytes);
+                mbar_expect_tx(fb, a.fold ? stage_bytes - a_bytes : stage_bytes);
                 if (swap) {
                     // A: x boxes of taps tap .. tap + 3 (the host passes the x maps first); a tap past the last one
                     // reads rows far outside the tensor, which TMA fills with zeros
@@ -1070,11 +1083,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
                         const int tj = tap + j, dyj = tj / a.kw, dxj = tj - dyj * a.kw;
                         const int rj = tj < taps_all ? q + (dyj - a.ph) * a.wp + (dxj - a.pw) : -(1 << 30);
                         tma_load_2d(sa + j * box_bytes, &tm_dyhi, fb, 0, rj);
-                        tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, 0, rj);
+                        if (!a.fold) tma_load_2d(sa + a_bytes + j * box_bytes, &tm_dylo, fb, 0, rj);
                     }
                     for (int j = 0; j < nb_boxes; ++j) {
-                        tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, co0 + bc * j, q);
-                        tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, co0 + bc * j, q);
+                        // fold: dy rows are [64 hi | 64 lo] per output pixel, one 64-channel box per pixel
+                        const int col = a.fold ? (co0 / bc + j) * a.fold_cs : co0 + bc * j;
+                        tma_load_2d(sa + 2 * a_bytes + j * box_bytes, &tm_xhi, fb, col, q);
+                        tma_load_2d(sa + 2 * a_bytes + b_bytes + j * box_bytes, &tm_xlo, fb, col, q);
                     }
                 } else {
 #pragma unroll
@@ -1110,8 +1125,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t ko = so + (uint64_t)k * kstep;
-                    if (!a.single || !(it | k)) umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
-                    if (!a.single) umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, 1u);
+                    if (!a.fold && (!a.single || !(it | k)))
+                        umma<F16, 0>(t_corr, dA_lo + ko, dB_hi + ko, idesc, (it | k) ? 1u : 0u);
+                    if (!a.single || (a.fold && !(it | k)))
+                        umma<F16, 1>(t_corr, dA_hi + ko, dB_lo + ko, idesc, (a.fold && !(it | k)) ? 0u : 1u);
                     umma<F16, 2>(t_main, dA_hi + ko, dB_hi + ko, idesc, (it >= 3 || k) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
@@ -1152,10 +1169,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyhi, const __grid_consta
             if (swap) {
                 if (row_ok) {
                     const size_t cstride = (size_t)taps * a.cin;      // next output channel
+                    // fold: TMEM lane m = (tap, pixel p, part, channel c); the lanes of the lo halves of x carry
+                    // x_lo * dy_hi in the main accumulators (a correction term) and nothing useful in the other
+                    const bool lo_lane = a.fold && ((sm_ >> 3) & 1);
+                    const float cu = lo_lane ? 0.f : corr, cm = lo_lane ? corr : 1.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         atomicAdd(orow + (size_t)(c0 + j) * cstride,
-                                  fmaf(__uint_as_float(u[j]), corr, __uint_as_float(v[j])) * inv);
+                                  fmaf(__uint_as_float(u[j]), cu, __uint_as_float(v[j]) * cm) * inv);
                 }
                 continue;
             }
@@ -1341,6 +1362,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
         if (a.cin % c == 0 && c % bc == 0) { bn = c; break; }
     if (!bn) return 0;
     const bool swap = a.cin == bc && a.cout % TC_BM == 0;   // see the kernel: x tiles of 128 / Cin taps as A, dy as B
+    if (a.fold && !(f16 && swap)) return 0;
     const int tpg = TC_BM / bc;                              // taps per CTA in swap mode
     if (swap) bn = TC_BM;
     const long long rows = (long long)a.x.n * a.x.hp * a.x.wp;
@@ -1375,6 +1397,7 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     t.rows = rows; t.rows_per_split = rps; t.dw = a.out;
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.yb = a.w_bound;
     t.single = g_bwd_single ? 1 : 0;
+    t.fold = a.fold; t.fold_cs = 2 * bc;
     const int stage_bytes = 2 * TC_BM * TC_BK * 4 + 2 * bn * TC_BK * 4;
     int stages = TC_SMEM_LIMIT / stage_bytes;
     if (stages > 6) stages = 6;
@@ -1384,8 +1407,17 @@ int conv_tc_wgrad(const ConvArgs &a, cudaStream_t st) {
     CUtensorMap mdh, mdl, mxh, mxl;
     int rc;
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if ((rc = make_map_pair(&mdh, &mdl, a.w_hi, a.w_lo, a.w_h2, rows, a.cout, krows, sw))) return rc;
-    if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, krows, sw))) return rc;
+    if (a.fold) {
+        // dy: rows of (cout / 64) output pixels x [64 hi | 64 lo]; x: one plane, rows of 64 halves
+        const long long dcols = 2LL * a.cout;
+        if ((rc = make_map(&mdh, a.w_h2, true, rows, dcols, dcols, krows, sw))) return rc;
+        if ((rc = make_map(&mdl, a.w_h2 + bc, true, rows, dcols - bc, dcols, krows, sw))) return rc;
+        if ((rc = make_map(&mxh, a.x_h2, true, rows, a.cin, a.cin, krows, sw))) return rc;
+        mxl = mxh;
+    } else {
+        if ((rc = make_map_pair(&mdh, &mdl, a.w_hi, a.w_lo, a.w_h2, rows, a.cout, krows, sw))) return rc;
+        if ((rc = make_map_pair(&mxh, &mxl, a.x_hi, a.x_lo, a.x_h2, rows, a.cin, krows, sw))) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         DLIO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));

@@ -197,11 +197,20 @@ struct BnPool {
     uint8_t *idx;
     float *ymax;                // optional [n, ho, wo, C]: the conv output y at the arg-max (what the BN backward
                                 // sums need from the input side: dlio_pool_bwd_sums)
+    int zero_tail;              // generic kernel: also write zeros to the output channels [y.c, out.c)
 };
 __device__ __forceinline__ void bnpool_store(const BnPool &a, unsigned pix, int c, const float4 &v, float s16) {
     const size_t o = (size_t)pix * a.out.c + a.c_off + c;
     if (a.out_hi) st4_split(a.out_hi, a.out_lo, o, v);
     if (a.out_h2) st4_h2(a.out_h2, pix, a.out.c, a.c_off + c, v, s16, a.group);
+}
+
+// channels [y.c, out.c) of one output pixel, shared among the pixel's threads (thread of channel c: y.c + c, 2 y.c + c ..)
+__device__ __forceinline__ void bnpool_zero_tail(const BnPool &a, unsigned pix, int c) {
+    for (int cz = a.y.c + c; cz < a.out.c; cz += a.y.c) {
+        if (a.out_hi) st4_split(a.out_hi, a.out_lo, (size_t)pix * a.out.c + cz, f4(0.f));
+        if (a.out_h2) st4_h2_zero(a.out_h2, pix, a.out.c, cz, a.group);
+    }
 }
 
 __device__ __forceinline__ float4 bnpool_value(const BnPool &a, int n, int h, int w, int c, const float4 &sc,
@@ -223,6 +232,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(BnPool a) {
         int yy = (int)(t % (unsigned)a.out.hp);
         int n = (int)(t / (unsigned)a.out.hp);
         int ho = yy - a.out.ph, wo = xx - a.out.pw;
+        if (a.zero_tail) bnpool_zero_tail(a, pix, c);
         if (ho < 0 || ho >= a.out.h || wo < 0 || wo >= a.out.w) {
             bnpool_store(a, pix, c, f4(0.f), 1.f);
             continue;
@@ -1526,6 +1536,8 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
     a.out_hi = out_hi; a.out_lo = out_lo; a.idx = pool_idx; a.ymax = pool_ymax;
     a.out_h2 = (__half *)out_h2; a.out_bound = out_bound;
     a.group = p.out_group == 2 ? 2 : 1;
+    a.zero_tail = p.zero_tail ? 1 : 0;
+    DLIO_CHECK_ARG(!a.zero_tail || (p.pool_k == 1 && p.c_off == 0), "bn_act_pool_fwd: zero_tail needs pool_k == 1 and c_off == 0");
     DLIO_CHECK_ARG(a.group == 1 || (out_h2 && a.out.wp % 2 == 0), "bn_act_pool_fwd: the pixel-pair layout needs fp16 planes and an even padded width");
     long long total = (long long)a.out.n * a.out.hp * a.out.wp * a.cg;
     const int block = block_for_cg(a.cg);

@@ -143,11 +143,14 @@ struct PairGather {
     Combos cb;
     Geo d;
     float *hi, *lo;
+    __half *h2;            // optional packed fp16 planes, per pixel [c hi | c lo], scaled from *bound
+    const float *bound;
     int *flags;
     int flag_bit;
 };
 __global__ void __launch_bounds__(256) pair_gather_kernel(PairGather a) {
     const Geo &d = a.d;
+    const float s16 = a.h2 ? f16_scale_from_bound(*a.bound) : 1.f;
     const unsigned total = (unsigned)d.n * d.hp * d.wp;
     bool bad = false;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -171,7 +174,9 @@ __global__ void __launch_bounds__(256) pair_gather_kernel(PairGather a) {
                 }
                 v[j] = x;
             }
-            st4_split(a.hi, a.lo, (size_t)i * d.c + c0, make_float4(v[0], v[1], v[2], v[3]));
+            const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+            if (a.hi) st4_split(a.hi, a.lo, (size_t)i * d.c + c0, v4);
+            if (a.h2) st4_h2(a.h2, i, d.c, c0, v4, s16, 1);
         }
     }
     if (a.flags && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(a.flags, a.flag_bit);
@@ -266,16 +271,20 @@ extern "C" int dlio_finite_check(const float *const *tensors, const long long *s
 
 extern "C" int dlio_pair_gather(const float *frames, long long sb, long long sf, long long sc, int B, int F,
                                 const int *combinations, int S, int c0, int C, dlio_tensor4 dst, float *dst_ptr,
-                                float *dst_lo, int *flags, int flag_bit, void *stream) {
+                                float *dst_lo, void *dst_h2, const float *bound, int *flags, int flag_bit,
+                                void *stream) {
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
-    DLIO_CHECK_ARG(frames && dst_ptr && valid_t4(dst) && dst.c % 4 == 0 && dst.c >= 2 * C && C > 0 && c0 >= 0 &&
-                       dst.n == B * S && B > 0 && F > 0,
+    DLIO_CHECK_ARG(frames && (dst_ptr || dst_h2) && valid_t4(dst) && dst.c % 4 == 0 && dst.c >= 2 * C && C > 0 &&
+                       c0 >= 0 && dst.n == B * S && B > 0 && F > 0,
                    "pair_gather: bad argument");
+    DLIO_CHECK_ARG((dst_ptr || !dst_lo) && (!dst_h2 || (bound && (((uintptr_t)dst_h2) & 15) == 0)),
+                   "pair_gather: dst_lo needs dst_ptr, fp16 planes need their bound");
     PairGather a;
     int rc = fill_combos(a.cb, combinations, S, F, "pair_gather");
     if (rc) return rc;
     a.src = frames; a.sb = sb; a.sf = sf; a.sc = sc; a.S = S; a.C = C; a.c0 = c0;
     a.d = Geo(dst); a.hi = dst_ptr; a.lo = dst_lo; a.flags = flags; a.flag_bit = flag_bit;
+    a.h2 = (__half *)dst_h2; a.bound = bound;
     const long long total = (long long)a.d.n * a.d.hp * a.d.wp;
     DLIO_CHECK_ARG(total < (1LL << 32), "pair_gather: tensor too large");
     long long blocks = (total + 255) / 256;

@@ -63,18 +63,36 @@ class PairedFrames:
         return self.frames[:, idx][:, :, :, self.c0:self.c0 + self.c]
 
 
-def pair_gather(run_device, paired, c_pad, ph, pw, split, flags=None, flag_bit=0):
-    """``PairedFrames`` -> padded NHWC [B*S, H+2ph, W+2pw, c_pad] (+ TF32 lo plane when ``split``) in one launch."""
+def frames_bound(paired):
+    """Upper bound of max|frames| (one float in device memory), taken over the whole frames tensor -- all channels, so
+    the views cut from one tensor (xyz, normals) can share it."""
+    fr = paired.frames
+    bound = torch.empty(1, device=fr.device, dtype=torch.float32)
+    L.absmax(ptr(fr), fr.numel(), ptr(bound), torch.cuda.current_stream().cuda_stream)
+    return bound
+
+
+def pair_gather(run_device, paired, c_pad, ph, pw, split, flags=None, flag_bit=0, f16=False, bound=None):
+    """``PairedFrames`` -> padded NHWC [B*S, H+2ph, W+2pw, c_pad] in one launch: fp32 (+ TF32 lo plane when
+    ``split``) -> (hi, lo), or with ``f16`` the packed fp16 planes [.., 2, c_pad] and their bound -> (h2, bound)."""
     fr = paired.frames
     b, f, _, h, w = fr.shape
     s = len(paired.combinations)
     shape = (b * s, h + 2 * ph, w + 2 * pw, c_pad)
+    comb = paired.combinations.ctypes.data_as(C.c_void_p)
+    st = torch.cuda.current_stream().cuda_stream
+    if f16:
+        if not fr.is_contiguous():
+            raise RuntimeError("pair_gather(f16=True): frames must be contiguous (their bound is taken over the storage)")
+        bound = frames_bound(paired) if bound is None else bound
+        h2 = torch.empty(shape[:3] + (2, c_pad), device=run_device, dtype=torch.float16)
+        L.pair_gather(ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2), b, f, comb, s, paired.c0, paired.c,
+                      L.Tensor4(b * s, h, w, c_pad, ph, pw), None, None, ptr(h2), ptr(bound), ptr(flags), flag_bit, st)
+        return h2, bound
     hi = torch.empty(shape, device=run_device, dtype=torch.float32)
     lo = torch.empty_like(hi) if split else None
-    comb = paired.combinations.ctypes.data_as(C.c_void_p)
     L.pair_gather(ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2), b, f, comb, s, paired.c0, paired.c,
-                  L.Tensor4(b * s, h, w, c_pad, ph, pw), ptr(hi), ptr(lo), ptr(flags), flag_bit,
-                  torch.cuda.current_stream().cuda_stream)
+                  L.Tensor4(b * s, h, w, c_pad, ph, pw), ptr(hi), ptr(lo), None, None, ptr(flags), flag_bit, st)
     return hi, lo
 
 

@@ -77,6 +77,18 @@ def f16_ok(cin, cout, stride):
     return USE_TC and USE_F16 and tuple(stride) == (1, 1) and cin % 64 == 0 and cout % 16 == 0
 
 
+# first layer on the fp16 kernels through the "folded split" operands (csrc/conv_s2d.cu); DLIO_FIRST_F16=0 keeps 3xTF32
+FIRST_F16 = os.environ.get("DLIO_FIRST_F16", "1") == "1"
+
+
+def first_layer_f16_ok(wshape, stride, width):
+    """The first convolution (<= 8 input channels) can run on packed fp16 input planes: W stride 2 (two outputs per
+    4-pixel group -> 128 tensor-core columns), 64 output channels (one dy box per output pixel in wgrad)."""
+    cout, cin, kh, kw = wshape
+    return (USE_TC and USE_F16 and FIRST_F16 and tuple(stride) == (1, 2) and cout == 64 and cin <= 8 and kw <= 7
+            and kw % 2 == 1 and width % 4 == 0)
+
+
 def pair_ok(x, cin, cout, kh, kw, stride):
     """W-stride-2 convolution on the tensor cores through the pixel-pair view (csrc/conv_s2d.cu): the input's fp16
     planes must be in the pixel-pair layout (producer called with ``out_group=2``); H stride 2 is computed over the
@@ -297,9 +309,14 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
     fwd_f16 = x.h2 is not None and x.group == 1 and f16_ok(cin_pad, cout, stride) and pads_ok
     fwd_tc = (not fwd_f16) and x.lo is not None and tc_ok(cin_pad, cout, stride) and pads_ok
     # first layer (8-channel input): stride-1 kh x 3 convolution over the space-to-depth views (csrc/conv_s2d.cu)
-    s2d = (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7 and x.w % 4 == 0
-           and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0 and not x.needs_grad)
-    assert fwd_f16 or pair or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
+    s2d_f16 = (x.h2 is not None and x.c == 8 and x.group == 1 and x.pw == 4 and x.ph >= cph and not x.needs_grad
+               and first_layer_f16_ok(w.shape, stride, x.w))
+    s2d = s2d_f16 or (USE_TC and x.lo is not None and x.c == 8 and sh == 1 and sw in (1, 2) and kw <= 7
+                      and x.w % 4 == 0 and x.pw == 4 and x.ph >= cph and (4 // sw * cout) % 128 == 0
+                      and not x.needs_grad)
+    if s2d:
+        fwd_f16 = fwd_tc = False
+    assert fwd_f16 or pair or s2d_f16 or x.t is not None, (cname, "input has no fp32 plane and the fp16 path does not apply")
     flops = 2.0 * cout * ho * wo * cin * kh * kw * x.n
     if FLOPS is not None:
         k = "conv_fwd_tc" if (s2d or pair or fwd_f16 or fwd_tc) else "conv_fwd_simt"
@@ -314,12 +331,21 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
         x4_t4 = L.Tensor4(n, x.h, x.w // 4, 32, x.ph, 1)
         y4_t4 = L.Tensor4(n, ho, x.w // 4, R * cout, 0, 0)
         cv4 = L.Conv(kh, 3, 1, 1, cph, 1)
-        w4, w4_lo = run.empty(R * cout, kh, 3, 32), run.empty(R * cout, kh, 3, 32)
-        L.weight_to_s2d(ptr(w), cout, cin, kh, kw, sw, ptr(w4), ptr(w4_lo), st)
         bias4 = b.repeat(R) if b is not None else None
         stats4 = run.zeros(2 * R * cout, dtype=torch.float64)
-        L.conv2d_fwd(x4_t4, ptr(x.t), ptr(x.lo), ptr(w4), ptr(w4_lo), ptr(bias4), cv4, act, y4_t4, ptr(y.t),
-                     ptr(stats4), st)
+        if s2d_f16:
+            # folded split: a 4-pixel group of the packed input planes is one row of 64 halves (hi and lo of 32 values)
+            x4_t4 = L.Tensor4(n, x.h, x.w // 4, 64, x.ph, 1)
+            w_bound = run.empty(1)
+            w_h2 = run.empty(R * cout, 2, kh * 3 * 64, dtype=torch.float16)
+            L.weight_to_s2d_f16(ptr(w), cout, cin, kh, kw, sw, ptr(w_bound), ptr(w_h2), st)
+            L.conv2d_fwd_f16_folded(x4_t4, ptr(x.h2), ptr(x.bound), ptr(w_h2), ptr(w_bound), ptr(bias4), cv4, act,
+                                    y4_t4, ptr(y.t), ptr(stats4), st)
+        else:
+            w4, w4_lo = run.empty(R * cout, kh, 3, 32), run.empty(R * cout, kh, 3, 32)
+            L.weight_to_s2d(ptr(w), cout, cin, kh, kw, sw, ptr(w4), ptr(w4_lo), st)
+            L.conv2d_fwd(x4_t4, ptr(x.t), ptr(x.lo), ptr(w4), ptr(w4_lo), ptr(bias4), cv4, act, y4_t4, ptr(y.t),
+                         ptr(stats4), st)
         L.fold_stats(ptr(stats4), R, cout, ptr(stats), st)
     elif pair:
         # [n, h, w/2, 2 cin] view of the same memory, stride-1 kh x kw2 convolution, even rows kept when sh == 2
@@ -377,10 +403,9 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             out = Act(n, oh, ow, oc, out_pad[0], out_pad[1], device=run.device, f32=out_f32, f16=o16,
                       split=USE_TC and out_f32 and not o16 and oc % 32 == 0)
             out.bound = out_bound
-            if out_c_pad and oc > cout:      # the BN pass writes channels [0, cout) only
-                for buf in (out.t, out.lo, out.h2):
-                    if buf is not None:
-                        buf.zero_()
+            if out_c_pad and oc > cout:      # the BN pass also zeroes channels [cout, oc)
+                assert not pool
+                bp.zero_tail = 1
             if out_group == 2 and o16 and (ow + 2 * out_pad[1]) % 2 == 0:
                 out.group = bp.out_group = 2
         assert out.h == oh and out.w == ow and out.n == n
@@ -412,7 +437,7 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             bpb = bp
         # which kernels consume dy: 3xF16 / 3xTF32 tensor-core kernels or the fp32 CUDA-core ones
         if s2d:
-            wg, dg = "tf32", None
+            wg, dg = ("f16" if s2d_f16 else "tf32"), None
         elif pair:
             wg, dg = "f16", ("f16" if x.needs_grad else None)
         else:
@@ -493,7 +518,13 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
                     dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2), ptr(w_bound), cv2s1,
                     L.Tensor4(n, x.h, x.w // 2, 2 * cin, 0, 0), ptr(buf), st))
             return
-        if s2d:
+        if s2d_f16:
+            # dy planes per output pixel [64 hi | 64 lo]; R output pixels per row of the space-to-depth view
+            dw64 = run.empty(R * cout, kh, 3, 64)
+            L.conv2d_bwd_weight_f16_folded(x4_t4, ptr(x.h2), ptr(x.bound), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1),
+                                           ptr(dya.h2), ptr(dya.bound), cv4, ptr(dw64), st)
+            L.weight_grad_from_s2d_f16(ptr(dw64), cout, cin, kh, kw, sw, ptr(dw), st)
+        elif s2d:
             dw4 = run.empty(R * cout, kh, 3, 32)
             L.conv2d_bwd_weight(x4_t4, ptr(x.t), ptr(x.lo), L.Tensor4(n, ho, x.w // 4, R * cout, x.ph, 1), ptr(dya.t),
                                 ptr(dya.lo), cv4, ptr(dw4), st)

@@ -21,7 +21,7 @@ from .. import functional as Fn
 from .. import _lib as L
 from .._lib import ptr
 from ..config import get_config_container
-from ..data import PairedFrames, pair_gather
+from ..data import PairedFrames, frames_bound, pair_gather
 from .base import BaseNet, ParamTree, conv_params, require_cuda
 
 
@@ -30,6 +30,7 @@ class _Encoder(ParamTree):
     """Parameter container + forward program of one encoder.  ``out_channels`` = pooled feature width."""
     out_channels = 0
     first_pad = (0, 0)
+    first_conv, first_stride = None, (1, 1)      # parameter prefix and stride of the first convolution
 
     def _conv(self, name, cin, cout, k, bias):
         return self.put(name, conv_params(cin, cout, k, bias))
@@ -53,6 +54,7 @@ class Simple1Encoder(_Encoder):
     """conv(+bias) -> ReLU -> BN, seven times; ceil-mode max-pools after blocks 1, 2, 4, 6; global mean."""
     out_channels = 512
     first_pad = (2, 3)
+    first_conv, first_stride = "conv1", (1, 2)
     SPEC = [(1, 64, (5, 7)), (2, 128, (3, 5)), (3, 128, 3), (4, 256, 3), (5, 256, 3), (6, 512, 3), (7, 512, 3)]
 
     def __init__(self, cin, bypass=False):
@@ -83,6 +85,7 @@ class FlowNetEncoder(_Encoder):
     """Nine conv(no bias) -> BN -> ReLU blocks (base_net.py:55-71), global mean."""
     out_channels = 1024
     first_pad = (2, 3)
+    first_conv, first_stride = "conv1.0", (1, 2)
     SPEC = [("conv1", 64, (5, 7), (1, 2)), ("conv2", 128, (3, 5), (1, 2)), ("conv3", 256, (3, 5), (1, 2)),
             ("conv3_1", 256, 3, (1, 1)), ("conv4", 512, 3, (2, 2)), ("conv4_1", 512, 3, (1, 1)),
             ("conv5", 512, 3, (2, 2)), ("conv5_1", 512, 3, (1, 1)), ("conv6", 1024, 3, (2, 2))]
@@ -122,6 +125,7 @@ class ResNetEncoder(_Encoder):
     (torchvision resnet.py:59-105) with first-block strides (1,2),(1,2),(2,2),(2,2); global mean."""
     out_channels = 512
     first_pad = (2, 3)
+    first_conv, first_stride = "conv1", (1, 1)
     LAYERS = [("layer1", 3, 64, (1, 2)), ("layer2", 3, 128, (1, 2)), ("layer3", 3, 256, (2, 2)),
               ("layer4", 2, 512, (2, 2))]
 
@@ -174,6 +178,7 @@ class PointSegEncoder(_Encoder):
     """PSEncoder: conv1a 3x5 s(1,2) -> BN -> ReLU -> pool; five Fire blocks with SE layers and pools."""
     out_channels = 768
     first_pad = (1, 2)
+    first_conv, first_stride = "conv1a.0", (1, 2)
     # block -> entries: ('F', cin, squeeze, expand) fire | ('S', c) SE | ('P', stride) pool
     BLOCKS = [("fire_blk1", [("F", 64, 16, 64), ("F", 128, 16, 64), ("S", 128), ("P", (1, 2))]),
               ("fire_blk2", [("F", 128, 32, 128), ("F", 256, 32, 128), ("S", 256), ("P", (1, 2))]),
@@ -256,6 +261,7 @@ class _EncoderPair(torch.autograd.Function):
         feats = [torch.empty((n, 2 * c if cat else c), device=dev, dtype=torch.float32)]
         feats.append(feats[0] if cat else torch.empty((n, c), device=dev, dtype=torch.float32))
         runs = []
+        bounds = {}
         streams = _fork(dev)
         for e, view in enumerate((xyz, normals)):
             pd = dict(zip(names[e], groups[e]))
@@ -268,8 +274,20 @@ class _EncoderPair(torch.autograd.Function):
                 # row pads of 4 pixels: space-to-depth first layer
                 if isinstance(view, PairedFrames):
                     # frames paired on the fly (deeplio_b200.data): no [B,S,2,C,H,W] tensor, no reshape copy
-                    hi, lo = pair_gather(dev, view, 8, enc[e].first_pad[0], 4, E.USE_TC)
-                    x0 = E.Act(n, view.shape[4], view.shape[5], 8, enc[e].first_pad[0], 4, t=hi, lo=lo, needs_grad=False)
+                    w1 = pd.get(str(enc[e].first_conv) + ".weight")
+                    if (w1 is not None and view.frames.is_contiguous()
+                            and E.first_layer_f16_ok(w1.shape, enc[e].first_stride, view.shape[5])):
+                        # packed fp16 planes (per pixel [8 hi | 8 lo]) for the folded-split first layer; one bound
+                        # per frames tensor, shared by the two encoders when both views are cut from it
+                        key = view.frames.data_ptr()
+                        if bounds.get("key") != key:
+                            bounds["key"], bounds["bound"] = key, frames_bound(view)
+                        h2, bnd = pair_gather(dev, view, 8, enc[e].first_pad[0], 4, False, f16=True, bound=bounds["bound"])
+                        x0 = E.Act(n, view.shape[4], view.shape[5], 8, enc[e].first_pad[0], 4, needs_grad=False, f32=False)
+                        x0.h2, x0.bound = h2, bnd
+                    else:
+                        hi, lo = pair_gather(dev, view, 8, enc[e].first_pad[0], 4, E.USE_TC)
+                        x0 = E.Act(n, view.shape[4], view.shape[5], 8, enc[e].first_pad[0], 4, t=hi, lo=lo, needs_grad=False)
                     run.keep.append((x0, view.frames))
                 else:
                     x0 = E.pack_input(run, view, 8, enc[e].first_pad[0], 4)

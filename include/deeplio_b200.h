@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLIO_ABI_VERSION 6
+#define DLIO_ABI_VERSION 7
 
 typedef enum {
     DLIO_OK = 0,
@@ -192,6 +192,29 @@ int dlio_conv2d_bwd_weight_f16(dlio_tensor4 x, const void *x_h2, const float *x_
                                const void *dy_h2, const float *dy_bound, dlio_conv cv, float *dw, void *stream);
 /* fp32 [rows][c] -> packed split plane, computing the bound (max |v|) first; test / staging helper */
 int dlio_pack_f16(const float *src, long long rows, int c, float *bound, void *dst_h2, void *stream);
+/* max |x| over n floats -> *bound (device float; written, not accumulated). */
+int dlio_absmax(const float *x, long long n, float *bound, void *stream);
+
+/* First layer on the fp16 tensor-core path ("folded split"; replaces the same reference calls as dlio_conv2d_fwd for
+ * the first convolution of every encoder: lidar_feat_nets.py:306 conv1, :248 FlowNet conv1, pointseg_net.py:20 conv1a).
+ * The 8-channel input planes hold per pixel [8 hi | 8 lo] halves, so FOUR consecutive pixels are one 128-byte row of
+ * 64 halves with K index k = p * 16 + part * 8 + c.  With weight planes B_main[k] = (part == 0 ? w_hi : 0) and
+ * B_corr[k] = (part == 0 ? w_lo : w_hi) (dlio_weight_to_s2d_f16; rows (r, co) of the R = 4 / sw outputs computed from
+ * a group, columns (dy, t, k)), x . B_main = x_hi w_hi and x . B_corr = x_hi w_lo + x_lo w_hi: the two accumulators of
+ * the split scheme from two products and one plane of x.
+ *   x: the [n, h, w/4, 64] view of the input planes (pads ph, 1: the planes are stored with row pads of 4 pixels);
+ *   y: the [n, h, w/4, R * cout] view of the fp32 output [n, h, w / sw, cout]; stats: 2 * R * cout (dlio_fold_stats).
+ * Weight gradient: dy is the [n, h, w/4, R * 64] view (pads as x) of planes stored per OUTPUT pixel as [64 hi | 64 lo]
+ * (cout == 64), dw64 [R * 64][kh][3][64] fp32, folded back to OIHW by dlio_weight_grad_from_s2d_f16. */
+int dlio_weight_to_s2d_f16(const float *w_oihw, int cout, int cin, int kh, int kw, int sw, float *w_bound, void *w4_h2,
+                           void *stream);
+int dlio_weight_grad_from_s2d_f16(const float *dw64, int cout, int cin, int kh, int kw, int sw, float *dw_oihw,
+                                  void *stream);
+int dlio_conv2d_fwd_f16_folded(dlio_tensor4 x, const void *x_h2, const float *x_bound, const void *w4_h2,
+                               const float *w_bound, const float *bias, dlio_conv cv, int act, dlio_tensor4 y,
+                               float *y_ptr, double *stats, void *stream);
+int dlio_conv2d_bwd_weight_f16_folded(dlio_tensor4 x, const void *x_h2, const float *x_bound, dlio_tensor4 dy,
+                                      const void *dy_h2, const float *dy_bound, dlio_conv cv, float *dw64, void *stream);
 
 /* ------------------------------------------------------------------ batch-norm / activation / pooling
  * Replaces aten::batch_norm (train + eval), relu, max_pool2d_with_indices, adaptive_avg_pool2d and the
@@ -224,6 +247,9 @@ typedef struct {
     int out_group;  /* layout of out_h2: 0 / 1 plain rows [C hi | C lo] per pixel; 2 pixel pairs
                        [p0 C hi | p1 C hi | p0 C lo | p1 C lo] -- the operand layout of a W-stride-2 convolution run
                        through the pixel-pair view [n, h, w/2, 2C] (dlio_weight_pack_pair_f16); needs an even padded width */
+    int zero_tail;  /* dlio_bn_act_pool_fwd, pool_k == 1, c_off == 0: the output has more channels than y (a narrow
+                       Fire squeeze output allocated with a multiple of 64 channels); write zeros to channels
+                       [y.c, out.c) in the same pass instead of a memset of the whole tensor before it */
 } dlio_bnpool;
 
 /* out[n,ho,wo,c_off+c] = maxpool(act(scale[c]*y + shift[c] (+res)) (+res)); writes out's pads as zeros for
@@ -407,10 +433,12 @@ int dlio_finite_check(const float *const *tensors, const long long *sizes, int c
  * with the encoders' input reshape (lidar_feat_nets.py:216-218): frames [B, F, *, H, W] (element strides sb, sf,
  * sc; H, W contiguous) -> padded NHWC dst with dst.n = B*S images and channels (frame combinations[s][0]: c0 ..
  * c0+C-1, frame combinations[s][1]: c0 .. c0+C-1, zeros up to dst.c).  No [B,S,2,C,H,W] copy of the pairs is made.
- * dst_lo (optional): TF32 low-order plane.  flags (optional): bit `flag_bit` is raised on a NaN / Inf input. */
+ * dst_ptr / dst_lo (optional): fp32 plane and its TF32 low-order plane.  dst_h2 (optional): packed fp16 planes, per
+ * pixel [dst.c hi | dst.c lo], scaled from *bound (an upper bound of max|frames| in device memory: dlio_absmax) --
+ * the operand of dlio_conv2d_fwd_f16_folded.  flags (optional): bit `flag_bit` is raised on a NaN / Inf input. */
 int dlio_pair_gather(const float *frames, long long sb, long long sf, long long sc, int B, int F,
                      const int *combinations, int S, int c0, int C, dlio_tensor4 dst, float *dst_ptr, float *dst_lo,
-                     int *flags, int flag_bit, void *stream);
+                     void *dst_h2, const float *bound, int *flags, int flag_bit, void *stream);
 
 /* ------------------------------------------------------------------ LiDAR / IMU preprocessing (N4)
  * dlio_scan_project: one velodyne frame -> range image channels, replacing LaserScan.open_scan's depth filter +

@@ -478,15 +478,18 @@ def test_conv_bn_block_vs_torch(cfg):
         assert relerr(from_nhwc(run.agrad[id(ra)]), leaves[5].grad) < tol
 
 
-@pytest.mark.parametrize("k,stride,pre_relu,pool,first_ph", [
-    ((5, 7), (1, 2), True, (1, 2), 2),      # Simple-1 conv1 (+ ceil-mode pool); FlowNet conv1 has the same convolution
-    ((3, 5), (1, 2), False, (1, 2), 1),     # PointSeg conv1a
-    ((5, 7), (1, 1), False, (1, 2), 2),     # ResNet conv1 (stride 1: four output pixels per space-to-depth group)
+@pytest.mark.parametrize("k,stride,pre_relu,pool,first_ph,folded", [
+    ((5, 7), (1, 2), True, (1, 2), 2, False),   # Simple-1 conv1 (+ ceil-mode pool); FlowNet conv1 has the same convolution
+    ((3, 5), (1, 2), False, (1, 2), 1, False),  # PointSeg conv1a
+    ((5, 7), (1, 1), False, (1, 2), 2, False),  # ResNet conv1 (stride 1: four output pixels per space-to-depth group)
+    ((5, 7), (1, 2), True, (1, 2), 2, True),    # the same layers on packed fp16 input planes ("folded split"
+    ((3, 5), (1, 2), False, (1, 2), 1, True),   # operands): what the nets run when they are fed PairedFrames
 ])
-def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_ph):
+def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_ph, folded):
     """The first convolution of every encoder at its real size (two 6-channel 64 x 2048 images): dlio_pack_input from
     the strided [N, T, C, H, W] view, the 3xTF32 tcgen05 kernel over the space-to-depth view (csrc/conv_s2d.cu), BN,
-    pool; backward through the swapped-operand wgrad.  Against the same block in torch fp64."""
+    pool; backward through the swapped-operand wgrad.  ``folded``: dlio_pair_gather writes packed fp16 planes and the
+    layer runs on the fp16 kernels with the folded-split operands.  Against the same block in torch fp64."""
     from deeplio_b200 import engine as E
     n, h, w, cout = 2, 64, 2048, 64
     kh, kw = k
@@ -529,9 +532,18 @@ def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_
     params = {"cv.weight": wt.to(DEV), "cv.bias": b.to(DEV), "bn.weight": gamma.to(DEV), "bn.bias": beta.to(DEV)}
     bufs = {"bn.running_mean": torch.zeros(cout, device=DEV), "bn.running_var": torch.ones(cout, device=DEV)}
     run = E.Run(params, bufs, torch.device(DEV), True, True)
-    view = pairs.to(DEV)[:, :, 0:3]                       # the non-contiguous channel slice the trainer hands over
-    x0 = E.pack_input(run, view, 8, first_ph, 4)
     L = _lib()
+    if folded:
+        from deeplio_b200 import data
+        frames = pairs.to(DEV)                            # [B, F = 2, 6, H, W], one pair (0, 1) per sample
+        h2, bound = data.pair_gather(torch.device(DEV), data.PairedFrames(frames, [[0, 1]], 0, 3), 8, first_ph, 4,
+                                     False, f16=True)
+        assert abs(bound.item() - pairs.abs().max().item()) <= 1e-6 * pairs.abs().max().item()
+        x0 = E.Act(n, h, w, 8, first_ph, 4, needs_grad=False, f32=False)
+        x0.h2, x0.bound = h2, bound
+    else:
+        view = pairs.to(DEV)[:, :, 0:3]                   # the non-contiguous channel slice the trainer hands over
+        x0 = E.pack_input(run, view, 8, first_ph, 4)
     L.profile_enable(1)
     E.MASK_TRACE = {}
     try:
