@@ -55,7 +55,7 @@ _PROTOS = {
     "dlio_weight_grad_from_s2d": (I, [P, I, I, I, I, I, P, P]),
     "dlio_fold_stats": (I, [P, I, I, P, P]),
     "dlio_conv2d_fwd": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
-    "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, P, P, Conv, Tensor4, P, P]),
+    "dlio_conv2d_bwd_data": (I, [Tensor4, P, P, P, P, P, P, Conv, Tensor4, P, I, P]),
     "dlio_conv2d_bwd_weight": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
     "dlio_weight_to_ohwi": (I, [P, I, I, I, I, I, P, P, P]),
     "dlio_weight_grad_to_oihw": (I, [P, I, I, I, I, I, P, P]),
@@ -70,7 +70,7 @@ _PROTOS = {
     "dlio_weight_pack_pair_f16": (I, [P, I, I, I, I, I, I, P, P, P]),
     "dlio_weight_grad_from_pair": (I, [P, I, I, I, I, P, P]),
     "dlio_conv2d_fwd_f16": (I, [Tensor4, P, P, P, P, P, Conv, I, Tensor4, P, P, P]),
-    "dlio_conv2d_bwd_data_f16": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, P]),
+    "dlio_conv2d_bwd_data_f16": (I, [Tensor4, P, P, P, P, Conv, Tensor4, P, I, P]),
     "dlio_conv2d_bwd_weight_f16": (I, [Tensor4, P, P, Tensor4, P, P, Conv, P, P]),
     "dlio_bn_finalize": (I, [P, LL, I, P, P, P, P, F, F, I, P, P, P, P, P, P, P, P]),
     "dlio_bn_act_pool_fwd": (I, [Tensor4, P, P, P, Tensor4, P, BnPool, Tensor4, P, P, P, P, P, P, P]),

@@ -21,6 +21,7 @@ struct ConvArgs {
     Geo o;               // geometry of `out` for dgrad (dx)
     long long p_chunk;   // wgrad: pixels per z-slice
     int hdec = 1;        // conv_tc_fwd: 2 = store / count only the even rows of the (stride-1) result
+    int accum = 0;       // dgrad: add to `out` instead of overwriting it
     int fold = 0;        // "folded split" first layer (conv_s2d.cu): x_h2 is ONE plane of 64-half rows [hi|lo per pixel],
                          // cin == 64; forward: w_h2 planes are [w_hi | 0] and [w_lo | w_hi]; wgrad: w_h2 (= dy) rows are
                          // [64 hi | 64 lo] per output pixel, cout / 64 pixels per row

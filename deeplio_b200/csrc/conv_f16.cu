@@ -194,7 +194,7 @@ extern "C" int dlio_absmax(const float *x, long long n, float *bound, void *stre
 
 extern "C" int dlio_conv2d_bwd_data_f16(dlio_tensor4 dy, const void *dy_h2, const float *dy_bound, const void *wt_h2,
                                         const float *w_bound, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr,
-                                        void *stream) {
+                                        int accumulate, void *stream) {
     int rc = same_conv_check(dx, dy, cv, "conv2d_bwd_data_f16");
     if (rc) return rc;
     DLIO_CHECK_ARG(dy_h2 && dy_bound && wt_h2 && w_bound && dx_ptr, "conv2d_bwd_data_f16: null pointer");
@@ -205,7 +205,7 @@ extern "C" int dlio_conv2d_bwd_data_f16(dlio_tensor4 dy, const void *dy_h2, cons
     t.cin = dy.c; t.cout = dx.c; t.act = 0;
     t.x_hi = t.x_lo = t.w_hi = t.w_lo = nullptr;
     t.x_h2 = (const __half *)dy_h2; t.w_h2 = (const __half *)wt_h2; t.x_bound = dy_bound; t.w_bound = w_bound;
-    t.bias = nullptr; t.out = dx_ptr; t.stats = nullptr; t.p_chunk = 0;
+    t.bias = nullptr; t.out = dx_ptr; t.stats = nullptr; t.p_chunk = 0; t.accum = accumulate ? 1 : 0;
     rc = conv_tc_fwd(t, DLIO_PROF_CONV_DGRAD_TC, (cudaStream_t)stream);
     if (rc < 0) return rc;
     DLIO_CHECK_ARG(rc == 1, "conv2d_bwd_data_f16: shape not supported (cout %d %% 64, cin %d %% 16, dy pads %d,%d)", dy.c,

@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(ConvArgs a) {
             long long t = m / a.x.w;
             int hh = (int)(t % a.x.h);
             int n = (int)(t / a.x.h);
-            st4(a.out + a.o.off(n, hh, ww) + ci, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            float *op = a.out + a.o.off(n, hh, ww) + ci;
+            float4 o4 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (a.accum) o4 = add4(o4, ld4(op));
+            st4(op, o4);
         }
     }
 }
@@ -377,7 +380,7 @@ extern "C" int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x
 
 extern "C" int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const float *dy_lo, const float *w_hi,
                                     const float *w_lo, const float *wt_hi, const float *wt_lo, dlio_conv cv,
-                                    dlio_tensor4 dx, float *dx_ptr, void *stream) {
+                                    dlio_tensor4 dx, float *dx_ptr, int accumulate, void *stream) {
     int rc = check_conv(dx, dy, cv);
     if (rc) return rc;
     DLIO_CHECK_ARG(dy_hi && w_hi && dx_ptr, "conv_bwd_data: null pointer");
@@ -389,7 +392,7 @@ extern "C" int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const f
         t.kh = cv.kh; t.kw = cv.kw; t.sh = cv.sh; t.sw = cv.sw; t.ph = cv.kh - 1 - cv.ph; t.pw = cv.kw - 1 - cv.pw;
         t.cin = dy.c; t.cout = dx.c; t.act = 0;
         t.x_hi = dy_hi; t.x_lo = dy_lo; t.w_hi = wt_hi; t.w_lo = wt_lo; t.bias = nullptr;
-        t.out = dx_ptr; t.stats = nullptr; t.p_chunk = 0;
+        t.out = dx_ptr; t.stats = nullptr; t.p_chunk = 0; t.accum = accumulate ? 1 : 0;
         rc = conv_tc_fwd(t, DLIO_PROF_CONV_DGRAD_TC, st);
         if (rc != 0) return rc < 0 ? rc : DLIO_OK;
     }
@@ -399,9 +402,9 @@ extern "C" int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const f
     a.kh = cv.kh; a.kw = cv.kw; a.sh = cv.sh; a.sw = cv.sw; a.ph = cv.ph; a.pw = cv.pw;
     a.cin = dx.c; a.cout = dy.c; a.act = 0;
     a.x_hi = dy_hi; a.x_lo = dy_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = nullptr;
-    a.out = dx_ptr; a.stats = nullptr; a.p_chunk = 0;
+    a.out = dx_ptr; a.stats = nullptr; a.p_chunk = 0; a.accum = accumulate ? 1 : 0;
     ProfScope prof(DLIO_PROF_CONV_DGRAD_SIMT, st);
-    if (dx.ph > 0 || dx.pw > 0) DLIO_CUDA(cudaMemsetAsync(dx_ptr, 0, a.o.numel() * sizeof(float), st));
+    if ((dx.ph > 0 || dx.pw > 0) && !accumulate) DLIO_CUDA(cudaMemsetAsync(dx_ptr, 0, a.o.numel() * sizeof(float), st));
     long long M = (long long)dx.n * dx.h * dx.w;
     dim3 grid(ceil_div(M, BM), ceil_div(dx.c, BN));
     conv_dgrad_kernel<<<grid, NT, 0, st>>>(a);

@@ -60,6 +60,7 @@ struct TcArgs {
     const float *xb, *wb;   // f16: device bounds of the two operands (-> power-of-two scales)
     int single;        // A/B switch "bwd_single_pass": hi*hi products only (the correction accumulator is initialised
                        // by one lo*hi MMA per tile and otherwise left alone) -- fp16 / TF32 accuracy at 1/3 of the MMAs
+    int accum;         // dgrad: add the result to what `out` holds (a second gradient contribution, no temporary)
     int fold;          // "folded split" (first layer, conv_s2d.cu): every 128-byte row of x holds hi AND lo halves of
                        // 32 channels, the weight planes are [w_hi | 0] and [w_lo | w_hi]: no x_lo plane, two products
 };
@@ -445,7 +446,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             if (j < ncol)
-                                st4(a.out + obase + c0 + j, make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]));
+                            {
+                                float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
+                                if (a.accum) o4 = add4(o4, ld4(a.out + obase + c0 + j));
+                                st4(a.out + obase + c0 + j, o4);
+                            }
                     }
                     if (a.stats) {
                         // per-column sums over the warp's 32 rows: butterfly transpose-reduce, lane l ends with column l
@@ -769,7 +774,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             if (j < ncol)
-                                st4(a.out + obase + c0 + j, make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]));
+                            {
+                                float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
+                                if (a.accum) o4 = add4(o4, ld4(a.out + obase + c0 + j));
+                                st4(a.out + obase + c0 + j, o4);
+                            }
                     }
                     if (a.stats) {
                         float sq[32];
@@ -888,6 +897,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     t.f16 = f16 ? 1 : 0; t.xb = a.x_bound; t.wb = a.w_bound;
     t.hdec = a.hdec;
     t.fold = a.fold;
+    t.accum = a.accum;
     t.single = (prof_kind == DLIO_PROF_CONV_DGRAD_TC && g_bwd_single) ? 1 : 0;
     t.x = a.x; t.o = a.o;
     t.kh = a.kh; t.kw = a.kw; t.ph = a.ph; t.pw = a.pw;
@@ -926,7 +936,7 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
         DLIO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 1024));
     }
     ProfScope prof(prof_kind, st);
-    if (a.o.ph > 0 || a.o.pw > 0) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
+    if ((a.o.ph > 0 || a.o.pw > 0) && !a.accum) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
     if (f16 && bn == 128 && conv_cg2_enabled()) {
         // CTA pairs (conv_tc2_kernel): 256-row tiles, each CTA stages half of the weight tile
         CUtensorMap mwh2, mwl2;

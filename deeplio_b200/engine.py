@@ -224,11 +224,15 @@ class Run:
         self.agrad[id(act)] = g
         return g, False
 
-    def add_grad(self, act, write):
-        """``write(buf)`` overwrites ``buf`` with a full gradient contribution for ``act``."""
+    def add_grad(self, act, write, accumulates=False):
+        """``write(buf)`` overwrites ``buf`` with a full gradient contribution for ``act``.  ``accumulates``: the
+        writer takes a second argument, ``write(buf, 1)`` ADDS its contribution to ``buf`` (the dgrad kernels'
+        epilogue), so a second contribution needs neither a temporary nor an add pass."""
         g, existed = self.grad_slot(act)
         if not existed:
             write(g)
+        elif accumulates:
+            write(g, 1)
         else:
             tmp = torch.empty_like(g)
             write(tmp)
@@ -514,9 +518,9 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             if dg == "f16":
                 wt_h2 = run.empty(2 * cin, 2, kh * kw2 * cout, dtype=torch.float16)
                 L.weight_pack_pair_f16(ptr(w), cout, cin, kh, kw, 1, 0, ptr(w_bound), ptr(wt_h2), st)
-                run.add_grad(x, lambda buf: L.conv2d_bwd_data_f16(
+                run.add_grad(x, lambda buf, acc=0: L.conv2d_bwd_data_f16(
                     dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2), ptr(w_bound), cv2s1,
-                    L.Tensor4(n, x.h, x.w // 2, 2 * cin, 0, 0), ptr(buf), st))
+                    L.Tensor4(n, x.h, x.w // 2, 2 * cin, 0, 0), ptr(buf), acc, st), accumulates=True)
             return
         if s2d_f16:
             # dy planes per output pixel [64 hi | 64 lo]; R output pixels per row of the space-to-depth view
@@ -543,8 +547,9 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             wt_h2 = run.empty(cin_pad, 2, kh * kw * cout, dtype=torch.float16)
             L.weight_pack_f16(ptr(w), cout, cin, kh, kw, cin_pad, 1, 0 if w_bound is not None else 1, ptr(wb),
                               ptr(wt_h2), st)
-            run.add_grad(x, lambda buf: L.conv2d_bwd_data_f16(dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2), ptr(wb),
-                                                              cv, x.t4_unpadded, ptr(buf), st))
+            run.add_grad(x, lambda buf, acc=0: L.conv2d_bwd_data_f16(dya.t4, ptr(dya.h2), ptr(dya.bound), ptr(wt_h2),
+                                                                     ptr(wb), cv, x.t4_unpadded, ptr(buf), acc, st),
+                         accumulates=True)
         elif dg is not None:
             wo_, wl_ = w_ohwi, w_lo
             if wo_ is None:
@@ -554,8 +559,9 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             if dg == "tf32":
                 wt_hi, wt_lo = torch.empty_like(wo_), torch.empty_like(wo_)
                 L.weight_flip_transpose(ptr(wo_), cout, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
-            run.add_grad(x, lambda buf: L.conv2d_bwd_data(dya.t4, ptr(dya.t), ptr(dya.lo), ptr(wo_), ptr(wl_),
-                                                          ptr(wt_hi), ptr(wt_lo), cv, x.t4_unpadded, ptr(buf), st))
+            run.add_grad(x, lambda buf, acc=0: L.conv2d_bwd_data(dya.t4, ptr(dya.t), ptr(dya.lo), ptr(wo_), ptr(wl_),
+                                                                 ptr(wt_hi), ptr(wt_lo), cv, x.t4_unpadded, ptr(buf),
+                                                                 acc, st), accumulates=True)
 
     run.tape.append(bwd)
     run.keep.append((x, y, out, res))
@@ -614,6 +620,13 @@ def max_pool(run, x, stride, ceil=False, out_pad=(0, 0), name=None):
 
     def bwd():
         dout = run.agrad.pop(id(out))
+        if FUSED_POOL_BWD and stride[0] in (1, 2) and stride[1] in (1, 2) and x.c % 16 == 0 and x.t is not None:
+            # the un-pooling of dlio_bn_pool_bwd_apply with an identity BatchNorm (no statistics, scale 1): rows of dout
+            # and of the arg-max bytes staged by bulk copies instead of the generic gather (233 -> ~90 us per PointSeg pool)
+            run.add_grad(x, lambda buf: L.bn_pool_bwd_apply(
+                x.t4, ptr(x.t), bp, out.t4_unpadded, ptr(dout), ptr(idx), None, 1, None, None, None, 0, 0,
+                x.t4_unpadded, ptr(buf), None, None, None, None, None, None, stream()))
+            return
         run.add_grad(x, lambda buf: L.bn_act_pool_bwd_reduce(
             x.t4, ptr(x.t), None, None, None, None, x.t4, None, bp, L.GRAD_POOL, out.t4_unpadded, ptr(dout), 0,
             ptr(idx), ptr(buf), None, 0, 0, None, 0, stream()))

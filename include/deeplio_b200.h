@@ -135,9 +135,11 @@ int dlio_conv2d_fwd(dlio_tensor4 x, const float *x_hi, const float *x_lo,
  * wt_hi / wt_lo (optional): the flipped / transposed weights of dlio_weight_flip_transpose as TF32 split
  * planes; when they and dy_lo are given, the stride is 1, dy is stored with pads >= (kh-1-ph, kw-1-pw) and
  * cout % 32 == 0, cin % 16 == 0, the dgrad runs on the tcgen05 kernel as a convolution of dy with wt. */
+/* accumulate != 0: dx += the gradient (a tensor with several consumers collects its contributions without a temporary
+ * and an add pass); 0: dx is overwritten. */
 int dlio_conv2d_bwd_data(dlio_tensor4 dy, const float *dy_hi, const float *dy_lo,
                          const float *w_hi, const float *w_lo, const float *wt_hi, const float *wt_lo,
-                         dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, void *stream);
+                         dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, int accumulate, void *stream);
 
 /* wgrad: dw[cout][kh][kw][cin] = sum_{n,h,w} dy * x (overwrites dw). */
 int dlio_conv2d_bwd_weight(dlio_tensor4 x, const float *x_hi, const float *x_lo,
@@ -187,7 +189,8 @@ int dlio_conv2d_fwd_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, 
                         const float *w_bound, const float *bias, dlio_conv cv, int act, dlio_tensor4 y,
                         float *y_ptr, double *stats, void *stream);
 int dlio_conv2d_bwd_data_f16(dlio_tensor4 dy, const void *dy_h2, const float *dy_bound, const void *wt_h2,
-                             const float *w_bound, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, void *stream);
+                             const float *w_bound, dlio_conv cv, dlio_tensor4 dx, float *dx_ptr, int accumulate,
+                             void *stream);
 int dlio_conv2d_bwd_weight_f16(dlio_tensor4 x, const void *x_h2, const float *x_bound, dlio_tensor4 dy,
                                const void *dy_h2, const float *dy_bound, dlio_conv cv, float *dw, void *stream);
 /* fp32 [rows][c] -> packed split plane, computing the bound (max |v|) first; test / staging helper */

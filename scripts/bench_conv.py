@@ -62,7 +62,7 @@ for name, cin, cout, h, w, kh, kw in LAYERS:
         fwd = lambda: L.conv2d_fwd_f16(xt4, xh.data_ptr(), xb.data_ptr(), wh.data_ptr(), wb.data_ptr(), None, cv, 1, yt4,
                                        y.data_ptr(), stats.data_ptr(), st)
         dgrad = lambda: L.conv2d_bwd_data_f16(dyt4, dyh.data_ptr(), dyb.data_ptr(), wth.data_ptr(), wb.data_ptr(), cv, dxt4,
-                                              dx.data_ptr(), st)
+                                              dx.data_ptr(), 0, st)
         wgrad = lambda: L.conv2d_bwd_weight_f16(xt4, xh.data_ptr(), xb.data_ptr(), dyt4, dyh.data_ptr(), dyb.data_ptr(), cv,
                                                 dw.data_ptr(), st)
     else:
@@ -83,7 +83,7 @@ for name, cin, cout, h, w, kh, kw in LAYERS:
         fwd = lambda: L.conv2d_fwd(xt4, xhi.data_ptr(), xlo.data_ptr(), whi.data_ptr(), wlo.data_ptr(), None, cv, 1, yt4,
                                    y.data_ptr(), stats.data_ptr(), st)
         dgrad = lambda: L.conv2d_bwd_data(dyt4, dyhi.data_ptr(), dylo.data_ptr(), whi.data_ptr(), wlo.data_ptr(),
-                                          wthi.data_ptr(), wtlo.data_ptr(), cv, dxt4, dx.data_ptr(), st)
+                                          wthi.data_ptr(), wtlo.data_ptr(), cv, dxt4, dx.data_ptr(), 0, st)
         wgrad = lambda: L.conv2d_bwd_weight(xt4, xhi.data_ptr(), xlo.data_ptr(), dyt4, dyhi.data_ptr(), dylo.data_ptr(), cv,
                                             dw.data_ptr(), st)
     flop = 2.0 * N * h * w * cout * cin * kh * kw

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, GPU call 10 (1 GPU): dgrad accumulate, max-pool backward through the bulk-copy un-pooling kernel, glue test;
+# PointSeg and headline bench
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_diag.jsonl
+( time timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider ) > gpurun_out/c10_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/c10_pytest.log
+timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload cfg2_pointseg_lstm_b32 > gpurun_out/c10_bench_pointseg.json 2> gpurun_out/c10_bench_pointseg.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c10_bench.json 2> gpurun_out/c10_bench.err
+echo done

@@ -89,8 +89,12 @@ def test_conv_fwd_dgrad_wgrad(case):
     dyd = to_padded_nhwc(dy, 0, 0)
     dx = torch.empty(n, h, w, cin_pad, device=DEV)
     L.conv2d_bwd_data(yt4, dyd.data_ptr(), None, w_ohwi.data_ptr(), None, None, None, cv,
-                      L.Tensor4(n, h, w, cin_pad, 0, 0), dx.data_ptr(), _st())
+                      L.Tensor4(n, h, w, cin_pad, 0, 0), dx.data_ptr(), 0, _st())
     assert relerr(from_nhwc(dx)[:, :cin], xr.grad) < 3e-6
+    # accumulate: dx += the gradient
+    L.conv2d_bwd_data(yt4, dyd.data_ptr(), None, w_ohwi.data_ptr(), None, None, None, cv,
+                      L.Tensor4(n, h, w, cin_pad, 0, 0), dx.data_ptr(), 1, _st())
+    assert relerr(from_nhwc(dx)[:, :cin], 2 * xr.grad) < 3e-6
     dw_ohwi = torch.empty(cout, kh, kw, cin_pad, device=DEV)
     L.conv2d_bwd_weight(xt4, xp.data_ptr(), None, yt4, dyd.data_ptr(), None, cv, dw_ohwi.data_ptr(), _st())
     dw = torch.empty(cout, cin, kh, kw, device=DEV)
@@ -193,8 +197,12 @@ def test_conv_f16_split_fwd_dgrad_wgrad(case):
     dx = torch.full((n, h, w, cin), float("nan"), device=DEV)
     dyt4 = L.Tensor4(n, h, w, cout, tph, tpw)
     L.conv2d_bwd_data_f16(dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), wt_h2.data_ptr(), w_b.data_ptr(), cv,
-                          L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), _st())
+                          L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), 0, _st())
     assert relerr(from_nhwc(dx).double(), xr.grad) < 1e-5
+    # accumulate: dx += the gradient (what a tensor with two consumers gets from its second one)
+    L.conv2d_bwd_data_f16(dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), wt_h2.data_ptr(), w_b.data_ptr(), cv,
+                          L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), 1, _st())
+    assert relerr(from_nhwc(dx).double(), 2 * xr.grad) < 1e-5
 
     # wgrad: x and dy on the same padded grid, both read pixel-major (MN-major fp16 operands, 128-byte swizzle)
     if cout % 64 == 0:      # Cout % 128 == 64: the upper half of the last 128-channel tile is TMA zero fill
@@ -280,7 +288,7 @@ def test_conv_tcgen05_fwd_and_dgrad(case):
     L.profile_enable(1)
     L.conv2d_bwd_data(L.Tensor4(n, h, w, cout, kh - 1 - ph, kw - 1 - pw), dy_hi.data_ptr(), dy_lo.data_ptr(),
                       w_hi.data_ptr(), w_lo.data_ptr(), wt_hi.data_ptr(), wt_lo.data_ptr(), cv,
-                      L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), _st())
+                      L.Tensor4(n, h, w, cin, 0, 0), dx.data_ptr(), 0, _st())
     torch.cuda.synchronize()
     prof = L.profile_read()
     L.profile_enable(0)
@@ -390,7 +398,7 @@ def test_conv_pair_view_strided_fwd_dgrad_wgrad(case):
     L.weight_pack_pair_f16(wd.data_ptr(), cout, cin, kh, kw, 1, 0, w_b.data_ptr(), wt_h2.data_ptr(), _st())
     dx = torch.full((n, h, w, cin), float("nan"), device=DEV)
     L.conv2d_bwd_data_f16(dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), wt_h2.data_ptr(), w_b.data_ptr(), cv1,
-                          L.Tensor4(n, h, w // 2, 2 * cin, 0, 0), dx.data_ptr(), _st())
+                          L.Tensor4(n, h, w // 2, 2 * cin, 0, 0), dx.data_ptr(), 0, _st())
     assert relerr(from_nhwc(dx).double(), xr.grad) < 1e-5
     dw2 = torch.full((cout, kh, kw2, 2 * cin), float("nan"), device=DEV)
     L.conv2d_bwd_weight_f16(x2t4, x_h2.data_ptr(), x_b.data_ptr(), dyt4, dy_h2.data_ptr(), dy_b.data_ptr(), cv1,
