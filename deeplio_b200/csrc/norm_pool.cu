@@ -36,6 +36,7 @@ static int ew_block_cap() {
 extern int g_conv_cg2;      // conv_tc.cu
 extern int g_nvtx;          // lib.cu
 extern int g_bwd_single;    // conv_tc.cu
+int g_apply_rows = 1;       // option "apply_rows": row-structured non-pooled BN-apply pass (0: the generic kernel)
 static int g_pool_tma = -1;
 static bool pool_tma_enabled() {
     if (g_pool_tma < 0) {
@@ -359,6 +360,66 @@ __global__ void __launch_bounds__(256, 5) bn_pool3_fwd_kernel(BnPool a) {
             if (irow) *reinterpret_cast<unsigned *>(irow + (size_t)wo * C) = bi;
             if (a.ymax) st4(a.ymax + ((size_t)(n * a.out.h + ho) * a.out.w + wo) * C + c, yb);
             bnpool_store(a, pix0 + x, c, best, s16);
+        }
+    }
+}
+
+// Row-structured variant of bn_act_pool_fwd_kernel for the layers WITHOUT pooling (every layer of FlowNet / ResNet,
+// every Fire convolution of PointSeg, Simple-1 conv3 / 5): a block walks whole padded output rows, a thread keeps its
+// channel group and strides along the row with four pixels of loads in flight -- no per-pixel divisions, scale / shift
+// loaded once.  The generic kernel ran these at 2.7 - 3.2 TB/s with 60 % of the issue slots busy on index arithmetic.
+__global__ void __launch_bounds__(256, 3) bn_apply_rows_kernel(BnPool a) {
+    const int cg = a.cg, C = cg * 4;
+    const int c = (int)(threadIdx.x % cg) * 4;
+    const int wl = (int)(threadIdx.x / cg), WL = (int)(blockDim.x / cg);
+    const float s16 = a.out_h2 ? f16_scale_from_bound(*a.out_bound) : 1.f;
+    float4 sc = f4(1.f), sf = f4(0.f);
+    if (a.scale) {
+        sc = ld4(a.scale + c);
+        sf = ld4(a.shift + c);
+    }
+    const int rows = a.out.n * a.out.hp, segs = a.segs, items = rows * segs;
+    const int seg_w = (a.out.wp + segs - 1) / segs;
+    constexpr int U = 4;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int row = item / segs, seg = item - row * segs;
+        const int x_begin = seg * seg_w, x_end = min(a.out.wp, x_begin + seg_w);
+        const int n = row / a.out.hp, ho = row - n * a.out.hp - a.out.ph;
+        const unsigned pix0 = (unsigned)row * (unsigned)a.out.wp;
+        if (ho < 0 || ho >= a.out.h) {
+            for (int x = x_begin + wl; x < x_end; x += WL) {
+                bnpool_store(a, pix0 + x, c, f4(0.f), 1.f);
+                if (a.zero_tail) bnpool_zero_tail(a, pix0 + x, c);
+            }
+            continue;
+        }
+        const float *yrow = a.yp + a.y.off(n, ho, 0) + c;
+        const float *rrow = a.res_mode ? a.resp + a.res.off(n, ho, 0) + a.c_off + c : nullptr;
+        const int rc = a.res.c;
+        for (int x0 = x_begin + wl; x0 < x_end; x0 += U * WL) {
+            float4 v[U], r[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = x0 + u * WL, wo = x - a.out.pw;
+                ok[u] = x < x_end && wo >= 0 && wo < a.out.w;
+                v[u] = ok[u] ? ld4(yrow + (size_t)wo * C) : f4(0.f);
+                r[u] = (ok[u] && rrow) ? ld4(rrow + (size_t)wo * rc) : f4(0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = x0 + u * WL;
+                if (x >= x_end) break;
+                float4 t = f4(0.f);
+                if (ok[u]) {
+                    t = a.scale ? fma4(sc, v[u], sf) : v[u];
+                    if (a.res_mode == 1) t = add4(t, r[u]);
+                    if (a.relu) t = relu4(t);
+                    if (a.res_mode == 2) t = add4(t, r[u]);
+                }
+                bnpool_store(a, pix0 + x, c, t, ok[u] ? s16 : 1.f);
+                if (a.zero_tail) bnpool_zero_tail(a, pix0 + x, c);
+            }
         }
     }
 }
@@ -866,9 +927,10 @@ struct PoolRowMax {
 // blockDim = cg * WS (channel groups x output columns of a segment).  Shared memory: RING_SLOTS input-row segments
 // of ((WS - 1) * SW + 3) columns x C floats.  Same arithmetic and tie-breaking as bn_pool3_fwd_kernel.
 template <int SH, int SW, bool RELU>
-__global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS, int nseg, long long units_per_cta) {
+__global__ void __launch_bounds__(256, 3) bn_pool3_fwd_tma_kernel(BnPool a, int WS, int nseg, long long units_per_cta) {
     // an output row keeps 3 input rows alive and consumes SH new ones: 3 + 3 rows of look-ahead (SH = 1), 3 + 5 (SH = 2)
-    constexpr int RING_SLOTS = SH == 1 ? 6 : 8;
+    constexpr int RING_SLOTS = 6;     // two output rows' worth of input rows; three CTAs per SM fit (ncu: these passes
+                                      // are issue-bound, 16 resident warps left 40 % of the issue slots empty)
     extern __shared__ __align__(128) unsigned char ring_raw[];
     __shared__ __align__(8) unsigned long long bars[RING_SLOTS];
     const int cg = a.cg, C = cg * 4;
@@ -1022,13 +1084,18 @@ __global__ void __launch_bounds__(256) bn_pool3_fwd_tma_kernel(BnPool a, int WS,
 // of bn_bwd_apply_kernel), rows staged by bulk copies: the conv output y (each element read once), and the pooled-side
 // rows of dout and of the arg-max bytes that the 2 - 3 input rows and 1.5 - 3 input columns of a window share.
 // blockDim = cg * WT; a thread owns a channel group and U input columns WT apart.  dout.c == C, c_off == 0.
-constexpr int APPLY_YSLOTS = 4, APPLY_PSLOTS = 6, APPLY_U = 2;
+constexpr int APPLY_YSLOTS_MAX = 4, APPLY_PSLOTS_MAX = 6, APPLY_U = 2;
+// ring depths: y rows / pooled rows in flight per CTA.  H stride 2 touches at most two pooled rows per input row, so
+// shallower rings keep three CTAs per SM resident at C = 512 too
+__host__ __device__ constexpr int apply_yslots(int sh) { return sh == 1 ? 4 : 3; }
+__host__ __device__ constexpr int apply_pslots(int sh) { return sh == 1 ? 6 : 4; }
 template <int SH, int SW>
 __global__ void __launch_bounds__(256, 3) bn_pool_bwd_apply_tma_kernel(BnApply a, int WT, int nseg, long long units_per_cta) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
-    __shared__ __align__(8) unsigned long long bars[APPLY_YSLOTS + APPLY_PSLOTS];
+    __shared__ __align__(8) unsigned long long bars[APPLY_YSLOTS_MAX + APPLY_PSLOTS_MAX];
     __shared__ float red[MAX_C];
     __shared__ float wred[32];
+    constexpr int APPLY_YSLOTS = apply_yslots(SH), APPLY_PSLOTS = apply_pslots(SH);
     const int cg = a.cg, C = cg * 4;
     constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;
     const int WSI = APPLY_U * WT;                                   // input columns per segment
@@ -1448,6 +1515,7 @@ extern "C" int dlio_set_option(const char *name, int value) {
     else if (!strcmp(name, "conv_cg2")) dlio::g_conv_cg2 = value ? 1 : 0;
     else if (!strcmp(name, "nvtx")) dlio::g_nvtx = value ? 1 : 0;
     else if (!strcmp(name, "bwd_single_pass")) dlio::g_bwd_single = value ? 1 : 0;
+    else if (!strcmp(name, "apply_rows")) dlio::g_apply_rows = value ? 1 : 0;
     else {
         set_error("set_option: unknown option %s", name);
         return DLIO_ERR_INVALID;
@@ -1549,7 +1617,7 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
         const int WS = a.cg >= 256 ? 1 : 256 / a.cg;
         const int nseg = (a.out.w + WS - 1) / WS;
         const int wcols = (WS - 1) * a.sw + 3;
-        const size_t smem = (size_t)(a.sh == 1 ? 6 : 8) * wcols * y.c * sizeof(float);
+        const size_t smem = (size_t)6 * wcols * y.c * sizeof(float);
         const long long total = (long long)a.out.n * nseg * a.out.h;
 #define DLIO_POOL3_TMA(SH_, SW_)                                                                              \
     do {                                                                                                      \
@@ -1588,6 +1656,10 @@ extern "C" int dlio_bn_act_pool_fwd(dlio_tensor4 y, const float *y_ptr, const fl
         else if (a.sh == 1 && a.sw == 1) DLIO_POOL3(1, 1);
         else DLIO_POOL3(2, 1);
 #undef DLIO_POOL3
+    } else if (a.pk == 1 && (long long)a.out.n * a.out.hp * a.out.wp < (1LL << 31) && g_apply_rows) {
+        const int grid = resident_grid(bn_apply_rows_kernel, block);
+        a.segs = row_segments(a.out.n * a.out.hp, a.out.wp, block / a.cg, grid);
+        bn_apply_rows_kernel<<<grid, block, 0, st>>>(a);
     } else {
         DLIO_CHECK_ARG(!pool_ymax, "bn_act_pool_fwd: pool_ymax needs a 3x3 pool without a residual");
         bn_act_pool_fwd_kernel<<<grid_for(total, block, 16), block, 0, st>>>(a);
@@ -1711,7 +1783,8 @@ static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz
             // bulk-copy row rings (bn_pool_bwd_apply_tma_kernel): dout carries exactly this layer's channels
             const int WT = a.cg >= 256 ? 1 : 256 / a.cg, WSI = APPLY_U * WT;
             const int ocols = WSI / p->pool_sw + 2;
-            const size_t smem = (size_t)APPLY_YSLOTS * WSI * y.c * 4 + (size_t)APPLY_PSLOTS * ocols * y.c * 5;
+            const size_t smem = (size_t)apply_yslots(p->pool_sh) * WSI * y.c * 4 +
+                                (size_t)apply_pslots(p->pool_sh) * ocols * y.c * 5;
             if (pool_tma_enabled() && dout_t.c == y.c && p->c_off == 0 && y.c % 16 == 0 && (a.cg * WT) % 32 == 0 &&
                 a.cg * WT <= 256 && smem <= 200 * 1024 && a.y.w % 1 == 0 &&
                 ((((uintptr_t)y_ptr) | ((uintptr_t)dout) | ((uintptr_t)pool_idx)) & 15) == 0) {

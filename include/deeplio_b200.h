@@ -91,7 +91,8 @@ typedef enum {
  * range named dlio/<kernel class> around the launches of every entry point (default 0; environment DLIO_NVTX; the
  * Python engine adds a range per layer, e.g. encoder1.conv3, when it is on), "bwd_single_pass" 0/1 -- MEASUREMENT ONLY:
  * dgrad and wgrad issue the hi*hi product alone (plain fp16 / TF32 operand accuracy, the reference's own cudnn.allow_tf32
- * level) instead of the three products of the split scheme; default 0, the gradient parity tests fail with it on. */
+ * level) instead of the three products of the split scheme; default 0, the gradient parity tests fail with it on;
+ * "apply_rows" 0/1 -- row-structured kernel for the BN-apply passes without pooling (default 1). */
 int dlio_set_option(const char *name, int value);
 /* Caller-owned scratch of one call, in bytes -- the library never allocates device memory.  One
  * query for every entry point that takes scratch:

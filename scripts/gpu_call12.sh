@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call 12 (1 GPU): row-structured BN-apply kernel and the occupancy retune of the pooling kernels: the op
+# tests first, then the whole tier, then benches (headline, PointSeg, ResNet, FlowNet)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_diag.jsonl
+( time timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q --maxfail=20 -p no:cacheprovider ) > gpurun_out/c12_ops.log 2>&1
+echo "ops rc=$?" >> gpurun_out/c12_ops.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c12_bench.json 2> gpurun_out/c12_bench.err
+for wl in cfg2_pointseg_lstm_b32 cfg3_resnet_gru_b64 cfg4_flownet_lstm_t50_b16; do
+  timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload $wl > gpurun_out/c12_bench_$wl.json 2> gpurun_out/c12_bench_$wl.err
+done
+( time timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider ) > gpurun_out/c12_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/c12_pytest.log
+echo done

@@ -12,8 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "deeplio_b200", "libdeeplio_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 PAT = collections.OrderedDict([
-    ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA\b"), ("UTCBAR (tcgen05.commit)", r"\bUTCBAR\b"), ("LDTM (tcgen05.ld)", r"\bLDTM\b"),
-    ("UTMALDG (TMA load)", r"\bUTMALDG\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"), ("UCGABAR (cluster barrier)", r"\bUCGABAR"),
+    ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA\b"), ("of which .2CTA (cta_group::2)", r"\bUTC[A-Z]*MMA\.2CTA"),
+    ("UTCBAR (tcgen05.commit)", r"\bUTCBAR\b"), ("LDTM (tcgen05.ld)", r"\bLDTM\b"),
+    ("UTMALDG (TMA load)", r"\bUTMALDG\b"), ("UBLKCP (cp.async.bulk)", r"\bUBLKCP\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"),
+    ("UCGABAR (cluster barrier)", r"\bUCGABAR"),
     ("MEMBAR.ALL.GPU", r"\bMEMBAR\.ALL\.GPU"), ("REDG (global reduction)", r"\bREDG\."),
     ("HMMA (legacy mma.sync)", r"\bHMMA\b"), ("FFMA", r"\bFFMA\b"),
 ])
@@ -32,7 +34,8 @@ for line in sass.splitlines():
                 counts[kern][name] += 1
 print("# SASS evidence (cuobjdump -sass deeplio_b200/libdeeplio_b200.so, sm_100a)\n")
 print("Static instruction counts per kernel of the mnemonics `B200_PROFILING.md` names.  tcgen05 / TMA / TMEM appear in the")
-print("convolution kernels only; no kernel uses the legacy `HMMA` tensor path; the whole-sequence RNN kernels use cluster")
+print("convolution kernels only (`UTCHMMA.2CTA`, `UTMALDG.2D.2CTA`, `UTCBAR.2CTA.MULTICAST` in the CTA-pair kernels); the pooling")
+print("passes stage rows with `UBLKCP` bulk copies; no kernel uses the legacy `HMMA` tensor path; the whole-sequence RNN kernels use cluster")
 print("barriers (each release-arrive carries a `MEMBAR.ALL.GPU`: part of their ~5 us per time step, DESIGN.md section 9).")
 print("Kernels without any of these (the HBM-bound passes, dense layers, Adam) are omitted: %d kernels in the library.\n" % len(order))
 cols = list(PAT)
@@ -40,6 +43,6 @@ print("| kernel | " + " | ".join(cols) + " |")
 print("|---|" + "---:|" * len(cols))
 for k in order:
     c = counts[k]
-    if not (c["UTC*MMA (tcgen05.mma)"] or c["UTMALDG (TMA load)"] or c["UCGABAR (cluster barrier)"] or k.startswith("conv_")):
+    if not (c["UTC*MMA (tcgen05.mma)"] or c["UTMALDG (TMA load)"] or c["UCGABAR (cluster barrier)"] or c["UBLKCP (cp.async.bulk)"] or k.startswith("conv_")):
         continue
     print("| `%s` | " % k[:60] + " | ".join(str(c[n]) for n in cols) + " |")

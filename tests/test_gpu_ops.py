@@ -823,3 +823,74 @@ def test_pooled_passes_bulk_copy_rings_equal_per_thread_loads(c, h, w, n, pool, 
         assert relerr(a[k], b[k]) < 2e-5, k
     # the bias of a convolution in front of a train-mode BatchNorm has zero gradient in exact arithmetic: noise only
     assert (a["db"] - b["db"]).abs().max().item() < 1e-5 * a["dw"].abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w,c,out_c,c_off,pad,relu,res_mode,planes,zero_tail", [
+    (2, 9, 33, 64, 64, 0, (1, 1), 1, 0, "h2", 0),        # a plain conv -> BN -> ReLU layer feeding an fp16 convolution
+    (3, 7, 21, 16, 64, 0, (1, 1), 1, 0, "h2+t", 1),      # Fire squeeze: 16 channels into a 64-channel tensor, zero tail
+    (2, 5, 18, 64, 128, 64, (1, 1), 1, 2, "t+lo", 0),    # Fire expand3x3: channel offset, bypass added after the ReLU
+    (2, 6, 20, 128, 128, 0, (1, 2), 1, 1, "h2+t", 0),    # BasicBlock: residual added before the ReLU
+    (1, 64, 513, 128, 128, 0, (1, 1), 0, 0, "h2", 0),    # a real Simple-1 conv3 output (no ReLU after the BN)
+    (2, 4, 10, 48, 64, 0, (0, 0), 1, 0, "t", 1),         # no spatial pads, 48 -> 64 channels
+])
+def test_row_structured_bn_apply_equals_the_generic_kernel(n, h, w, c, out_c, c_off, pad, relu, res_mode, planes,
+                                                           zero_tail):
+    """dlio_bn_act_pool_fwd without pooling: the row-structured kernel (option "apply_rows", the default) writes the
+    same bits as the generic per-pixel kernel -- fp32 plane, TF32 lo plane, packed fp16 planes, spatial pads, zero
+    tail -- and both equal scale * y + shift (+ residual, ReLU) in torch."""
+    L = _lib()
+    g = torch.Generator().manual_seed(n * 100 + c + w)
+    y = torch.randn(n, c, h, w, generator=g)
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    res = torch.randn(n, out_c, h, w, generator=g) if res_mode else None
+    ref = y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
+    if res_mode == 1:
+        ref = ref + res[:, c_off:c_off + c]
+    if relu:
+        ref = F.relu(ref)
+    if res_mode == 2:
+        ref = ref + res[:, c_off:c_off + c]
+    yd, sd, fd = to_padded_nhwc(y, 0, 0), scale.to(DEV), shift.to(DEV)
+    rd = to_padded_nhwc(res, 0, 0) if res_mode else None
+    bound = torch.tensor([ref.abs().max().item() * 1.01], device=DEV)
+    ph, pw = pad
+    outs = []
+    for rows in (0, 1):
+        L.set_option(b"apply_rows", rows)
+        try:
+            shape = (n, h + 2 * ph, w + 2 * pw, out_c)
+            t = torch.full(shape, float("nan"), device=DEV) if "t" in planes else None
+            lo = torch.full(shape, float("nan"), device=DEV) if "lo" in planes else None
+            h2 = torch.full(shape[:3] + (2, out_c), float("nan"), dtype=torch.float16, device=DEV) if "h2" in planes else None
+            bp = L.BnPool(relu, res_mode, 1, 1, 1, c_off, 1, zero_tail)
+            L.bn_act_pool_fwd(L.Tensor4(n, h, w, c, 0, 0), yd.data_ptr(), sd.data_ptr(), fd.data_ptr(),
+                              L.Tensor4(n, h, w, out_c, 0, 0), rd.data_ptr() if rd is not None else None, bp,
+                              L.Tensor4(n, h, w, out_c, ph, pw), t.data_ptr() if t is not None else None,
+                              lo.data_ptr() if lo is not None else None, h2.data_ptr() if h2 is not None else None,
+                              bound.data_ptr() if h2 is not None else None, None, None, _st())
+            torch.cuda.synchronize()
+        finally:
+            L.set_option(b"apply_rows", 1)
+        outs.append((t, lo, h2))
+    written = slice(c_off, out_c if zero_tail else c_off + c)
+    for a, b in zip(*outs):
+        if a is not None:
+            av, bv = (a[..., written], b[..., written]) if a.dim() == 4 else (a[..., written], b[..., written])
+            assert torch.equal(av.view(torch.int32 if av.dtype == torch.float32 else torch.int16),
+                               bv.view(torch.int32 if bv.dtype == torch.float32 else torch.int16))
+    t, lo, h2 = outs[1]
+    if t is not None:
+        got = from_nhwc(t[:, ph:ph + h, pw:pw + w, c_off:c_off + c])
+        assert relerr(got, ref) < 1e-6
+        if zero_tail:
+            assert (t[..., c:] == 0).all()
+        if ph or pw:
+            border = t.clone()
+            border[:, ph:ph + h, pw:pw + w] = 0
+            assert (border[..., written] == 0).all()
+    if h2 is not None:
+        s = 2.0 ** (14 - torch.tensor(bound.item()).frexp().exponent.item())
+        back = (h2[:, ph:ph + h, pw:pw + w, 0, c_off:c_off + c].double() + h2[:, ph:ph + h, pw:pw + w, 1, c_off:c_off + c].double() / 2048.0) / s
+        assert relerr(from_nhwc(back), ref.double()) < 1e-6
+        if zero_tail:
+            assert (h2[..., c:] == 0).all()
