@@ -548,6 +548,83 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_reduce_kernel(BnBwd a) {
     }
 }
 
+// Backward pass 1 without pooling on flat tensors (y and dout unpadded, no pre-activation residual: every Fire
+// convolution of PointSeg, the plain layers of FlowNet, Simple-1 conv3 / 5 / 7): pixel p of every tensor is at p * stride,
+// so there is no index arithmetic at all, and four pixels of loads are in flight per thread (the generic kernel issues
+// one pixel per iteration behind two divisions: 2.7 - 3.1 TB/s at 35 - 44 % of the issue slots).
+__global__ void __launch_bounds__(256) bn_bwd_reduce_flat_kernel(BnBwd a) {
+    __shared__ float red[2 * MAX_C];
+    const int C = a.cg * 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int c = (int)(threadIdx.x % a.cg) * 4;
+    float4 sc = f4(1.f), sf = f4(0.f), mu = f4(0.f), is = f4(1.f);
+    if (a.scale) {
+        sc = ld4(a.scale + c);
+        sf = ld4(a.shift + c);
+    }
+    if (a.mean) {
+        mu = ld4(a.mean + c);
+        is = ld4(a.invstd + c);
+    }
+    float4 s1 = f4(0.f), s2 = f4(0.f);
+    float amax = 0.f;
+    const unsigned npix = (unsigned)(a.y.n * a.y.h * a.y.w);
+    constexpr int U = 4;
+    const unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) / (unsigned)a.cg;
+    const unsigned step = (gridDim.x * blockDim.x) / (unsigned)a.cg;
+    const float *dbase = a.doutp + a.c_off + c;
+    const size_t dstride = (size_t)a.dout.c;
+    for (unsigned pix = p0; pix < npix; pix += U * step) {
+        float4 g[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned p = pix + u * step;
+            const bool ok = p < npix;
+            g[u] = ok ? ld4(dbase + (size_t)p * dstride) : f4(0.f);
+            y[u] = ok ? ld4(a.yp + (size_t)p * C + c) : mu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned p = pix + u * step;
+            if (p >= npix) break;
+            float4 gg = g[u];
+            if (a.res_mode == 2 && a.dres) {
+                const size_t ro = (size_t)p * a.dres_c + a.c_off + c;
+                st4(a.dres + ro, a.dres_acc ? add4(ld4(a.dres + ro), gg) : gg);
+            }
+            if (a.relu) {
+                const float4 v = a.scale ? fma4(sc, y[u], sf) : y[u];
+                if (!(v.x > 0.f)) gg.x = 0.f;
+                if (!(v.y > 0.f)) gg.y = 0.f;
+                if (!(v.z > 0.f)) gg.z = 0.f;
+                if (!(v.w > 0.f)) gg.w = 0.f;
+            }
+            if (a.dz) st4(a.dz + (size_t)p * C + c, gg);
+            if (a.sums) {
+                const float4 yh = make_float4((y[u].x - mu.x) * is.x, (y[u].y - mu.y) * is.y, (y[u].z - mu.z) * is.z,
+                                              (y[u].w - mu.w) * is.w);
+                s1 = add4(s1, gg);
+                s2 = fma4(gg, yh, s2);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(gg.x), fabsf(gg.y)), fmaxf(fabsf(gg.z), fabsf(gg.w))));
+            }
+        }
+    }
+    if (a.sums && a.want_absmax) {
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0)
+            atomicMax(reinterpret_cast<unsigned long long *>(a.sums + 2 * C), (unsigned long long)__double_as_longlong((double)amax));
+    }
+    if (a.sums) {
+        atomicAdd(&red[c + 0], s1.x); atomicAdd(&red[c + 1], s1.y);
+        atomicAdd(&red[c + 2], s1.z); atomicAdd(&red[c + 3], s1.w);
+        atomicAdd(&red[C + c + 0], s2.x); atomicAdd(&red[C + c + 1], s2.y);
+        atomicAdd(&red[C + c + 2], s2.z); atomicAdd(&red[C + c + 3], s2.w);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + i, (double)red[i]);
+    }
+}
+
 // Row-structured variant of backward pass 1 for pooled layers without a residual (the bulk of its traffic): a block
 // walks whole input rows, so the candidate pooling-window rows, their arg-max / gradient row pointers and the
 // window-relative row offsets are computed once per row instead of per element (see bn_pool3_fwd_kernel).
@@ -1717,7 +1794,10 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
         DLIO_LAUNCH_CHECK();
         return DLIO_OK;
     }
-    if (a.pk == 1) bn_act_pool_bwd_reduce_kernel<0, 0><<<grid, block, 0, st>>>(a);
+    const bool flat = a.pk == 1 && grad_src == DLIO_GRAD_DIRECT && a.res_mode != 1 && y.ph == 0 && y.pw == 0 &&
+                      dout.ph == 0 && dout.pw == 0 && (long long)y.n * y.h * y.w < (1LL << 30) && g_apply_rows;
+    if (flat) bn_bwd_reduce_flat_kernel<<<grid_for((total + 3) / 4, block, 8), block, 0, st>>>(a);
+    else if (a.pk == 1) bn_act_pool_bwd_reduce_kernel<0, 0><<<grid, block, 0, st>>>(a);
     else if (a.sh == 1 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<1, 2><<<grid, block, 0, st>>>(a);
     else if (a.sh == 2 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<2, 2><<<grid, block, 0, st>>>(a);
     else if (a.sh == 1 && a.sw == 1) bn_act_pool_bwd_reduce_kernel<1, 1><<<grid, block, 0, st>>>(a);

@@ -894,3 +894,57 @@ def test_row_structured_bn_apply_equals_the_generic_kernel(n, h, w, c, out_c, c_
         assert relerr(from_nhwc(back), ref.double()) < 1e-6
         if zero_tail:
             assert (h2[..., c:] == 0).all()
+
+
+@pytest.mark.parametrize("n,h,w,c,dout_c,c_off,relu,res_mode,want_dz", [
+    (2, 9, 33, 64, 64, 0, 1, 0, True),         # conv -> BN -> ReLU, dz materialised
+    (1, 64, 257, 128, 128, 0, 0, 0, False),    # Simple-1 conv5 at its real size: sums only (SKIP_DZ)
+    (3, 7, 21, 64, 128, 64, 1, 2, True),       # Fire expand3x3: channel offset into the concat gradient, bypass gradient
+    (2, 5, 10, 16, 16, 0, 1, 0, True),         # Fire squeeze: 16 channels
+])
+def test_flat_bn_backward_reduce_equals_the_generic_kernel(n, h, w, c, dout_c, c_off, relu, res_mode, want_dz):
+    """Backward pass 1 of a layer without pooling (dz = ReLU-masked gradient, sums of dz and dz * yhat, max |dz|,
+    bypass gradient): the flat four-pixels-in-flight kernel against the generic per-pixel kernel and torch."""
+    L = _lib()
+    g = torch.Generator().manual_seed(n + h + w + c)
+    y = torch.randn(n, c, h, w, generator=g)
+    dout = torch.randn(n, dout_c, h, w, generator=g)
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    mean, invstd = y.mean((0, 2, 3)), 1.0 / (y.var((0, 2, 3), unbiased=False) + 1e-5).sqrt()
+    yd, dd = to_padded_nhwc(y, 0, 0), to_padded_nhwc(dout, 0, 0)
+    dev = lambda t: t.to(DEV).contiguous()
+    sd, fd, md, isd = dev(scale), dev(shift), dev(mean), dev(invstd)
+    dsl = dout[:, c_off:c_off + c]
+    v = y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
+    dz_ref = dsl * (v > 0) if relu else dsl
+    yhat = (y - mean.view(1, c, 1, 1)) * invstd.view(1, c, 1, 1)
+    outs = []
+    for rows in (0, 1):
+        L.set_option(b"apply_rows", rows)
+        try:
+            dz = torch.full((n, h, w, c), float("nan"), device=DEV) if want_dz else None
+            dres = torch.ones(n, h, w, dout_c, device=DEV) if res_mode == 2 else None
+            sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=DEV)
+            L.bn_act_pool_bwd_reduce(L.Tensor4(n, h, w, c, 0, 0), yd.data_ptr(), sd.data_ptr(), fd.data_ptr(),
+                                     md.data_ptr(), isd.data_ptr(), L.Tensor4(n, h, w, c, 0, 0), None,
+                                     L.BnPool(relu, res_mode, 1, 1, 1, c_off), L.GRAD_DIRECT,
+                                     L.Tensor4(n, h, w, dout_c, 0, 0), dd.data_ptr(), 0, None,
+                                     dz.data_ptr() if dz is not None else None,
+                                     dres.data_ptr() if dres is not None else None, dout_c, 1, sums.data_ptr(),
+                                     1 if c % 32 == 0 else 0, _st())
+            torch.cuda.synchronize()
+        finally:
+            L.set_option(b"apply_rows", 1)
+        outs.append((dz, dres, sums))
+    (dz0, dres0, s0), (dz1, dres1, s1) = outs
+    if want_dz:
+        assert torch.equal(dz0, dz1)
+        assert relerr(from_nhwc(dz1), dz_ref) < 1e-6
+    if dres1 is not None:
+        assert torch.equal(dres0, dres1)
+        assert relerr(from_nhwc(dres1)[:, c_off:c_off + c], 1.0 + dsl) < 1e-6     # accumulated into the existing ones
+    assert torch.allclose(s0[:2 * c], s1[:2 * c], rtol=1e-5, atol=1e-4)             # fp32 partial sums: order only
+    assert torch.allclose(s1[:c].cpu(), dz_ref.double().sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(s1[c:2 * c].cpu(), (dz_ref * yhat).double().sum((0, 2, 3)), rtol=1e-4, atol=2e-3)
+    if c % 32 == 0:
+        assert s0[2 * c].item() == s1[2 * c].item() == dz_ref.abs().max().item()
