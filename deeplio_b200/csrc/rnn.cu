@@ -337,14 +337,19 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
             }
         }
         __syncthreads();
-        // (B) cell update, one (batch row, unit) per thread
+        // (B) cell update, one (batch row, unit) per thread.  The new h goes to the NEXT h buffer of all four CTAs
+        // first; the tensors saved for the backward pass (gates, c, h_{t-1}, y) are stored to global memory AFTER the
+        // barrier arrive: its release (a MEMBAR.ALL.GPU) then waits for the shared-memory exchange only, and the
+        // global stores drain while the CTA waits for its peers (they are ordered by the next step's arrive).
         float *hnext = hs + (cur ^ 1) * H * RB;
+        float sv[SEQ_ITEMS][8];        // LSTM: gi gf gg go c cp hp h;  GRU: r z n ghn hp h
+        bool live[SEQ_ITEMS];
 #pragma unroll
         for (int q = 0; q < SEQ_ITEMS; ++q) {
             const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
-            if (it >= RB * HU || bl >= nb) continue;
-            const int b = b0 + bl, j = j0 + u;
-            const size_t row = (size_t)b * T + t;
+            live[q] = it < RB * HU && bl < nb;
+            if (!live[q]) continue;
+            const int j = j0 + u;
             const float hp = hc[j * RB + bl];
             float pre[G];
 #pragma unroll
@@ -361,28 +366,40 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                 const float c = gf * cp + gi * gg;
                 h = go * tanhf(c);
                 creg[q] = c;
-                float *gt = s.gates + row * 4 * H;
-                gt[j] = gi; gt[H + j] = gf; gt[2 * H + j] = gg; gt[3 * H + j] = go;
-                s.cst[row * H + j] = c;
-                s.cprev_save[row * H + j] = cp;
-                if (step == T - 1 && s.cn) s.cn[(size_t)b * H + j] = c;
+                sv[q][0] = gi; sv[q][1] = gf; sv[q][2] = gg; sv[q][3] = go; sv[q][4] = c; sv[q][5] = cp;
             } else {
                 const float ghn = pre[2];
                 const float r = sigmoidf_(gxr[q][0] + pre[0]), z = sigmoidf_(gxr[q][1] + pre[1]);
                 const float n = tanhf(gxr[q][2] + r * ghn);
                 h = (1.f - z) * n + z * hp;
-                float *gt = s.gates + row * 4 * H;
-                gt[j] = r; gt[H + j] = z; gt[2 * H + j] = n; gt[3 * H + j] = ghn;
+                sv[q][0] = r; sv[q][1] = z; sv[q][2] = n; sv[q][3] = ghn;
             }
-            s.hprev_save[row * H + j] = hp;
-            s.y[((size_t)b * T + t) * a.DH + j] = h;
-            if (step == T - 1 && s.hn) s.hn[(size_t)b * H + j] = h;
+            sv[q][6] = hp; sv[q][7] = h;
             hnext[j * RB + bl] = h;
 #pragma unroll
             for (int p = 0; p < SEQ_CLUSTER - 1; ++p)
                 st_peer(peer_hs[p] + (uint32_t)(((cur ^ 1) * H * RB + j * RB + bl) * sizeof(float)), h);
         }
-        cluster_barrier();      // h_t complete in both CTAs; everybody is done reading h_{t-1} and the partial sums
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < SEQ_ITEMS; ++q) {
+            if (!live[q]) continue;
+            const int it = threadIdx.x + q * blockDim.x, bl = it / HU, u = it - bl * HU;
+            const int b = b0 + bl, j = j0 + u;
+            const size_t row = (size_t)b * T + t;
+            float *gt = s.gates + row * 4 * H;
+            gt[j] = sv[q][0]; gt[H + j] = sv[q][1]; gt[2 * H + j] = sv[q][2]; gt[3 * H + j] = sv[q][3];
+            if (KIND == 0) {
+                s.cst[row * H + j] = sv[q][4];
+                s.cprev_save[row * H + j] = sv[q][5];
+                if (step == T - 1 && s.cn) s.cn[(size_t)b * H + j] = sv[q][4];
+            }
+            s.hprev_save[row * H + j] = sv[q][6];
+            s.y[((size_t)b * T + t) * a.DH + j] = sv[q][7];
+            if (step == T - 1 && s.hn) s.hn[(size_t)b * H + j] = sv[q][7];
+        }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        // h_t complete in all CTAs; everybody is done reading h_{t-1} and the partial sums
         cur ^= 1;
     }
 }
@@ -448,6 +465,27 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                       (uint32_t)((((int)rank - o - 1 + SEQ_CLUSTER) % SEQ_CLUSTER) * RB * HU * sizeof(float));
     cluster_barrier();
     const int kq = threadIdx.x % H, rg = threadIdx.x / H;
+    // saved tensors of one (batch row, unit) at one time step: LSTM gi gf gg go c cp dout; GRU r z n ghn hp dout.
+    // A thread's (first) item of the NEXT step is loaded while the recurrent product of this step runs, so the L2
+    // round trip of seven dependent-free loads is off the per-step critical path.
+    auto load_saved = [&](int i, int tt, float (&v)[7]) {
+        const int bl = i / HU, u = i - bl * HU, j = j0 + u;
+        if (bl >= nb) return;
+        const int b = b0 + bl;
+        const size_t row = (size_t)b * T + tt;
+        const float *gt = s.gates + row * 4 * H;
+        v[0] = __ldg(gt + j); v[1] = __ldg(gt + H + j); v[2] = __ldg(gt + 2 * H + j); v[3] = __ldg(gt + 3 * H + j);
+        if (KIND == 0) {
+            v[4] = __ldg(s.cst + row * H + j);
+            v[5] = __ldg(s.cprev_save + row * H + j);
+        } else {
+            v[4] = __ldg(s.hprev_save + row * H + j);
+            v[5] = 0.f;
+        }
+        v[6] = s.dout ? __ldg(s.dout + ((size_t)b * T + tt) * a.DH + j) : 0.f;
+    };
+    float pf[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if ((int)threadIdx.x < RB * HU) load_saved(threadIdx.x, reverse ? 0 : T - 1, pf);
     for (int step = T - 1; step >= 0; --step) {
         const int t = reverse ? T - 1 - step : step;
         for (int i = threadIdx.x; i < RB * HU; i += blockDim.x) {
@@ -460,12 +498,18 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
             }
             const int b = b0 + bl;
             const size_t row = (size_t)b * T + t;
-            const float dhv = dh[i] + (s.dout ? __ldg(s.dout + ((size_t)b * T + t) * a.DH + j) : 0.f);
+            float sv[7];
+            if (i == (int)threadIdx.x) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) sv[q] = pf[q];
+            } else {
+                load_saved(i, t, sv);
+            }
+            const float dhv = dh[i] + sv[6];
             if (KIND == 0) {
-                const float *gt = s.gates + row * 4 * H;
-                const float gi = __ldg(gt + j), gf = __ldg(gt + H + j), gg = __ldg(gt + 2 * H + j), go = __ldg(gt + 3 * H + j);
-                const float tc = tanhf(__ldg(s.cst + row * H + j));
-                const float cp = __ldg(s.cprev_save + row * H + j);
+                const float gi = sv[0], gf = sv[1], gg = sv[2], go = sv[3];
+                const float tc = tanhf(sv[4]);
+                const float cp = sv[5];
                 const float dcv = dhv * go * (1.f - tc * tc) + dc[i];
                 const float d0 = dcv * gg * gi * (1.f - gi), d1 = dcv * cp * gf * (1.f - gf);
                 const float d2 = dcv * gi * (1.f - gg * gg), d3 = dhv * tc * go * (1.f - go);
@@ -475,9 +519,8 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                 dc[i] = dcv * gf;
                 dh[i] = 0.f;
             } else {
-                const float *gt = s.gates + row * 4 * H;
-                const float r = __ldg(gt + j), z = __ldg(gt + H + j), n = __ldg(gt + 2 * H + j), ghn = __ldg(gt + 3 * H + j);
-                const float hp = __ldg(s.hprev_save + row * H + j);
+                const float r = sv[0], z = sv[1], n = sv[2], ghn = sv[3];
+                const float hp = sv[4];
                 const float dn_pre = dhv * (1.f - z) * (1.f - n * n);
                 const float dr_pre = dn_pre * ghn * r * (1.f - r);
                 const float dz_pre = dhv * (hp - n) * z * (1.f - z);
@@ -488,6 +531,7 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                 dh[i] = dhv * z;
             }
         }
+        if (step > 0 && (int)threadIdx.x < RB * HU) load_saved(threadIdx.x, reverse ? T - step : step - 1, pf);
         __syncthreads();
         // partial dh_{t-1}[b][k] over this CTA's rows; row group rg handles rows rg, rg + ngroups, ...
         if (rg < ngroups) {
