@@ -137,3 +137,45 @@ def test_gloo_world2_overlapped_gradient_reducer():
         assert n_late > 0 and n_early > 0 and n_late + n_early == numel
         assert err < 1e-6 and scale == 0.5
         assert not fired_after and pending == 0
+
+
+def _extra_late_worker(rank, world, port, out):
+    """The split-backward call pattern of bench.py on the CPU: no hook, ``fire()`` called explicitly after the
+    downstream backward, ``extra_late`` holding a module (a criterion with sx / sq) and a bare Parameter."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    torch.manual_seed(3)
+    model = _ToyModel()
+    crit = torch.nn.Module()
+    crit.sx, crit.sq = torch.nn.Parameter(torch.tensor(0.0)), torch.nn.Parameter(torch.tensor(-3.0))
+    extra = torch.nn.Parameter(torch.ones(3))
+    opt = _FlatOpt(list(model.parameters()) + list(crit.parameters()) + [extra])
+    red = parallel.OverlappedGradReducer(model, opt, extra_late=[crit, extra])
+    model.on_head_grads_ready = None                      # fired explicitly, as with a split backward pass
+    late = sum(b - a for a, b in red.late_ranges)
+    base = sum(b - a for a, b in parallel.OverlappedGradReducer(model, opt).late_ranges)
+    model.on_head_grads_ready = None
+    torch.manual_seed(10 + rank)
+    pos, ori = model(torch.randn(4, 6))
+    loss = (pos.pow(2).sum() + ori.sum()) * torch.exp(-crit.sx) + crit.sx + crit.sq * extra.sum()
+    loss.backward()
+    local = opt.flat_grad.clone()
+    assert not red.fired
+    red.fire()
+    pending = len(red.work)
+    scale = red.finish()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    out[rank] = (late, base, pending, float((opt.flat_grad - sum(gathered)).abs().max()), scale)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_reducer_with_extra_late_parameters_fired_explicitly():
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_extra_late_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        late, base, pending, err, scale = out[rank]
+        assert late == base + 4 + 4 + 4          # sx, sq (one padded slot each) and the 3-element parameter
+        assert pending >= 1 and err < 1e-6 and scale == 0.5
