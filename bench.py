@@ -224,6 +224,8 @@ def run_b200(args):
         if split:
             lidar_net.split_backward = True
             model.on_head_grads_ready = None       # fired explicitly after loss.backward()
+        # measurement only: the step without any gradient exchange (what the max over N unequal GPUs alone costs)
+        reducer.disabled = os.environ.get("DLIO_NO_EXCHANGE", "0") == "1"
 
     host = {k: v.pin_memory() for k, v in synthetic_host_batch(B, S, T, seed=100 + rank).items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
@@ -414,6 +416,9 @@ def run_b200(args):
                      "encoder_streams": 2 if E.ENC_STREAMS else 1,
                      **({"ab": "bwd_single_pass: dgrad / wgrad at plain fp16 operand accuracy -- NOT the parity-tested "
                                "path, not a bench value"} if single_bwd else {}),
+                     **({"ab": "no gradient exchange (DLIO_NO_EXCHANGE=1): replicas drift apart -- measures the "
+                               "max-over-ranks cost alone, not a bench value"}
+                        if (reducer is not None and reducer.disabled) else {}),
                      "l2": "working set per step (%.1f GB peak, activations) exceeds the 126 MB L2; no explicit flush" % peak_gb})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -80,6 +80,7 @@ class OverlappedGradReducer:
             else:
                 rs.append([a, b])
         self.work, self.fired = [], False
+        self.disabled = False         # measurement only (bench.py DLIO_NO_EXCHANGE=1): issue no collective at all
         model.on_head_grads_ready = self._fire
 
     def fire(self):
@@ -87,7 +88,7 @@ class OverlappedGradReducer:
         self._fire()
 
     def _fire(self):
-        if world_size() > 1 and not self.fired:
+        if world_size() > 1 and not self.fired and not self.disabled:
             for a, b in self.late_ranges:
                 self.work.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
         self.fired = True
@@ -95,7 +96,7 @@ class OverlappedGradReducer:
     def finish(self):
         """Call after backward(): reduces what the hook did not, waits for everything.  Returns the 1/world factor
         for the optimizer's ``grad_scale``."""
-        if world_size() > 1:
+        if world_size() > 1 and not self.disabled:
             if self.fired:
                 for a, b in self.early_ranges:
                     dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM)
