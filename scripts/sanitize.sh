@@ -6,10 +6,11 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 SAN=/usr/local/cuda/bin/compute-sanitizer
-TESTS="tests/test_gpu_ops.py tests/test_gpu_conv_pair.py tests/test_gpu_glue.py tests/test_gpu_scan.py tests/test_gpu_model.py::test_model_matches_oracle_and_golden[simple1_lstm_rnn]"
+TESTS="tests/test_gpu_conv_pair.py tests/test_gpu_glue.py tests/test_gpu_scan.py tests/test_gpu_ops.py"
+LIMIT=${SANITIZE_TIMEOUT:-1200}
 rc=0
 for tool in memcheck initcheck; do
-  timeout 1200 $SAN --tool $tool --error-exitcode 9 --launch-timeout 0 \
+  timeout $LIMIT $SAN --tool $tool --error-exitcode 9 --launch-timeout 0 \
       python -m pytest $TESTS -m gpu -q -x -p no:cacheprovider > gpurun_out/sanitize_$tool.log 2>&1
   r=$?
   grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_$tool.log | tail -3
