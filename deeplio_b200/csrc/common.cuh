@@ -132,6 +132,9 @@ __device__ __forceinline__ __half *h2_addr(__half *base, size_t row, int C, int 
 }
 // (packed conversions: cvt.rn.f16x2.f32 handles two channels per instruction; same round-to-nearest results as the
 // scalar f16_split)
+__device__ __forceinline__ unsigned pack_h2(__half a, __half b) {
+    return (unsigned)__half_as_ushort(a) | ((unsigned)__half_as_ushort(b) << 16);
+}
 __device__ __forceinline__ void st4_h2(__half *base, size_t row, int C, int c, const float4 &v, float s, int group = 1) {
     const float x0 = v.x * s, x1 = v.y * s, x2 = v.z * s, x3 = v.w * s;
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);

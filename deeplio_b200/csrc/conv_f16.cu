@@ -21,33 +21,40 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x
 __global__ void __launch_bounds__(256) weight_pack_f16_kernel(const float *__restrict__ w, int cout, int cin, int kh,
                                                               int kw, int cin_pad, int flip, const float *bound,
                                                               __half *__restrict__ out) {
+    // four consecutive output columns per thread (cin_pad and cout are multiples of 4): one index decode and two
+    // 8-byte stores per four elements -- with one element per thread the kernel was bound by its divisions
     const int taps = kh * kw;
-    const long long total = (long long)cout * taps * cin_pad;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const long long total4 = (long long)cout * taps * cin_pad / 4;
+    const long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const long long i = i4 * 4;
     const float s = f16_scale_from_bound(*bound);
     int row, col;
     long long K;
-    int co, ci, tap;
+    __half h[4], l[4];
     if (!flip) {
-        ci = (int)(i % cin_pad);
+        const int ci = (int)(i % cin_pad);
         long long t = i / cin_pad;
-        tap = (int)(t % taps);
-        co = (int)(t / taps);
+        const int tap = (int)(t % taps);
+        const int co = (int)(t / taps);
         row = co; col = tap * cin_pad + ci; K = (long long)taps * cin_pad;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            f16_split((ci + j < cin ? w[((size_t)co * cin + ci + j) * taps + tap] : 0.f) * s, h[j], l[j]);
     } else {
-        co = (int)(i % cout);
+        const int co = (int)(i % cout);
         long long t = i / cout;
-        int tapf = (int)(t % taps);
-        ci = (int)(t / taps);
-        tap = taps - 1 - tapf;        // (kh-1-dy)*kw + (kw-1-dx)
+        const int tapf = (int)(t % taps);
+        const int ci = (int)(t / taps);
+        const int tap = taps - 1 - tapf;        // (kh-1-dy)*kw + (kw-1-dx)
         row = ci; col = tapf * cout + co; K = (long long)taps * cout;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            f16_split((ci < cin ? w[((size_t)(co + j) * cin + ci) * taps + tap] : 0.f) * s, h[j], l[j]);
     }
-    float v = ci < cin ? w[((size_t)co * cin + ci) * taps + tap] : 0.f;
-    __half h, l;
-    f16_split(v * s, h, l);
-    out[(size_t)row * 2 * K + col] = h;
-    out[(size_t)row * 2 * K + K + col] = l;
+    __half *o = out + (size_t)row * 2 * K + col;
+    *reinterpret_cast<uint2 *>(o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    *reinterpret_cast<uint2 *>(o + K) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
 }
 
 __global__ void __launch_bounds__(256) pack_f16_kernel(const float *__restrict__ src, long long rows, int c,
@@ -86,7 +93,9 @@ extern "C" int dlio_weight_pack_f16(const float *w_oihw, int cout, int cin, int 
         absmax_kernel<<<grid > 592 ? 592 : grid, 256, 0, st>>>(w_oihw, n, w_bound);
         DLIO_LAUNCH_CHECK();
     }
-    const long long total = (long long)cout * kh * kw * cin_pad;
+    DLIO_CHECK_ARG(cin_pad % 4 == 0 && cout % 4 == 0 && (((uintptr_t)w_h2) & 7) == 0,
+                   "weight_pack_f16: cin_pad and cout must be multiples of 4");
+    const long long total = (long long)cout * kh * kw * cin_pad / 4;
     weight_pack_f16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w_oihw, cout, cin, kh, kw, cin_pad, transpose_flip,
                                                                 w_bound, (__half *)w_h2);
     DLIO_LAUNCH_CHECK();

@@ -143,32 +143,39 @@ __device__ __forceinline__ float pair_weight(const float *__restrict__ w, int ci
 __global__ void __launch_bounds__(256) weight_pack_pair_f16_kernel(const float *__restrict__ w, int cout, int cin,
                                                                    int kh, int kw, int kw2, int flip,
                                                                    const float *bound, __half *__restrict__ out) {
+    // four consecutive output columns per thread (cin and cout are multiples of 4): see weight_pack_f16_kernel
     const int taps = kh * kw2, c2 = 2 * cin;
-    const long long total = (long long)cout * taps * c2;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const long long total4 = (long long)cout * taps * c2 / 4;
+    const long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const long long i = i4 * 4;
     const float s = f16_scale_from_bound(*bound);
-    int row, col, co, pc, tap;
+    int row, col;
     long long K;
+    __half h[4], l[4];
     if (!flip) {
-        pc = (int)(i % c2);
+        const int pc = (int)(i % c2);
         long long t = i / c2;
-        tap = (int)(t % taps);
-        co = (int)(t / taps);
+        const int tap = (int)(t % taps);
+        const int co = (int)(t / taps);
         row = co; col = tap * c2 + pc; K = (long long)taps * c2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            f16_split(pair_weight(w, cin, kh, kw, kw2, co, tap / kw2, tap % kw2, pc + j) * s, h[j], l[j]);
     } else {
-        co = (int)(i % cout);
+        const int co = (int)(i % cout);
         long long t = i / cout;
         const int tapf = (int)(t % taps);
-        pc = (int)(t / taps);
-        tap = taps - 1 - tapf;
+        const int pc = (int)(t / taps);
+        const int tap = taps - 1 - tapf;
         row = pc; col = tapf * cout + co; K = (long long)taps * cout;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            f16_split(pair_weight(w, cin, kh, kw, kw2, co + j, tap / kw2, tap % kw2, pc) * s, h[j], l[j]);
     }
-    const float v = pair_weight(w, cin, kh, kw, kw2, co, tap / kw2, tap % kw2, pc);
-    __half h, l;
-    f16_split(v * s, h, l);
-    out[(size_t)row * 2 * K + col] = h;
-    out[(size_t)row * 2 * K + K + col] = l;
+    __half *o = out + (size_t)row * 2 * K + col;
+    *reinterpret_cast<uint2 *>(o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    *reinterpret_cast<uint2 *>(o + K) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
 }
 
 // dw[co][c][dy][dx] (OIHW) = dw2[co][dy][t][p * cin + c] for the one (t, p) that maps to dx
@@ -215,7 +222,9 @@ extern "C" int dlio_weight_pack_pair_f16(const float *w_oihw, int cout, int cin,
         DLIO_LAUNCH_CHECK();
     }
     const int kw2 = kw > 1 ? 3 : 1;
-    const long long total = (long long)cout * kh * kw2 * 2 * cin;
+    DLIO_CHECK_ARG(cin % 4 == 0 && cout % 4 == 0 && (((uintptr_t)w_h2) & 7) == 0,
+                   "weight_pack_pair_f16: cin and cout must be multiples of 4");
+    const long long total = (long long)cout * kh * kw2 * 2 * cin / 4;
     weight_pack_pair_f16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w_oihw, cout, cin, kh, kw, kw2, transpose_flip,
                                                                      w_bound, (__half *)w_h2);
     DLIO_LAUNCH_CHECK();

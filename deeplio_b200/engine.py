@@ -82,11 +82,12 @@ FIRST_F16 = os.environ.get("DLIO_FIRST_F16", "1") == "1"
 
 
 def first_layer_f16_ok(wshape, stride, width):
-    """The first convolution (<= 8 input channels) can run on packed fp16 input planes: W stride 2 (two outputs per
-    4-pixel group -> 128 tensor-core columns), 64 output channels (one dy box per output pixel in wgrad)."""
+    """The first convolution (<= 8 input channels) can run on packed fp16 input planes: W stride 1 or 2 (four or two
+    outputs per 4-pixel group -> 256 or 128 tensor-core columns), 64 output channels (one dy box per output pixel
+    in wgrad)."""
     cout, cin, kh, kw = wshape
-    return (USE_TC and USE_F16 and FIRST_F16 and tuple(stride) == (1, 2) and cout == 64 and cin <= 8 and kw <= 7
-            and kw % 2 == 1 and width % 4 == 0)
+    return (USE_TC and USE_F16 and FIRST_F16 and tuple(stride) in ((1, 1), (1, 2)) and cout == 64 and cin <= 8
+            and kw <= 7 and kw % 2 == 1 and width % 4 == 0)
 
 
 def pair_ok(x, cin, cout, kh, kw, stride):

@@ -492,6 +492,7 @@ def test_conv_bn_block_vs_torch(cfg):
     ((5, 7), (1, 1), False, (1, 2), 2, False),  # ResNet conv1 (stride 1: four output pixels per space-to-depth group)
     ((5, 7), (1, 2), True, (1, 2), 2, True),    # the same layers on packed fp16 input planes ("folded split"
     ((3, 5), (1, 2), False, (1, 2), 1, True),   # operands): what the nets run when they are fed PairedFrames
+    ((5, 7), (1, 1), False, (1, 2), 2, True),   # ResNet conv1 folded: four output pixels per group, N = 256
 ])
 def test_first_layer_space_to_depth_at_64x2048(k, stride, pre_relu, pool, first_ph, folded):
     """The first convolution of every encoder at its real size (two 6-channel 64 x 2048 images): dlio_pack_input from
