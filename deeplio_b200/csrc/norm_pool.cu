@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApp
     constexpr int U = GATHER ? 1 : 4;
     constexpr int NR = SH == 1 ? 3 : 2, NC = SW == 1 ? 3 : 2;     // candidate windows per axis (gather)
     const int wl = (int)(threadIdx.x / a.cg), WL = (int)(blockDim.x / a.cg);
+    const int DC = a.dy.c;
     const int rows = a.dy.n * a.dy.hp, segs = a.segs, items = rows * segs;
     const int seg_w = (a.dy.wp + segs - 1) / segs;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -873,11 +874,17 @@ __global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApp
                 const int x = x0 + u * WL;
                 if (x >= x_end) break;
                 const unsigned pix = pix0 + (unsigned)x;
-                const size_t o = (size_t)pix * C + c;
+                const size_t o = (size_t)pix * DC + c;
+                // dy may carry more channels than y (a narrow layer padded to the tensor cores' granularity): zeros
+                for (int cz = C + c; cz < DC; cz += C) {
+                    if (a.dy_hi) st4(a.dy_hi + (size_t)pix * DC + cz, f4(0.f));
+                    if (a.dy_lo) st4(a.dy_lo + (size_t)pix * DC + cz, f4(0.f));
+                    if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, DC, cz);
+                }
                 if (!ok[u]) {
                     if (a.dy_hi) st4(a.dy_hi + o, f4(0.f));
                     if (a.dy_lo) st4(a.dy_lo + o, f4(0.f));
-                    if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, C, c);
+                    if (a.dy_h2) st4_h2_zero(a.dy_h2, pix, DC, c);
                     continue;
                 }
                 const float4 yh = make_float4((y[u].x - mu.x) * is.x, (y[u].y - mu.y) * is.y, (y[u].z - mu.z) * is.z,
@@ -898,7 +905,7 @@ __global__ void __launch_bounds__(256, SH > 0 ? 4 : 1) bn_bwd_apply_kernel(BnApp
                     if (!(y[u].w > 0.f)) d.w = 0.f;
                 }
                 if (a.dy_hi) st4_split(a.dy_hi, a.dy_lo, o, d);
-                if (a.dy_h2) st4_h2(a.dy_h2, pix, C, c, d, s16);
+                if (a.dy_h2) st4_h2(a.dy_h2, pix, DC, c, d, s16);
                 sb = add4(sb, d);
             }
         }
@@ -1827,7 +1834,9 @@ static int bn_bwd_apply_impl(dlio_tensor4 y, const float *y_ptr, const float *dz
     // dy_t.h == y.h: dy on y's own grid.  dy_t.h == input height of an H-stride-2 convolution: y row i goes to dy row
     // 2 i and the odd rows are zero (the backward of that convolution runs as a stride-1 one over the input grid)
     const int hs = dy_t.h == y.h ? 1 : 2;
-    DLIO_CHECK_ARG(dy_t.n == y.n && (hs == 1 || (dy_t.h - 1) / 2 + 1 == y.h) && dy_t.w == y.w && dy_t.c == y.c,
+    // dy_t.c > y.c (dz variant only): the extra channels are written as zeros
+    DLIO_CHECK_ARG(dy_t.n == y.n && (hs == 1 || (dy_t.h - 1) / 2 + 1 == y.h) && dy_t.w == y.w &&
+                       (dy_t.c == y.c || (dz && dy_t.c > y.c && dy_t.c % 4 == 0)),
                    "bn_bwd_apply: dy geometry");
     int rc = check_cg(y.c, "bn_bwd_apply");
     if (rc) return rc;

@@ -77,6 +77,8 @@ def f16_ok(cin, cout, stride):
     return USE_TC and USE_F16 and tuple(stride) == (1, 1) and cin % 64 == 0 and cout % 16 == 0
 
 
+# backward of narrow 3xTF32 layers (Fire squeezes) on the tensor cores through zero-padded dy channels / weight rows
+NARROW_TC_BWD = os.environ.get("DLIO_NARROW_TC_BWD", "1") == "1"
 # first layer on the fp16 kernels through the "folded split" operands (csrc/conv_s2d.cu); DLIO_FIRST_F16=0 keeps 3xTF32
 FIRST_F16 = os.environ.get("DLIO_FIRST_F16", "1") == "1"
 
@@ -450,6 +452,16 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             dg = None
             if x.needs_grad:
                 dg = ("f16" if (f16_ok(cout, cin_pad, stride)) else ("tf32" if tc_ok(cout, cin_pad, stride) else "simt"))
+        # narrow layer on the 3xTF32 forward path (Fire squeeze: 16 / 48 / 80 output channels): its backward runs on the
+        # tensor cores too when dy carries zero channels up to a multiple of 32 (written by dlio_bn_bwd_apply) and the
+        # weights zero rows -- instead of the CUDA-core dgrad / wgrad kernels (1.9 ms of the PointSeg step)
+        cb = cout
+        if (NARROW_TC_BWD and not s2d and not pair and wg == "simt" and fwd_tc and ymax is None and cout % 4 == 0
+                and tuple(stride) == (1, 1)):
+            cb = (cout + 31) // 32 * 32
+            wg = "tf32"
+            if x.needs_grad:
+                dg = "tf32" if tc_ok(cb, cin_pad, stride) else "simt"
         assert wg != "simt" or x.t is not None, (cname, "wgrad on the CUDA cores needs the fp32 input plane")
         modes = (wg, dg)
         if FLOPS is not None:
@@ -488,7 +500,7 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             # dy on the padded grid of the pixel-pair view; with sh == 2 its rows are spread over the even input rows
             dya = Act(n, x.h, wo, cout, x.ph, x.pw // 2, device=run.device, f32=False, f16=True)
         else:
-            dya = Act(n, ho, wo, cout, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
+            dya = Act(n, ho, wo, cb, dpad[0], dpad[1], device=run.device, f32="simt" in modes or "tf32" in modes,
                       split="tf32" in modes, f16="f16" in modes)
         dya.bound = run.empty(1) if dya.h2 is not None else None
         dgamma, dbeta = run.param_grad(bname + ".weight", gamma), run.param_grad(bname + ".bias", beta)
@@ -535,7 +547,7 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
                                 ptr(dya.lo), cv4, ptr(dw4), st)
             L.weight_grad_from_s2d(ptr(dw4), cout, cin, kh, kw, sw, ptr(dw), st)
         else:
-            dw_ohwi = run.empty(cout, kh, kw, cin_pad)
+            dw_ohwi = run.empty(cb, kh, kw, cin_pad)      # rows [cout, cb): gradients of the zero rows, not read
             if wg == "f16":
                 L.conv2d_bwd_weight_f16(x.t4, ptr(x.h2), ptr(x.bound), dya.t4, ptr(dya.h2), ptr(dya.bound), cv,
                                         ptr(dw_ohwi), st)
@@ -556,10 +568,16 @@ def _conv_bn(run, x, cname, bname, stride=(1, 1), pre_relu=False, relu=True, poo
             if wo_ is None:
                 wo_ = run.empty(cout, kh, kw, cin_pad)
                 L.weight_to_ohwi(ptr(w), cout, cin, kh, kw, cin_pad, ptr(wo_), None, st)
+            if cb != cout:
+                wo_p, wl_p = run.zeros(cb, kh, kw, cin_pad), run.zeros(cb, kh, kw, cin_pad)
+                wo_p[:cout].copy_(wo_)
+                if wl_ is not None:
+                    wl_p[:cout].copy_(wl_)
+                wo_, wl_ = wo_p, wl_p
             wt_hi = wt_lo = None
             if dg == "tf32":
                 wt_hi, wt_lo = torch.empty_like(wo_), torch.empty_like(wo_)
-                L.weight_flip_transpose(ptr(wo_), cout, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
+                L.weight_flip_transpose(ptr(wo_), cb, cin_pad, kh, kw, ptr(wt_hi), ptr(wt_lo), st)
             run.add_grad(x, lambda buf, acc=0: L.conv2d_bwd_data(dya.t4, ptr(dya.t), ptr(dya.lo), ptr(wo_), ptr(wl_),
                                                                  ptr(wt_hi), ptr(wt_lo), cv, x.t4_unpadded, ptr(buf),
                                                                  acc, st), accumulates=True)

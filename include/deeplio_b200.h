@@ -294,7 +294,9 @@ int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, const float 
  * the dy operand of that convolution's backward run as a stride-1 convolution over its input grid.
  * post_relu != 0 (needs `shift`): `dz` is the gradient of the ReLU OUTPUT (BN -> ReLU layers, base_net.py:55-71) and
  * the kernel masks it with scale*y + shift > 0 itself -- pass 1 then runs with dz == NULL (sums only) and the masked
- * gradient never goes through HBM. */
+ * gradient never goes through HBM.  dy_t.c > y.c (multiple of 4): channels [y.c, dy_t.c) of dy are written as zeros,
+ * so that the backward of a narrow convolution (Fire squeeze, 16 / 48 / 80 output channels) runs on the tensor cores
+ * against weights padded with zero rows. */
 int dlio_bn_bwd_apply(dlio_tensor4 y, const float *y_ptr, const float *dz, const double *sums,
                       long long count, const float *scale, const float *mean, const float *invstd,
                       int pre_relu, int batch_stats, dlio_tensor4 dy_t, float *dy_hi, float *dy_lo,
