@@ -18,6 +18,11 @@
 // issuer (one elected lane of the converged warp) + TMEM owner, warps 2-9 epilogue (TMEM -> registers -> scale /
 // bias / ReLU -> global, per-channel BN statistics); the epilogue of tile t overlaps the main loop of tile t + 1.
 // wgrad_tc_kernel: one 128 x BN tile of dw per CTA, split-K over pixel ranges, both operands MN-major.
+// conv_tc2_kernel / wgrad_tc2_kernel: the same pipelines on CTA PAIRS (tcgen05 cta_group::2, M = 256): each CTA stages
+// its own 128 A rows and half of the B tile, the leader CTA issues, commits are multicast to both CTAs' barriers --
+// halves the B-side shared-memory traffic that bounds the single-CTA kernels; used whenever the output tile is 128
+// channels wide (forward / dgrad) or Cin % 128 == 0 and Cout % 256 == 0 (wgrad).
+// "fold" mode (first layer, conv_s2d.cu): one plane of x whose 128-byte rows hold hi AND lo halves, two products.
 //
 // Accumulation accuracy.  The tensor core adds each MMA into the fp32 accumulator with truncation, so the
 // error of ONE accumulator grows linearly with the number of MMA steps (measured: 8e-9 * K relative, 3.7e-5 at
@@ -927,9 +932,9 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     if ((rc = make_map_pair(&mwh, &mwl, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn))) return rc;
     t.mtiles = (rows + TC_BM - 1) / TC_BM;
     t.ntiles = a.cout / bn;
-    // (CTA pairs sharing the weight tile through TMA multicast were tried in round 1 and measured 6 % slower:
-    // the main loop is bound by shared-memory bandwidth -- TMA fills plus the SS operand reads of the MMAs --
-    // not by L2 -> SM traffic.)
+    // (Sharing the weight tile of two independent CTAs through TMA multicast measured 6 % slower: the main loop is
+    // bound by shared-memory bandwidth -- TMA fills plus the SS operand reads of the MMAs -- not by L2 -> SM traffic.
+    // What does help is cta_group::2 below: ONE MMA over a CTA pair, each CTA holding half of the weight tile.)
 
     static int n_sm = 0;
     if (!n_sm) {
