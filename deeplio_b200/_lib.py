@@ -86,6 +86,7 @@ _PROTOS = {
     "dlio_axpby": (I, [P, F, P, F, P, LL, P]),
     "dlio_sum_mid": (I, [P, P, LL, I, I, P]),
     "dlio_mul": (I, [P, P, P, LL, P]),
+    "dlio_copy2d": (I, [P, LL, P, LL, LL, I, P]),
     "dlio_dropout_mask": (I, [P, LL, F, C.c_ulonglong, P, P]),
     "dlio_linear_fwd": (I, [P, I, P, P, I, I, I, I, P, I, P]),
     "dlio_linear_bwd": (I, [P, I, P, P, I, P, I, I, I, I, I, P, I, P, P, P, P]),

@@ -1564,6 +1564,18 @@ __global__ void sum_mid_kernel(const float *__restrict__ x, float *__restrict__ 
     for (int t = 0; t < T; ++t) s += x[((size_t)a * T + t) * C + c];
     out[i] = s;
 }
+// dst[r * ldd + c] = src[r * lds + c]: a [rows, cols] block between two row-strided buffers (concatenation along
+// the last axis and its backward, stacking per-window features)
+__global__ void copy2d_kernel(const float *__restrict__ src, long long lds, float *__restrict__ dst, long long ldd,
+                              long long rows, int cols) {
+    const long long total = rows * cols;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
 __global__ void mul_kernel(const float *__restrict__ a, const float *__restrict__ b, float *out, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -2033,6 +2045,14 @@ extern "C" int dlio_sum_mid(const float *x, float *out, long long a, int t, int 
     ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
     DLIO_CHECK_ARG(x && out && a > 0 && t > 0 && c > 0, "sum_mid: bad argument");
     sum_mid_kernel<<<ceil_div(a * c, 256), 256, 0, (cudaStream_t)stream>>>(x, out, a, t, c);
+    DLIO_LAUNCH_CHECK();
+    return DLIO_OK;
+}
+extern "C" int dlio_copy2d(const float *src, long long lds, float *dst, long long ldd, long long rows, int cols,
+                           void *stream) {
+    ProfScope prof_(DLIO_PROF_ELEMENTWISE, (cudaStream_t)stream);
+    DLIO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "copy2d: bad argument");
+    copy2d_kernel<<<grid_for(rows * cols, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
 }

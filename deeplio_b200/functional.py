@@ -121,6 +121,81 @@ def mul(a, b):
     return _Mul.apply(a, b)
 
 
+class _CatLast(torch.autograd.Function):
+    """torch.cat(tensors, dim=-1) for tensors that agree on the leading dimensions: one strided copy per input."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [x.contiguous() for x in xs]
+        widths = [x.shape[-1] for x in xs]
+        rows = xs[0].numel() // widths[0]
+        out = torch.empty(xs[0].shape[:-1] + (sum(widths),), device=xs[0].device, dtype=torch.float32)
+        off = 0
+        for x, w in zip(xs, widths):
+            L.copy2d(ptr(x), w, out.data_ptr() + 4 * off, sum(widths), rows, w, _stream())
+            off += w
+        ctx.widths, ctx.rows = widths, rows
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        total, off, grads = sum(ctx.widths), 0, []
+        for i, w in enumerate(ctx.widths):
+            g = None
+            if ctx.needs_input_grad[i]:
+                g = torch.empty(d.shape[:-1] + (w,), device=d.device, dtype=torch.float32)
+                L.copy2d(d.data_ptr() + 4 * off, total, ptr(g), w, ctx.rows, w, _stream())
+            grads.append(g)
+            off += w
+        return tuple(grads)
+
+
+def cat_last(*xs):
+    """Concatenation along the last axis (fusion_nets.py:27,70,75) through the library's strided copy."""
+    for x in xs:
+        _check(x, "cat_last input")
+        assert x.shape[:-1] == xs[0].shape[:-1]
+    return _CatLast.apply(*xs)
+
+
+class _StackMid(torch.autograd.Function):
+    """torch.stack([B, C] tensors, dim=1) -> [B, S, C]; the inputs may be row-strided views (``x[:, -1, :C]``)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        b, c = xs[0].shape
+        s = len(xs)
+        out = torch.empty((b, s, c), device=xs[0].device, dtype=torch.float32)
+        for i, x in enumerate(xs):
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            L.copy2d(ptr(x), x.stride(0), out.data_ptr() + 4 * i * c, s * c, b, c, _stream())
+        ctx.shape = (b, s, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        b, s, c = ctx.shape
+        grads = []
+        for i in range(s):
+            g = None
+            if ctx.needs_input_grad[i]:
+                g = torch.empty((b, c), device=d.device, dtype=torch.float32)
+                L.copy2d(d.data_ptr() + 4 * i * c, s * c, ptr(g), c, b, c, _stream())
+            grads.append(g)
+        return tuple(grads)
+
+
+def stack_mid(xs):
+    """torch.stack(xs, dim=1) of [B, C] tensors (the per-window IMU features, imu_feat_nets.py:81-83)."""
+    for x in xs:
+        _check(x, "stack_mid input")
+        assert x.dim() == 2 and x.shape == xs[0].shape
+    return _StackMid.apply(*xs)
+
+
 _drop_counter = [0]
 # device int64 counter mixed into every dropout seed at run time (None: not used).  deeplio_b200.graph sets it while
 # it captures a train step and advances it inside the graph, so that replays draw fresh masks.

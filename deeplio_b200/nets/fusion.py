@@ -27,7 +27,7 @@ class DeepLIOFusionCat(BaseNet):
     def forward(self, x):
         if self.type != "cat":
             raise NotImplementedError()
-        return torch.cat((x[0], x[1]), dim=2)
+        return Fn.cat_last(x[0], x[1])
 
 
 class DeepLIOFusionSoft(BaseNet):
@@ -49,7 +49,7 @@ class DeepLIOFusionSoft(BaseNet):
 
     def forward(self, x):
         lidar_feat, imu_feat = x[0], x[1]
-        cat_feat = torch.cat((lidar_feat, imu_feat), dim=2)
+        cat_feat = Fn.cat_last(lidar_feat, imu_feat)
         self.s1_feat = Fn.linear(cat_feat, self.layers[0].weight, self.layers[0].bias, "sigmoid")
         self.s2_feat = Fn.linear(cat_feat, self.layers[1].weight, self.layers[1].bias, "sigmoid")
-        return torch.cat((Fn.mul(lidar_feat.contiguous(), self.s1_feat), Fn.mul(imu_feat.contiguous(), self.s2_feat)), dim=2)
+        return Fn.cat_last(Fn.mul(lidar_feat.contiguous(), self.s1_feat), Fn.mul(imu_feat.contiguous(), self.s2_feat))

@@ -70,4 +70,4 @@ class ImufeatRNN0(BaseImuFeatNet):
             out, state = Fn.rnn(x[:, seq], state, self.rnn_type, self.num_layers, self.bidirectional,
                                 self.hidden_size, weights, self.p, self.training)
             feats.append(out[:, -1, :self.hidden_size])
-        return torch.stack(feats, dim=1)
+        return Fn.stack_mid(feats)

@@ -339,6 +339,9 @@ int dlio_channel_scale_bwd(const float *dout, const float *gate, const float *dm
 int dlio_axpby(const float *a, float alpha, const float *b, float beta, float *out, long long n, void *stream);
 int dlio_sum_mid(const float *x, float *out, long long a, int t, int c, void *stream);
 int dlio_mul(const float *a, const float *b, float *out, long long n, void *stream);
+/* dst[r * ldd + c] = src[r * lds + c] for a [rows, cols] block (element strides): torch.cat along the last axis
+ * (fusion_nets.py:27,70,75), torch.stack of the per-window IMU features (imu_feat_nets.py:81-83) and their backward. */
+int dlio_copy2d(const float *src, long long lds, float *dst, long long ldd, long long rows, int cols, void *stream);
 int dlio_dropout_mask(float *mask, long long n, float p, unsigned long long seed,
                       const unsigned long long *seed_epoch, void *stream);
 
