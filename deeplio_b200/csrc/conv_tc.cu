@@ -946,7 +946,11 @@ int conv_tc_fwd(const ConvArgs &a, int prof_kind, cudaStream_t st) {
     }
     ProfScope prof(prof_kind, st);
     if ((a.o.ph > 0 || a.o.pw > 0) && !a.accum) DLIO_CUDA(cudaMemsetAsync(a.out, 0, a.o.numel() * sizeof(float), st));
-    if (f16 && bn == 128 && conv_cg2_enabled()) {
+    // 64-channel output tiles (ResNet layer1, conv2's dgrad) on CTA pairs too: the B side of their shared-memory
+    // traffic halves as well (A dominates there: 4 KB + 1 KB per MMA and CTA instead of 4 + 2); DLIO_CG2_N64=0 keeps
+    // them on the single-CTA kernel
+    static const bool pairs_n64 = [] { const char *e = getenv("DLIO_CG2_N64"); return !(e && e[0] == '0'); }();
+    if (f16 && (bn == 128 || (bn == 64 && pairs_n64)) && conv_cg2_enabled()) {
         // CTA pairs (conv_tc2_kernel): 256-row tiles, each CTA stages half of the weight tile
         CUtensorMap mwh2, mwl2;
         if ((rc = make_map_pair(&mwh2, &mwl2, a.w_hi, a.w_lo, a.w_h2, a.cout, K, bn / 2))) return rc;

@@ -17,6 +17,9 @@ CASES = [
     (2, 64, 128, 64, 513, (3, 5), True, 1),       # Simple-1 conv2 at its real size
     (1, 256, 256, 33, 129, (3, 3), True, 1),      # conv5
     (2, 768, 128, 6, 10, (1, 1), True, 0),        # 1x1, K = 12 chunks
+    (2, 128, 64, 9, 33, (3, 3), True, 1),         # 64-channel output tiles: each CTA stages 32 weight rows
+    (1, 64, 64, 20, 70, (3, 3), False, 0),        # ResNet layer1
+    (2, 128, 64, 64, 513, (3, 5), False, 0),      # the shape of Simple-1 conv2's dgrad
 ]
 
 
