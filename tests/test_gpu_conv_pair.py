@@ -58,7 +58,9 @@ def test_conv_cta_pair_equals_single_cta(case):
     assert relerr(from_nhwc(y1).double(), ref) < 1e-5
     assert torch.equal(y0, y1)                              # same K order, same accumulator segments per output
     assert torch.allclose(s0, s1, rtol=1e-12, atol=1e-9)    # fp64 atomics: order only
-    assert torch.allclose(s1.cpu()[:cout], ref.sum((0, 2, 3)), rtol=5e-5, atol=1e-4)
+    # sums of up to 65 k values of both signs: the bar is relative to the sum of magnitudes
+    assert torch.allclose(s1.cpu()[:cout], ref.sum((0, 2, 3)), rtol=5e-5,
+                          atol=max(1e-4, 2e-6 * ref.abs().sum((0, 2, 3)).max().item()))
 
 
 WGRAD_CASES = [
