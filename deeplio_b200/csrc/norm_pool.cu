@@ -69,6 +69,10 @@ static inline int row_segments(int rows, int width, int wlanes, int grid) {
     if (segs > max_segs) segs = max_segs;
     return segs < 1 ? 1 : segs;
 }
+// blocks per SM of the reduction passes that end in 2 C fp64 atomics per block: at C = 512 a grid of 8 blocks per SM
+// sends 1.2 M atomics to 1024 addresses (~20 us of every launch, whatever the tensor size); two blocks per SM with
+// eight 16-byte loads in flight per thread still cover the HBM latency
+static inline int reduce_blocks_per_sm(int c) { return c >= 256 ? 2 : (c >= 128 ? 4 : 8); }
 static inline int grid_for(long long total, int block, int per_sm = 8) {
     long long g = (total + block - 1) / block;
     long long cap = 148LL * per_sm;
@@ -1815,7 +1819,7 @@ extern "C" int dlio_bn_act_pool_bwd_reduce(dlio_tensor4 y, const float *y_ptr, c
     }
     const bool flat = a.pk == 1 && grad_src == DLIO_GRAD_DIRECT && a.res_mode != 1 && y.ph == 0 && y.pw == 0 &&
                       dout.ph == 0 && dout.pw == 0 && (long long)y.n * y.h * y.w < (1LL << 30) && g_apply_rows;
-    if (flat) bn_bwd_reduce_flat_kernel<<<grid_for((total + 3) / 4, block, 8), block, 0, st>>>(a);
+    if (flat) bn_bwd_reduce_flat_kernel<<<grid_for((total + 3) / 4, block, reduce_blocks_per_sm(y.c)), block, 0, st>>>(a);
     else if (a.pk == 1) bn_act_pool_bwd_reduce_kernel<0, 0><<<grid, block, 0, st>>>(a);
     else if (a.sh == 1 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<1, 2><<<grid, block, 0, st>>>(a);
     else if (a.sh == 2 && a.sw == 2) bn_act_pool_bwd_reduce_kernel<2, 2><<<grid, block, 0, st>>>(a);
@@ -1954,7 +1958,7 @@ extern "C" int dlio_pool_bwd_sums(dlio_tensor4 dout, const float *dout_ptr, int 
     const int cg = c / 4, block = block_for_cg(cg);
     const long long total = (long long)dout.n * dout.h * dout.w * cg;
     DLIO_CHECK_ARG((long long)dout.n * dout.h * dout.w < (1LL << 30), "pool_bwd_sums: tensor too large");
-    pool_bwd_sums_kernel<<<grid_for((total + 3) / 4, block, 8), block, 0, (cudaStream_t)stream>>>(
+    pool_bwd_sums_kernel<<<grid_for((total + 3) / 4, block, reduce_blocks_per_sm(c)), block, 0, (cudaStream_t)stream>>>(
         Geo(dout), dout_ptr, c_off, ymax, mean, invstd, cg, (float)windows, sums);
     DLIO_LAUNCH_CHECK();
     return DLIO_OK;
