@@ -823,10 +823,9 @@ extern "C" int dlio_rnn_bwd(int kind, int L, int D, int B, int T, int I, int H, 
         for (int d = 0; d < D; ++d) {
             const float *const *w = weights + 4 * (l * D + d);
             float *const *g = grads + 4 * (l * D + d);
-            if ((rc = linear_dw_launch(dg[d][0], G * H, xin, Il, (int)bt, G * H, Il, g[0], st))) return rc;
-            if ((rc = linear_dw_launch(dg[d][1], G * H, lay.hps(reserve, l, d), H, (int)bt, G * H, H, g[1], st))) return rc;
-            if ((rc = colsum_launch(dg[d][0], G * H, (int)bt, G * H, g[2], st))) return rc;
-            if ((rc = colsum_launch(dg[d][1], G * H, (int)bt, G * H, g[3], st))) return rc;
+            // weight gradients; the bias gradients (column sums of the same gate gradients) ride along
+            if ((rc = linear_dw_launch(dg[d][0], G * H, xin, Il, (int)bt, G * H, Il, g[0], st, g[2]))) return rc;
+            if ((rc = linear_dw_launch(dg[d][1], G * H, lay.hps(reserve, l, d), H, (int)bt, G * H, H, g[1], st, g[3]))) return rc;
             if (dxl && (rc = linear_dx_launch(dg[d][0], G * H, w[0], (int)bt, G * H, Il, dxl, Il, st))) return rc;
         }
         if (l > 0 && drop_mask) {
