@@ -236,6 +236,39 @@ constexpr int SEQ_MAXR = 3;        // W_hh rows per row thread: G * H / 2 <= 384
 // writes the saved tensors, and stores h_t into the NEXT h buffer of BOTH CTAs (the peer's through distributed
 // shared memory); one cluster barrier per step.  (A first version with one warp per hidden unit and a shuffle
 // transpose-reduce per unit spent 77 % of its 2200 instructions per warp and step outside the FMAs.)
+// part[(kg * RB + b) * R + r] = sum over k in [k_begin, k_end) of W_hh^T[k][r] * h[k][b] for this thread's NROW rows
+template <int NROW>
+__device__ __forceinline__ void seq_partial_product(const float *ws, const float *hc, float *part, int k_begin, int k_end,
+                                                    int RP, int rp, int kg, int R, const bool (&rowok)[SEQ_MAXR]) {
+    float acc[NROW][RB];
+#pragma unroll
+    for (int m = 0; m < NROW; ++m)
+#pragma unroll
+        for (int b = 0; b < RB; ++b) acc[m][b] = 0.f;
+    const float *wr = ws + (size_t)k_begin * RP + rp;
+    const float *hp4 = hc + k_begin * RB;
+#pragma unroll 4
+    for (int k = k_begin; k < k_end; ++k, wr += RP, hp4 += RB) {
+        const float4 h0 = *reinterpret_cast<const float4 *>(hp4);
+        const float4 h1 = *reinterpret_cast<const float4 *>(hp4 + 4);
+        const float hv[RB] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int m = 0; m < NROW; ++m) {
+            const float w = rowok[m] ? wr[m * SEQ_ROWT] : 0.f;  // select, not a branch
+#pragma unroll
+            for (int b = 0; b < RB; ++b) acc[m][b] = fmaf(w, hv[b], acc[m][b]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NROW; ++m) {
+        const int r = rp + m * SEQ_ROWT;
+        if (r < R) {
+#pragma unroll
+            for (int b = 0; b < RB; ++b) part[(kg * RB + b) * R + r] = acc[m][b];
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS * 32) rnn_seq_fwd_kernel(SeqArgs a) {
     extern __shared__ float sm[];
@@ -304,38 +337,13 @@ __global__ void __cluster_dims__(SEQ_CLUSTER, 1, 1) __launch_bounds__(SEQ_WARPS 
                 for (int g = 0; g < G; ++g) gxr[q][g] = __ldg(gx + (size_t)g * H);
             }
         }
-        // (A) recurrent pre-activations, partial over this thread's k range
-        {
-            float acc[SEQ_MAXR][RB];
-#pragma unroll
-            for (int m = 0; m < SEQ_MAXR; ++m)
-#pragma unroll
-                for (int b = 0; b < RB; ++b) acc[m][b] = 0.f;
-            const float *wr = ws + (size_t)k_begin * RP + rp;
-            const float *hp4 = hc + k_begin * RB;
-#pragma unroll 4
-            for (int k = k_begin; k < k_end; ++k, wr += RP, hp4 += RB) {
-                const float4 h0 = *reinterpret_cast<const float4 *>(hp4);
-                const float4 h1 = *reinterpret_cast<const float4 *>(hp4 + 4);
-                const float hv[RB] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int m = 0; m < SEQ_MAXR; ++m) {
-                    if (m < nrow) {                                         // uniform over the CTA
-                        const float w = rowok[m] ? wr[m * SEQ_ROWT] : 0.f;  // select, not a branch
-#pragma unroll
-                        for (int b = 0; b < RB; ++b) acc[m][b] = fmaf(w, hv[b], acc[m][b]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int m = 0; m < SEQ_MAXR; ++m) {
-                const int r = rp + m * SEQ_ROWT;
-                if (r < R) {
-#pragma unroll
-                    for (int b = 0; b < RB; ++b) part[(kg * RB + b) * R + r] = acc[m][b];
-                }
-            }
-        }
+        // (A) recurrent pre-activations, partial over this thread's k range.  The number of W_hh rows per row thread
+        // (1 at H = 128) is a compile-time constant of the specialised loop: with a run-time bound the inner loop
+        // carried a branch per row and k -- 27 % of the kernel's instructions (ncu source view), and the kernel is
+        // issue-bound at four warps per scheduler.
+        if (nrow == 1) seq_partial_product<1>(ws, hc, part, k_begin, k_end, RP, rp, kg, R, rowok);
+        else if (nrow == 2) seq_partial_product<2>(ws, hc, part, k_begin, k_end, RP, rp, kg, R, rowok);
+        else seq_partial_product<3>(ws, hc, part, k_begin, k_end, RP, rp, kg, R, rowok);
         __syncthreads();
         // (B) cell update, one (batch row, unit) per thread.  The new h goes to the NEXT h buffer of all four CTAs
         // first; the tensors saved for the backward pass (gates, c, h_{t-1}, y) are stored to global memory AFTER the
