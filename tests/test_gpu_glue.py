@@ -204,3 +204,66 @@ def test_paired_frames_equal_the_materialised_pairs():
     data.pair_gather(torch.device(DEV), data.PairedFrames(fr.to(DEV), cfg["datasets"]["combinations"], 3, 3), 8, 2, 4,
                      True, flags, 4)
     assert int(flags.item()) == 4
+
+
+def test_cat_and_stack_through_the_strided_copy_equal_torch():
+    """functional.cat_last / stack_mid (dlio_copy2d) against torch.cat / torch.stack, values and gradients; the stack
+    takes the row-strided views the IMU net hands it (out[:, -1, :H] of a [B, T, 2H] tensor)."""
+    from deeplio_b200 import functional as Fn
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(3, 4, 5, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(3, 4, 7, generator=g).to(DEV).requires_grad_(True)
+    w = torch.randn(3, 4, 12, generator=g).to(DEV)
+    (Fn.cat_last(a, b) * w).sum().backward()
+    ga, gb = a.grad.clone(), b.grad.clone()
+    a.grad = b.grad = None
+    ref = torch.cat((a, b), dim=2)
+    assert torch.equal(Fn.cat_last(a, b), ref)
+    (ref * w).sum().backward()
+    assert torch.equal(ga, a.grad) and torch.equal(gb, b.grad)
+    outs = [torch.randn(4, 6, 10, generator=g).to(DEV).requires_grad_(True) for _ in range(3)]
+    feats = [o[:, -1, :5] for o in outs]
+    ws = torch.randn(4, 3, 5, generator=g).to(DEV)
+    got = Fn.stack_mid(feats)
+    assert torch.equal(got, torch.stack(feats, dim=1))
+    (got * ws).sum().backward()
+    grads = [o.grad.clone() for o in outs]
+    for o in outs:
+        o.grad = None
+    (torch.stack([o[:, -1, :5] for o in outs], dim=1) * ws).sum().backward()
+    assert all(torch.equal(x, o.grad) for x, o in zip(grads, outs))
+
+
+def test_pair_gather_fp16_planes_equal_packing_the_materialised_pairs():
+    """dlio_pair_gather(dst_h2): the packed fp16 planes of the first layer, written straight from the un-paired frames,
+    are bit for bit what dlio_pack_f16-style splitting of the materialised pairs gives at the same bound; pads are zero."""
+    from deeplio_b200 import data
+    g = torch.Generator().manual_seed(12)
+    B, F_, H, W = 2, 3, 6, 16
+    frames = (torch.randn(B, F_, 6, H, W, generator=g) * torch.tensor([0.1, 0.1, 0.01, 0.4, 0.4, 0.5]).view(1, 1, 6, 1, 1)).to(DEV)
+    combos = [[0, 1], [1, 2]]
+    pf = data.PairedFrames(frames, combos, 3, 3)
+    h2, bound = data.pair_gather(torch.device(DEV), pf, 8, 2, 4, False, f16=True)
+    assert abs(bound.item() - frames.abs().max().item()) <= 1e-6 * frames.abs().max().item()
+    pairs = pf.materialize().reshape(B * 2, 6, H, W)                      # channels (t0: c0..c2, t1: c0..c2)
+    s = 2.0 ** (14 - torch.tensor(bound.item()).frexp().exponent.item())
+    v = torch.zeros(B * 2, H + 4, W + 8, 8, device=DEV)
+    v[:, 2:2 + H, 4:4 + W, :6] = pairs.permute(0, 2, 3, 1)
+    hi = (v * s).half()
+    lo = ((v * s - hi.float()) * 2048.0).half()
+    assert torch.equal(h2[..., 0, :].view(torch.int16), hi.view(torch.int16))
+    assert torch.equal(h2[..., 1, :].view(torch.int16), lo.view(torch.int16))
+
+
+def test_nvtx_switch_is_harmless():
+    """dlio_set_option("nvtx", 1): ranges are pushed / popped around the launches of an entry point; results unchanged."""
+    from deeplio_b200 import _lib as L
+    x = torch.randn(1000, device=DEV)
+    b0, b1 = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    L.absmax(x.data_ptr(), x.numel(), b0.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    L.set_option(b"nvtx", 1)
+    try:
+        L.absmax(x.data_ptr(), x.numel(), b1.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    finally:
+        L.set_option(b"nvtx", 0)
+    assert b0.item() == b1.item() == x.abs().max().item()
