@@ -218,16 +218,13 @@ def run_b200(args):
     # the bytes: odometry LSTM, fusion, heads, IMU net, fc1, sx / sq) are all-reduced while the encoders' backward runs
     lidar_net = getattr(model, "lidar_feat_net", None)
     split = world > 1 and lidar_net is not None and os.environ.get("DLIO_SPLIT_BWD", "1") != "0"
-    reducer, odom_in_graph = None, False
+    reducer = None
     if world > 1:
         late = [criterion] + ([model.imu_feat_net, lidar_net.fc1] if split else [])
         reducer = parallel.OverlappedGradReducer(model, opt, extra_late=[m for m in late if m is not None])
         if split:
             lidar_net.split_backward = True
             model.on_head_grads_ready = None       # fired explicitly after loss.backward()
-        # DLIO_ODOM_AR_IN_GRAPH=1: capture the all-reduce of the odometry-net gradients (78 % of the bytes) into graph A,
-        # fired by a hook right after the odometry net's backward (OverlappedGradReducer.fire_odom)
-        odom_in_graph = split and os.environ.get("DLIO_ODOM_AR_IN_GRAPH", "0") == "1"
         # measurement only: the step without any gradient exchange (what the max over N unequal GPUs alone costs)
         reducer.disabled = os.environ.get("DLIO_NO_EXCHANGE", "0") == "1"
 
@@ -260,12 +257,6 @@ def run_b200(args):
 
     def graph_step(d):
         # forward + loss + backward: graph launches (two per step when the backward pass is split)
-        if odom_in_graph:
-            # the all-reduce of the odometry net + heads is a node of graph A (under the fusion / IMU backward); the
-            # rest follows after graph B
-            loss = gstep[0](d)
-            opt.step(reducer.finish_rest())
-            return loss
         loss = gstep[0](d, between=reducer.fire if split else None)
         opt.step(reducer.finish() if reducer is not None else 1.0)
         return loss
@@ -322,11 +313,8 @@ def run_b200(args):
             if reducer is not None:
                 model.on_head_grads_ready = None       # under the graph nothing fires from a hook
             E.ENC_STREAMS = enc_streams
-            if odom_in_graph:
-                model.on_odom_grads_ready = reducer.fire_odom
             gstep[0] = GraphedTrainStep(fwd_loss, resident, opt.zero_grad, model=model,
-                                        second_backward=lidar_net.backward_encoders if split else None,
-                                        after_backward=reducer.join_odom if odom_in_graph else None)
+                                        second_backward=lidar_net.backward_encoders if split else None)
             state["resident"] = gstep[0].input_slots[0]     # the graph's own input buffers: resident steps copy nothing
             for _ in range(args.warmup):
                 train_step(state["resident"])
@@ -334,8 +322,7 @@ def run_b200(args):
             ms_total = timed(resident_steps, args.steps)
             launches = _lib.launch_count() - n0 + gstep[0].captured_launches * args.steps
             launch_mode = "cuda-graph (forward + loss + backward: %d library kernels per replay%s; all-reduce and Adam eager)" % (
-                gstep[0].captured_launches, (", split at the encoder features, the odometry-net all-reduce a node of the first graph" if odom_in_graph else
-                                              ", split at the encoder features with the downstream all-reduce under the encoders' backward") if split else "")
+                gstep[0].captured_launches, ", split at the encoder features with the downstream all-reduce under the encoders' backward" if split else "")
         except Exception as e:      # capture is an optimisation: report the eager numbers and say why
             gstep[0] = None
             launch_mode = "eager (CUDA graph capture failed: %s)" % str(e).splitlines()[0][:160]

@@ -35,8 +35,7 @@ class GraphedTrainStep:
     then happens on the current stream.  When the current stream is the default stream, a side stream is used and no
     eager step may have run before."""
 
-    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None, slots=2, second_backward=None,
-                 after_backward=None):
+    def __init__(self, fwd_loss, example, zero_grad, warmup=3, model=None, slots=2, second_backward=None):
         """``model`` (optional): its buffers (BatchNorm running statistics and ``num_batches_tracked``) and the dropout
         call counter are snapshotted before the warm-up passes and restored before the capture, so that building the
         graph leaves the training state exactly as an eager run would find it.
@@ -50,11 +49,7 @@ class GraphedTrainStep:
         loss, ``loss.backward()`` and (B) ``second_backward()`` -- for a model whose autograd graph is cut in two
         (``LidarFeatNet.split_backward``: (B) is the encoders' backward).  ``step(inputs, between=f)`` calls ``f()``
         between the two replays: a data-parallel step launches the all-reduce of the gradients (A) completed there,
-        so that it runs under (B).
-
-        ``after_backward`` (optional callable): called inside graph (A) right after ``loss.backward()`` (and in the
-        warm-up passes): joins work that hooks started on other streams during the backward pass -- the all-reduce of
-        the odometry-net gradients captured INTO the graph (parallel.OverlappedGradReducer.fire_odom / join_odom)."""
+        so that it runs under (B)."""
         dev = next(iter(example.values())).device
         self.input_slots = [{k: torch.empty_like(v) for k, v in example.items()} for _ in range(max(1, slots))]
         for slot in self.input_slots:
@@ -77,8 +72,6 @@ class GraphedTrainStep:
                 for _ in range(warmup):
                     zero_grad()
                     fwd_loss(self.static_in).backward()
-                    if after_backward is not None:
-                        after_backward()
                     if second_backward is not None:
                         second_backward()
                 with torch.no_grad():
@@ -98,8 +91,6 @@ class GraphedTrainStep:
                     zero_grad()
                     loss = fwd_loss(slot)
                     loss.backward()
-                    if after_backward is not None:
-                        after_backward()
                 pool = graph.pool()
                 if second_backward is not None:
                     graph_b = torch.cuda.CUDAGraph()

@@ -30,9 +30,6 @@ class DeepLIO(BaseNet):
         # optional callable, invoked during backward when the gradients of everything downstream of the feature nets
         # (fusion, odometry net, heads) are complete (deeplio_b200.parallel.OverlappedGradReducer)
         self.on_head_grads_ready = None
-        # optional callable, invoked during backward as soon as the gradients of the odometry net and the two heads are
-        # complete (before the fusion / IMU backward): OverlappedGradReducer.fire_odom
-        self.on_odom_grads_ready = None
 
     def initialize(self):
         last = next(n for n in (self.odom_feat_net, self.fusion_net, self.imu_feat_net, self.lidar_feat_net)
@@ -56,17 +53,10 @@ class DeepLIO(BaseNet):
         if self.fusion_net is not None:
             last = self.fusion_net([lidar, imu])
         if self.odom_feat_net is not None:
-            if self.on_odom_grads_ready is not None and last is not None and last.requires_grad:
-                last.register_hook(self._odom_grads_hook)
             last = self.odom_feat_net(last)
         last = Fn.dropout(last, self.p, self.training)
         return (Fn.linear(last, self.fc_pos.weight, self.fc_pos.bias),
                 Fn.linear(last, self.fc_ori.weight, self.fc_ori.bias))
-
-    def _odom_grads_hook(self, grad):
-        if self.on_odom_grads_ready is not None:
-            self.on_odom_grads_ready()
-        return None
 
     def _head_grads_hook(self, grad):
         if self.on_head_grads_ready is not None:

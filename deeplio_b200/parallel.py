@@ -82,20 +82,6 @@ class OverlappedGradReducer:
         self.work, self.fired = [], False
         self.disabled = False         # measurement only (bench.py DLIO_NO_EXCHANGE=1): issue no collective at all
         model.on_head_grads_ready = self._fire
-        # the odometry net + heads alone (78 % of the arena, one contiguous range): their gradients are complete BEFORE
-        # the fusion / IMU backward runs, see fire_odom
-        odom = set()
-        for m in (getattr(model, name, None) for name in ("odom_feat_net", "fc_pos", "fc_ori")):
-            if isinstance(m, torch.nn.Module):
-                odom.update(id(p) for p in m.parameters())
-        self.odom_ranges, self.rest_ranges = [], []
-        for p, a, b in zip(opt.params, opt.offsets, ends):
-            rs = self.odom_ranges if id(p) in odom else self.rest_ranges
-            if rs and rs[-1][1] == a:
-                rs[-1][1] = b
-            else:
-                rs.append([a, b])
-        self.odom_work, self.odom_fired = [], False
 
     def fire(self):
         """The downstream gradients are complete: start reducing them (asynchronously, on NCCL's stream)."""
@@ -106,31 +92,6 @@ class OverlappedGradReducer:
             for a, b in self.late_ranges:
                 self.work.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
         self.fired = True
-
-    def fire_odom(self):
-        """Inside the backward pass (``model.on_odom_grads_ready``), also under CUDA-graph capture: the gradients of the
-        odometry net and the heads are final -- all-reduce them now, so that the exchange runs under the latency-bound
-        fusion / IMU backward (a few SMs busy) and is over before the encoders' persistent convolution kernels start
-        (those lose a whole wave to every SM a collective holds).  ``join_odom()`` must follow in the same graph."""
-        if world_size() > 1 and not self.odom_fired and not self.disabled:
-            for a, b in self.odom_ranges:
-                self.odom_work.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
-        self.odom_fired = True
-
-    def join_odom(self):
-        """Orders the current stream after the collectives of ``fire_odom`` (end of the first graph)."""
-        for w in self.odom_work:
-            w.wait()
-        self.odom_work, self.odom_fired = [], False
-
-    def finish_rest(self):
-        """After the whole backward pass of a step whose first graph CONTAINS ``fire_odom`` / ``join_odom`` (a replay
-        runs no Python hook, so there is no flag to consult): reduces everything else -- encoders, fc1, IMU net,
-        fusion, loss parameters.  Returns the 1/world factor."""
-        if world_size() > 1 and not self.disabled:
-            for a, b in self.rest_ranges:
-                dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM)
-        return 1.0 / world_size()
 
     def finish(self):
         """Call after backward(): reduces what the hook did not, waits for everything.  Returns the 1/world factor

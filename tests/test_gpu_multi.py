@@ -161,80 +161,3 @@ def test_nccl_world2_split_backward_graphs_overlap_the_exchange():
         # 79 % of the benchmark model's
         assert 0.05 < late_frac < 1.0
         assert d_loss < 1e-6 and d_grad < 2e-5, (d_loss, d_grad)
-
-
-def _worker_odom_in_graph(rank, world, port, out):
-    """The all-reduce of the odometry-net gradients captured INTO the first graph (fired by a hook right after the
-    odometry net's backward, joined at the end of the graph), the rest reduced after the second graph."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
-    from deeplio_b200 import data, losses, nets, parallel, pose
-    from deeplio_b200.config import build_config_container
-    from deeplio_b200.graph import GraphedTrainStep
-    from deeplio_b200.optim import FlatAdam
-    from deeplio_b200.workloads import synthetic_gts
-    from oracle import deeplio_oracle as O
-    from oracle.configs import make_cfg
-    parallel.init_from_env()
-    dev = torch.device("cuda", rank)
-    torch.cuda.set_device(rank)
-    with torch.cuda.stream(torch.cuda.Stream(dev)):
-        B, S, H, W, T = 2, 2, 16, 128, 6
-        cfg = make_cfg(lidar="lidar-feat-simple-1", imu="imu-feat-rnn", odom="odom-feat-rnn", seq=S, height=H, width=W,
-                       odom_hidden=64)
-        combos = cfg["datasets"]["combinations"]
-        build_config_container(cfg, argparse.Namespace(device=str(dev), batch_size=B))
-        model = nets.get_model((3, H, W), cfg, str(dev))
-        model.load_state_dict(O.synthetic_state(cfg, seed=3))
-        model.train()
-        crit = losses.get_loss_function(cfg, str(dev))
-        opt = FlatAdam([{"params": model.parameters()}, {"params": crit.parameters()}], lr=1e-3)
-        lidar = model.lidar_feat_net
-        lidar.split_backward = True
-        red = parallel.OverlappedGradReducer(model, opt)
-        model.on_head_grads_ready = None
-        model.on_odom_grads_ready = red.fire_odom
-        g = torch.Generator().manual_seed(50 + rank)
-        d = {"frames": torch.randn(B, S + 1, 6, H, W, generator=g).to(dev), "imus": torch.randn(B, S, T, 6, generator=g).to(dev),
-             "gts": synthetic_gts(B, S + 1, seed=rank).to(dev)}
-
-        def fwd_loss(t):
-            f2f, f2g = data.ground_truth(t["gts"], combos)
-            pos, ori = model([[data.PairedFrames(t["frames"], combos, 0, 3), data.PairedFrames(t["frames"], combos, 3, 3)],
-                              t["imus"]])
-            p, q = pose.se3_to_SE3(pos, ori, check=False)
-            return crit(pos, ori, p[:, 1:3], q[:, 1:3], f2f[:, :, 0:3], f2f[:, :, 3:], f2g[:, 1:3, 0:3], f2g[:, 1:3, 3:7])
-        step = GraphedTrainStep(fwd_loss, d, opt.zero_grad, model=model, second_backward=lidar.backward_encoders,
-                                after_backward=red.join_odom)
-        results = []
-        for k in (0, 1, 0):                           # both slots, and a graph replayed twice
-            loss_g = step(step.input_slots[k])
-            scale = red.finish_rest()
-            torch.cuda.synchronize()
-            results.append((float(loss_g), opt.flat_grad.clone()))
-        # the same step eagerly, unsplit, no hooks, one all-reduce of the whole arena
-        lidar.split_backward = False
-        model.on_odom_grads_ready = None
-        opt.zero_grad()
-        loss_e = fwd_loss(d)
-        loss_e.backward()
-        plain = opt.flat_grad.clone()
-        dist.all_reduce(plain)
-        torch.cuda.synchronize()
-        gmax = plain.abs().max().item()
-        n_odom = sum(b - a for a, b in red.odom_ranges)
-        out[rank] = (scale, n_odom / opt.numel, len(red.odom_ranges),
-                     max(abs(l - float(loss_e)) / abs(float(loss_e)) for l, _ in results),
-                     max((gr - plain).abs().max().item() / gmax for _, gr in results), pose.raise_for_status(dev))
-    dist.destroy_process_group()
-
-
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_nccl_world2_odometry_allreduce_captured_into_the_first_graph():
-    world, port = 2, _free_port()
-    out = mp.Manager().dict()
-    mp.spawn(_worker_odom_in_graph, args=(world, port, out), nprocs=world, join=True)
-    for rank in range(world):
-        scale, odom_frac, n_ranges, d_loss, d_grad, status = out[rank]
-        assert scale == 0.5 and status == 0 and n_ranges == 1 and 0.0 < odom_frac < 1.0
-        assert d_loss < 1e-6 and d_grad < 2e-5, (d_loss, d_grad)

@@ -179,41 +179,3 @@ def test_gloo_world2_reducer_with_extra_late_parameters_fired_explicitly():
         late, base, pending, err, scale = out[rank]
         assert late == base + 4 + 4 + 4          # sx, sq (one padded slot each) and the 3-element parameter
         assert pending >= 1 and err < 1e-6 and scale == 0.5
-
-
-def _odom_ranges_worker(rank, world, port, out):
-    """fire_odom / join_odom / finish_rest on the CPU: the odometry net + heads as one early exchange, everything else
-    afterwards; together the same sums as one all-reduce of the arena."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
-    parallel.init_from_env(backend="gloo")
-    torch.manual_seed(3)
-    model = _ToyModel()
-    opt = _FlatOpt(model.parameters())
-    red = parallel.OverlappedGradReducer(model, opt)
-    model.on_head_grads_ready = None
-    torch.manual_seed(10 + rank)
-    pos, ori = model(torch.randn(4, 6))
-    (pos.pow(2).sum() + ori.sum()).backward()
-    local = opt.flat_grad.clone()
-    red.fire_odom()
-    pending = len(red.odom_work)
-    red.join_odom()
-    scale = red.finish_rest()
-    gathered = [torch.zeros_like(local) for _ in range(world)]
-    dist.all_gather(gathered, local)
-    n_odom = sum(b - a for a, b in red.odom_ranges)
-    n_rest = sum(b - a for a, b in red.rest_ranges)
-    out[rank] = (pending, n_odom, n_rest, opt.numel, float((opt.flat_grad - sum(gathered)).abs().max()), scale,
-                 red.odom_fired)
-    dist.destroy_process_group()
-
-
-def test_gloo_world2_odometry_ranges_first_then_the_rest():
-    world, port = 2, _free_port()
-    out = mp.Manager().dict()
-    mp.spawn(_odom_ranges_worker, args=(world, port, out), nprocs=world, join=True)
-    for rank in range(world):
-        pending, n_odom, n_rest, numel, err, scale, fired_after = out[rank]
-        assert pending == 1 and n_odom > 0 and n_rest > 0 and n_odom + n_rest == numel
-        assert err < 1e-6 and scale == 0.5 and not fired_after
