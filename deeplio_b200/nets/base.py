@@ -9,7 +9,6 @@ created under the reference's attribute names, so ``state_dict()`` keys, shapes,
 ``.to()``, ``requires_grad`` freezing and optimizer parameter order match the reference.  Those objects
 are parameter containers only: their ``forward`` is never called -- compute goes through the C ABI.
 """
-import torch
 from torch import nn
 
 

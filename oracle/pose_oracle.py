@@ -17,7 +17,6 @@ What is restated, and how it is pinned:
   covers it and the library itself cannot be run here; when the reference functions above are executed for the
   goldens, THIS class is what they call.  Its call sites: trainer.py:339,349; misc.py:104,119.
 """
-import math
 
 import torch
 

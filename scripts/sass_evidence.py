@@ -6,7 +6,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "deeplio_b200", "libdeeplio_b200.so")

@@ -8,7 +8,7 @@ import torch
 
 from oracle import deeplio_oracle as O
 from oracle.configs import make_cfg
-from tests.helpers import count_relu_flips, diag, forced_oracle_step, grad_rows, oracle_train_step, rel_err
+from tests.helpers import count_relu_flips, diag, forced_oracle_step, grad_rows, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
